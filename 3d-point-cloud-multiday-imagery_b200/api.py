@@ -1,0 +1,246 @@
+"""Public Python API: the drop-in for the reference's multi-day point-cloud fusion step.
+
+The reference has no such routine of its own; the signature below is
+assembled from the three anchors it does have:
+
+* the plugin contract ``SatellitePlugin.run(...) -> List[Layer]`` (``interface.py:10-47``,
+  ``Layer = (ndarray, params, type)`` at ``interface.py:5-7``),
+* the unprojection tail of ``HeightMapExtractor.run``
+  (``members/rafael/disparity/plugin.py:147-233``), whose Points layer this module
+  reproduces (napari (z, y, x) column order, ``plugin.py:192``; layer params ``:220-233``),
+* scikit-learn's ``KMeans`` call convention as the reference uses it
+  (``members/jasraj/land_use_classification/core.py:227-228``): ``n_clusters``, ``init``,
+  ``n_init``, ``max_iter=300``, ``tol=1e-4``, ``random_state``; results named like
+  ``labels_ / cluster_centers_ / inertia_ / n_iter_``.
+
+Everything numeric happens in libmdkm.so (sm_100a CUDA kernels); this file only validates
+arguments, draws the host-side random numbers scikit-learn would draw, and packs results.
+"""
+from __future__ import annotations
+
+import traceback
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Literal, Optional, Tuple
+
+import numpy as np
+
+from .engine import Engine
+
+LayerType = Literal["image", "labels", "points", "shapes"]
+Layer = Tuple[np.ndarray, Dict[str, Any], LayerType]  # interface.py:5-7
+
+MAX_ABS_HEIGHT = 144.0  # MAX_DISP / 2 (constants.py:54, plugin.py:151)
+
+
+@dataclass
+class FusionResult:
+    """What the fused k-means returns (names follow scikit-learn's fitted attributes)."""
+
+    labels: np.ndarray           # int32 [N], np.where order per day, days concatenated
+    centroids: np.ndarray        # float64 [K,3] as (x, y, z)
+    fused_cloud: Optional[np.ndarray]  # float32 [N,3] in napari (z, y, x) order, or None
+    n_iter: int
+    inertia: float
+    n_points: int
+    n_refined: int = 0           # point-iterations decided by the FP64 refine (near-ties)
+    n_relocations: int = 0
+    height_norm: Optional[np.ndarray] = None  # plugin.py:184-188 'height' property, if requested
+    extra: Dict[str, Any] = field(default_factory=dict)
+
+    # scikit-learn style aliases
+    @property
+    def labels_(self):
+        return self.labels
+
+    @property
+    def cluster_centers_(self):
+        return self.centroids
+
+    @property
+    def inertia_(self):
+        return self.inertia
+
+    @property
+    def n_iter_(self):
+        return self.n_iter
+
+
+def _check_random_state(seed):
+    if seed is None or isinstance(seed, (int, np.integer)):
+        return np.random.RandomState(seed)
+    if isinstance(seed, np.random.RandomState):
+        return seed
+    raise ValueError("random_state must be None, an int or a numpy RandomState")
+
+
+def _is_same_clustering(l1, l2, k) -> bool:
+    """sklearn/cluster/_k_means_common.pyx:314-330 (labels equal up to a permutation)."""
+    mapping = np.full(k, -1, dtype=np.int64)
+    first = np.unique(l1, return_index=True)
+    for lab, i in zip(*first):
+        mapping[lab] = l2[i]
+    return bool(np.array_equal(mapping[l1], l2))
+
+
+def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True):
+    """KMeans.fit driver (sklearn/_kmeans.py:1436-1563): init, n_init restarts, best inertia."""
+    n = eng.n_points
+    k = int(n_clusters)
+    if k < 1:
+        raise ValueError("n_clusters must be >= 1")
+    if n < k:
+        raise ValueError(f"n_samples={n} should be >= n_clusters={k}.")
+    rs = _check_random_state(random_state)
+    init_is_array = not isinstance(init, str)
+    if init_is_array:
+        init_arr = np.ascontiguousarray(init, dtype=np.float64)
+        if init_arr.shape != (k, 3):
+            raise ValueError(f"The shape of the initial centers {init_arr.shape} does not match (n_clusters, 3)")
+        n_init = 1  # sklearn/_kmeans.py:905-913: explicit init => single run
+    elif init not in ("k-means++", "random"):
+        raise ValueError("init must be 'k-means++', 'random' or an array of shape (n_clusters, 3)")
+    if n_init == "auto":
+        n_init = 1 if init == "k-means++" else 10  # sklearn/_kmeans.py:896-903
+    best = None
+    for _ in range(int(n_init)):
+        if init_is_array:
+            centers0 = init_arr
+        elif init == "random":
+            seeds = rs.choice(n, size=k, replace=False)  # sklearn/_kmeans.py:1014-1021
+            centers0 = eng.gather_points(seeds).astype(np.float64)
+        else:
+            centers0, _ = eng.kmeans_plusplus(k, rs)
+        r = eng.fit(centers0, max_iter=max_iter, tol=tol, want_labels=want_labels)
+        if best is None or (
+            r["inertia"] < best["inertia"]
+            and not (want_labels and _is_same_clustering(r["labels"], best["labels"], k))
+        ):
+            best = r
+    return best
+
+
+def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k-means++", n_init=1,
+                         max_iter=300, tol=1e-4, random_state=None, max_abs_height=MAX_ABS_HEIGHT,
+                         detrend=False, disparity_scale=None, ground_level=False, return_cloud=True,
+                         device=0, engine: Optional[Engine] = None) -> FusionResult:
+    """Unproject a multi-day height-map stack into one XYZ cloud and cluster it (Lloyd).
+
+    height_maps : float32 ``[D,H,W]`` (NaN = nodata), numpy or torch (CPU or CUDA); or int16
+        OpenCV fixed-point disparity with ``disparity_scale=-1/16`` (plugin.py:147-148).
+    valid_masks : optional bool/uint8 ``[D,H,W]`` (``final_defined`` of disparity.py:203-204).
+    n_clusters, init, n_init, max_iter, tol, random_state : as sklearn.cluster.KMeans.
+    detrend : apply the per-day plane fit of plugin.py:161-171 to z before clustering.
+    ground_level : additionally shift z by the 2nd percentile and return the 'height'
+        colour property of plugin.py:181-192 (after clustering; does not change labels).
+    Returns a FusionResult; ``fused_cloud`` is float32 ``[N,3]`` in napari (z,y,x) order.
+    """
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        n = eng.unproject(height_maps, valid_masks, max_abs_height=max_abs_height, detrend=detrend,
+                          disparity_scale=disparity_scale)
+        r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
+                        tol=tol, random_state=random_state)
+        hn = None
+        extra = {}
+        if ground_level:
+            lo, hi, hn = eng.ground_level(True)
+            extra["h_min"], extra["h_max"] = lo, hi
+            r["centers"] = r["centers"].copy()
+            r["centers"][:, 2] -= lo
+        cloud = eng.get_cloud(napari_order=True) if return_cloud else None
+        return FusionResult(labels=r["labels"], centroids=r["centers"], fused_cloud=cloud,
+                            n_iter=r["n_iter"], inertia=r["inertia"], n_points=n,
+                            n_refined=r["n_refined"], n_relocations=r["n_relocations"],
+                            height_norm=hn, extra=extra)
+    finally:
+        if own:
+            eng.close()
+
+
+def kmeans_points(points, *, n_clusters=8, init="k-means++", n_init=1, max_iter=300, tol=1e-4,
+                  random_state=None, return_cloud=False, device=0,
+                  engine: Optional[Engine] = None) -> FusionResult:
+    """Lloyd k-means of an already unprojected ``[N,3]`` (x,y,z) float32 cloud."""
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        n = eng.set_points(points)
+        r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
+                        tol=tol, random_state=random_state)
+        cloud = eng.get_cloud(napari_order=True) if return_cloud else None
+        return FusionResult(labels=r["labels"], centroids=r["centers"], fused_cloud=cloud,
+                            n_iter=r["n_iter"], inertia=r["inertia"], n_points=n,
+                            n_refined=r["n_refined"], n_relocations=r["n_relocations"])
+    finally:
+        if own:
+            eng.close()
+
+
+def to_layers(result: FusionResult, prefix: str = "Multi-day") -> List[Layer]:
+    """napari layers for a FusionResult, mirroring plugin.py:220-233.
+
+    One Points layer with the fused cloud coloured by cluster (or by the reference's
+    'height' property when it was computed) and one with the K centroids.
+    """
+    if result.fused_cloud is None:
+        raise ValueError("result has no fused_cloud (return_cloud=False)")
+    props: Dict[str, Any] = {"cluster": result.labels}
+    face = "cluster"
+    if result.height_norm is not None:
+        props["height"] = result.height_norm
+    layers: List[Layer] = [(
+        result.fused_cloud,
+        {
+            "name": f"{prefix} 3D Point Cloud",
+            "size": 2,
+            "properties": props,
+            "scale": (1, 1, 1),
+            "opacity": 0.8,
+            "face_colormap": "turbo",
+            "face_color": face,
+        },
+        "points",
+    )]
+    c = result.centroids
+    layers.append((
+        np.stack([c[:, 2], c[:, 1], c[:, 0]], axis=1),
+        {"name": f"{prefix} Cluster Centroids", "size": 12, "scale": (1, 1, 1),
+         "properties": {"cluster": np.arange(c.shape[0])}, "face_color": "cluster",
+         "face_colormap": "turbo", "symbol": "cross"},
+        "points",
+    ))
+    return layers
+
+
+class MultiDayFusionPlugin:
+    """``SatellitePlugin``-shaped wrapper (interface.py:10-47) around the fused path.
+
+    ``run`` never raises: like ``HeightMapExtractor.run`` (plugin.py:236-241) it returns a
+    single 100x100 image layer named ``"Error: ..."`` on failure, so the napari worker thread
+    (widget.py:116-147) sees the same convention.
+    """
+
+    requires_image = False  # plugin.py:30
+
+    def __init__(self, n_clusters=8, device=0, **kmeans_kwargs):
+        self.n_clusters = n_clusters
+        self.device = device
+        self.kmeans_kwargs = kmeans_kwargs
+
+    @property
+    def name(self) -> str:
+        return "Multi-day 3D Point Cloud (B200 k-means fusion)"
+
+    @property
+    def requires_viewer(self) -> bool:
+        return False
+
+    def run(self, image, viewer=None, valid_masks=None) -> List[Layer]:
+        try:
+            res = fuse_multiday_kmeans(image, valid_masks, n_clusters=self.n_clusters, device=self.device,
+                                       **self.kmeans_kwargs)
+            return to_layers(res)
+        except Exception as e:  # noqa: BLE001 - reference convention, plugin.py:236-241
+            traceback.print_exc()
+            return [(np.ones((100, 100)), {"name": f"Error: {str(e)}"}, "image")]

@@ -1,0 +1,58 @@
+// Shared device/host definitions for libmdkm (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmdkm is written for sm_100a (B200); compile with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+namespace mdkm {
+
+constexpr int kThreads = 256;          // threads per CTA of the streaming kernels
+constexpr int kMaxK = 4096;            // largest supported cluster count
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float -> integer by mantissa alignment
+constexpr uint32_t kMagicBits = 0x4B400000u;
+constexpr int kQuantBits = 22;         // |quantised coordinate| < 2^22
+
+// Device-resident control block.  Written by the update / finalize kernels, read by every
+// kernel of the Lloyd loop (early exit once `done`), mirrored to pinned host memory between
+// batches of iterations only.
+struct DevStatus {
+  int done;       // 1: converged or max_iter reached
+  int strict;     // 1: exit because no label changed (sklearn/_kmeans.py:721-726)
+  int paused;     // 1: an empty cluster needs relocation (host-sequenced rare path)
+  int iter;       // Lloyd iterations completed
+  int max_iter;
+  int n_empty;    // empty clusters found by the last update
+  int k;
+  int first;      // 1 until the first step has run (labels_old = -1 in sklearn)
+  unsigned long long n_changed;  // labels changed in the last step (global after allreduce)
+  unsigned long long n_refined;  // point-iterations re-decided in float64 (this rank)
+  unsigned long long n_relocated;
+  double shift2;   // sum_j ||c_new - c_old||^2 of the last update
+  double tol;      // scaled tolerance  mean(var(X)) * tol
+  double inertia;  // written by the finalize pass
+  float thresh;    // 2 * FP32 error bound of the fast distances for the current table
+  float pad0;
+};
+
+// Frame of the resident cloud: x' = x - origin (exact for pixel grids), fixed-point scale.
+struct Frame {
+  double origin[3];
+  double scale[3];     // power of two; q = rint((x - origin) * scale), |q| < 2^22
+  double halfrange[3]; // max |x - origin| over ALL ranks (upper bound)
+};
+
+struct FrameF {
+  float ox, oy, oz;    // origin as float (exactly representable)
+  float sx, sy, sz;    // fixed-point scales (powers of two)
+};
+
+// One centroid table in global memory: [Kpad] float4 fast rows, then [Kpad] double4 exact rows.
+//   fast row  = (-2c'x, -2c'y, -2c'z, ||c'||^2) rounded to FP32 ; padding rows = (0,0,0,+inf)
+//   exact row = ( c'x,   c'y,   c'z,  ||c'||^2) in FP64, c' = c - origin
+__host__ __device__ inline int pad_k(int k) { return (k + 7) & ~7; }
+__host__ __device__ inline size_t table_bytes(int kpad) { return (size_t)kpad * (16 + 32); }
+
+}  // namespace mdkm

@@ -1,0 +1,909 @@
+// libmdkm.so -- host side of the C ABI declared in include/mdkm.h.
+// One handle = one B200 = one rank.  All arithmetic runs in the CUDA kernels of lloyd.cuh /
+// unproject.cuh / extras.cuh; this file only allocates, sequences launches and moves bytes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mdkm.h"
+#include "common.cuh"
+#include "extras.cuh"
+#include "extras_impl.cuh"
+#include "lloyd.cuh"
+#include "nccl_shim.h"
+#include "unproject.cuh"
+
+using namespace mdkm;
+
+namespace {
+
+constexpr int kStepG = 2;                          // float4 groups per thread in the step kernel
+constexpr long long kTile = kThreads * 4 * kStepG;  // points per CTA tile (2048)
+constexpr int kBatch = 10;                          // Lloyd iterations enqueued between status polls
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+}  // namespace
+
+struct mdkm_handle {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // resident cloud (SoA, capacity padded to the tile)
+  DevBuf<float> x, y, z;
+  long long n = 0;        // points on this rank
+  long long n_total = 0;  // points over all ranks
+  bool have_points = false;
+  bool frame_ok = false;
+  Frame fr{};
+  FrameF ff{};
+  double mean[3] = {0, 0, 0};
+  bool mean_ok = false;
+
+  // k-means state
+  DevBuf<unsigned char> labels;  // uint8 / uint16 per point
+  DevBuf<unsigned char> table;
+  DevBuf<unsigned long long> acc;
+  DevBuf<int> labels32;
+  DevBuf<double> dscratch;    // init / centroid read-back / sums
+  DevBuf<double> partials;    // inertia / moments partials
+  DevBuf<unsigned int> uscratch;  // tickets, minmax
+  DevBuf<unsigned long long> reloc;  // relocation scratch
+  DevStatus* d_status = nullptr;
+  DevStatus* h_status = nullptr;  // pinned, 2 slots
+  cudaEvent_t batch_ev[2] = {nullptr, nullptr};
+  int last_k = 0;
+  long long stat_refined = 0, stat_reloc = 0;
+  double stat_tol = 0.0;
+
+  // unprojection scratch
+  DevBuf<unsigned int> chunk_counts;
+  DevBuf<long long> chunk_offsets;
+  DevBuf<unsigned char> staging;  // host inputs staged here
+  DevBuf<double> planes;
+  long long* h_total = nullptr;  // pinned
+
+  // communicator
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+
+  // profiling
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_used = 0;
+  double prof_ms = 0.0;
+  int prof_steps = 0;
+  int launches = 0;
+};
+
+namespace {
+
+int fail(mdkm_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? MDKM_ERR_OOM : MDKM_ERR_CUDA,         \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define NC(call)                                                                               \
+  do {                                                                                         \
+    ncclResult_t r__ = (call);                                                                 \
+    if (r__ != 0)                                                                              \
+      return fail(h, MDKM_ERR_NCCL, "%s failed: %s", #call,                                    \
+                  nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "nccl error");  \
+  } while (0)
+
+#define OK(call)              \
+  do {                        \
+    int rc__ = (call);        \
+    if (rc__ != MDKM_OK) return rc__; \
+  } while (0)
+
+template <typename T>
+int ensure(mdkm_handle* h, DevBuf<T>& b, size_t elems) {
+  if (b.cap >= elems && b.p) return MDKM_OK;
+  if (b.p) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  if (elems == 0) elems = 1;
+  CU(cudaMalloc(&b.p, elems * sizeof(T)));
+  b.cap = elems;
+  return MDKM_OK;
+}
+
+template <typename T>
+void release(DevBuf<T>& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+int grid_for(const mdkm_handle* h, long long work_items, int per_sm) {
+  long long g = std::min<long long>(work_items, (long long)h->sm_count * per_sm);
+  return (int)std::max<long long>(1, g);
+}
+
+int alloc_points(mdkm_handle* h, long long n) {
+  const size_t cap = (size_t)round_up(std::max<long long>(n, 1), kTile);
+  OK(ensure(h, h->x, cap));
+  OK(ensure(h, h->y, cap));
+  OK(ensure(h, h->z, cap));
+  return MDKM_OK;
+}
+
+// zero the padding behind the last point so the tail tile reads finite values
+int zero_tail(mdkm_handle* h) {
+  const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
+  const size_t tail = (size_t)(cap - h->n);
+  if (tail) {
+    CU(cudaMemsetAsync(h->x.p + h->n, 0, tail * 4, h->stream));
+    CU(cudaMemsetAsync(h->y.p + h->n, 0, tail * 4, h->stream));
+    CU(cudaMemsetAsync(h->z.p + h->n, 0, tail * 4, h->stream));
+  }
+  return MDKM_OK;
+}
+
+int allreduce(mdkm_handle* h, void* buf, size_t count, int dtype, int op) {
+  if (h->n_ranks <= 1) return MDKM_OK;
+  NC(nccl_api().AllReduce(buf, buf, count, dtype, op, h->comm, h->stream));
+  return MDKM_OK;
+}
+
+// Frame of the resident cloud: origin / fixed-point scale / half-range from the global
+// per-dimension min and max.
+int compute_frame(mdkm_handle* h) {
+  OK(ensure(h, h->uscratch, 16));
+  OK(ensure(h, h->dscratch, 64));
+  unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  if (h->n > 0) {
+    minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, 0, h->stream>>>(
+        h->x.p, h->y.p, h->z.p, h->n, h->uscratch.p + 4);
+    ++h->launches;
+    CU(cudaGetLastError());
+  }
+  unsigned int ord[6];
+  CU(cudaMemcpyAsync(ord, h->uscratch.p + 4, sizeof(ord), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float mm[6];
+  for (int i = 0; i < 6; ++i) mm[i] = ord2f(ord[i]);
+  long long ntot = h->n;
+  if (h->n_ranks > 1) {
+    // exchange min / max / count (tiny, once per cloud)
+    float* dmm = reinterpret_cast<float*>(h->dscratch.p);
+    long long* dn = reinterpret_cast<long long*>(h->dscratch.p + 8);
+    CU(cudaMemcpyAsync(dmm, mm, sizeof(mm), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dn, &ntot, 8, cudaMemcpyHostToDevice, h->stream));
+    OK(allreduce(h, dmm, 3, kNcclFloat32, kNcclMin));
+    OK(allreduce(h, dmm + 3, 3, kNcclFloat32, kNcclMax));
+    OK(allreduce(h, dn, 1, kNcclInt64, kNcclSum));
+    CU(cudaMemcpyAsync(mm, dmm, sizeof(mm), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&ntot, dn, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->n_total = ntot;
+  for (int d = 0; d < 3; ++d) {
+    double lo = mm[d], hi = mm[3 + d];
+    if (!(lo <= hi)) { lo = 0.0; hi = 0.0; }  // empty cloud
+    if (!isfinite(lo) || !isfinite(hi)) return fail(h, MDKM_ERR_INVALID, "points contain non-finite coordinates");
+    // origin: midrange rounded to an integer (exactly representable in FP32, makes pixel
+    // coordinates exact); kept at 0 when that would not shorten the range noticeably.
+    double mid = 0.5 * (lo + hi);
+    double half = 0.5 * (hi - lo);
+    double o = (fabs(mid) > 0.25 * half) ? nearbyint(mid) : 0.0;
+    o = (double)(float)o;
+    double hr = std::max(fabs(lo - o), fabs(hi - o));
+    hr = hr * (1.0 + 1e-6) + 1e-30;  // FP32 rounding of x - o
+    int e = (int)floor(log2((double)((1 << kQuantBits) - 2) / hr));
+    e = std::max(-100, std::min(100, e));
+    h->fr.origin[d] = o;
+    h->fr.scale[d] = ldexp(1.0, e);
+    h->fr.halfrange[d] = hr;
+  }
+  h->ff.ox = (float)h->fr.origin[0]; h->ff.oy = (float)h->fr.origin[1]; h->ff.oz = (float)h->fr.origin[2];
+  h->ff.sx = (float)h->fr.scale[0]; h->ff.sy = (float)h->fr.scale[1]; h->ff.sz = (float)h->fr.scale[2];
+  h->frame_ok = true;
+  h->mean_ok = false;
+  return MDKM_OK;
+}
+
+// mean and mean(var) of the global cloud (sklearn/_kmeans.py:285-293 and :1487-1490)
+int compute_moments(mdkm_handle* h, double* mean_var_out) {
+  const int g = grid_for(h, (h->n + 1023) / 1024, 4);
+  OK(ensure(h, h->partials, (size_t)std::max(g, h->sm_count * 8) * 8 + 16));
+  OK(ensure(h, h->uscratch, 16));
+  OK(ensure(h, h->dscratch, 64));
+  CU(cudaMemsetAsync(h->uscratch.p, 0, 4, h->stream));
+  CU(cudaMemsetAsync(h->dscratch.p, 0, 8 * sizeof(double), h->stream));
+  if (h->n > 0) {
+    moments_kernel<<<g, kThreads, 0, h->stream>>>(h->x.p, h->y.p, h->z.p, h->n, h->ff, h->partials.p,
+                                                  h->uscratch.p, h->dscratch.p);
+    ++h->launches;
+    CU(cudaGetLastError());
+  }
+  OK(allreduce(h, h->dscratch.p, 6, kNcclFloat64, kNcclSum));
+  double m[6];
+  CU(cudaMemcpyAsync(m, h->dscratch.p, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const double N = (double)std::max<long long>(h->n_total, 1);
+  double mv = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    const double mu = m[d] / N;
+    h->mean[d] = mu + h->fr.origin[d];
+    mv += m[3 + d] / N - mu * mu;
+  }
+  h->mean_ok = true;
+  if (mean_var_out) *mean_var_out = mv / 3.0;
+  return MDKM_OK;
+}
+
+template <typename LabT>
+int launch_step_t(mdkm_handle* h, const StepParams& sp, size_t smem, int grid) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT, kStepG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            200 * 1024));
+    attr_done = true;
+  }
+  lloyd_step_kernel<LabT, kStepG><<<grid, kThreads, smem, h->stream>>>(sp);
+  ++h->launches;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+template <typename LabT>
+int launch_final_t(mdkm_handle* h, const FinalParams& fp, size_t smem, int grid) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(lloyd_final_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  lloyd_final_kernel<LabT><<<grid, kThreads, smem, h->stream>>>(fp);
+  ++h->launches;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+struct KmBuffers {
+  int k, kpad;
+  size_t step_smem, final_smem;
+  int step_grid, final_grid;
+  bool wide;  // uint16 labels
+};
+
+int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
+  if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident: call mdkm_unproject or mdkm_set_points first");
+  if (k < 1 || k > kMaxK) return fail(h, MDKM_ERR_INVALID, "k must be in [1, %d]", kMaxK);
+  if (!h->frame_ok) OK(compute_frame(h));
+  if ((long long)k > h->n_total) return fail(h, MDKM_ERR_INVALID, "n_samples=%lld should be >= n_clusters=%d", h->n_total, k);
+  kb.k = k;
+  kb.kpad = pad_k(k);
+  kb.wide = k > 256;
+  kb.step_smem = (size_t)kb.kpad * (16 + 32);
+  kb.final_smem = (size_t)kb.kpad * 16;
+  const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
+  OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
+  OK(ensure(h, h->table, table_bytes(kb.kpad)));
+  OK(ensure(h, h->acc, (size_t)kb.kpad * 4 + 8));
+  OK(ensure(h, h->dscratch, (size_t)std::max(64, k * 4 + 16)));
+  OK(ensure(h, h->uscratch, 16));
+  const long long tiles = (h->n + kTile - 1) / kTile;
+  const int per_sm = kb.step_smem > 100 * 1024 ? 1 : 2;
+  kb.step_grid = grid_for(h, tiles, per_sm);
+  const long long ftiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);
+  kb.final_grid = grid_for(h, ftiles, 4);
+  OK(ensure(h, h->partials, (size_t)std::max(kb.final_grid, h->sm_count * 8) * 8 + 16));
+  if (!h->d_status) {
+    CU(cudaMalloc(&h->d_status, sizeof(DevStatus)));
+    CU(cudaMallocHost(&h->h_status, 2 * sizeof(DevStatus)));
+    CU(cudaEventCreateWithFlags(&h->batch_ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->batch_ev[1], cudaEventDisableTiming));
+  }
+  h->last_k = k;
+  return MDKM_OK;
+}
+
+int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
+  StepParams sp{};
+  sp.x = h->x.p; sp.y = h->y.p; sp.z = h->z.p; sp.n = h->n;
+  sp.labels = h->labels.p;
+  sp.table = h->table.p;
+  sp.acc = h->acc.p;
+  sp.st = h->d_status;
+  sp.f = h->ff;
+  sp.k = kb.k; sp.kpad = kb.kpad;
+  sp.ignore_status = ignore_status;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->prof) {
+    while ((int)h->prof_ev.size() < h->prof_used + 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      h->prof_ev.push_back(e);
+    }
+    e0 = h->prof_ev[h->prof_used++];
+    e1 = h->prof_ev[h->prof_used++];
+    CU(cudaEventRecord(e0, h->stream));
+  }
+  if (kb.wide) OK(launch_step_t<unsigned short>(h, sp, kb.step_smem, kb.step_grid));
+  else OK(launch_step_t<unsigned char>(h, sp, kb.step_smem, kb.step_grid));
+  if (h->prof) CU(cudaEventRecord(e1, h->stream));
+  return MDKM_OK;
+}
+
+int launch_update(mdkm_handle* h, const KmBuffers& kb, int allow_pause, int ignore_status) {
+  UpdateParams up{};
+  up.acc = h->acc.p;
+  up.table = h->table.p;
+  up.st = h->d_status;
+  up.fr = h->fr;
+  for (int d = 0; d < 3; ++d) up.mean[d] = h->mean_ok ? h->mean[d] : h->fr.origin[d];
+  up.k = kb.k; up.kpad = kb.kpad;
+  up.allow_pause = allow_pause;
+  up.ignore_status = ignore_status;
+  lloyd_update_kernel<<<1, kThreads, 0, h->stream>>>(up);
+  ++h->launches;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+int upload_table(mdkm_handle* h, const KmBuffers& kb, const double* centers_host) {
+  CU(cudaMemcpyAsync(h->dscratch.p, centers_host, (size_t)kb.k * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                     h->stream));
+  InitTableParams ip{};
+  ip.centers = h->dscratch.p;
+  ip.table = h->table.p;
+  ip.st = h->d_status;
+  ip.fr = h->fr;
+  ip.k = kb.k; ip.kpad = kb.kpad;
+  init_table_kernel<<<1, kThreads, 0, h->stream>>>(ip);
+  ++h->launches;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+int collect_profile(mdkm_handle* h) {
+  if (!h->prof) return MDKM_OK;
+  for (int i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+    h->prof_ms += ms;
+    ++h->prof_steps;
+  }
+  h->prof_used = 0;
+  return MDKM_OK;
+}
+
+// Empty-cluster relocation (sklearn/_k_means_common.pyx:167-211), sequenced from the host
+// while the Lloyd loop is paused.  All arithmetic on the device (extras.cuh).
+int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
+  // scratch: [0] best distance bits, [1] best global index, [2..5] payload (qx,qy,qz,old label),
+  //          [6] taken count, [8 .. 8+kMaxK) taken global indices
+  OK(ensure(h, h->reloc, 8 + 2 * (size_t)kMaxK));
+  CU(cudaMemsetAsync(h->reloc.p, 0, (8 + 2 * (size_t)kMaxK) * 8, h->stream));
+  long long rank_offset = 0;
+  if (h->n_ranks > 1) {
+    // global index of this rank's first point: exclusive prefix of the shard sizes
+    std::vector<long long> sizes(h->n_ranks, 0);
+    sizes[h->rank] = h->n;
+    long long* d = reinterpret_cast<long long*>(h->dscratch.p);
+    CU(cudaMemcpyAsync(d, sizes.data(), sizeof(long long) * h->n_ranks, cudaMemcpyHostToDevice, h->stream));
+    OK(allreduce(h, d, h->n_ranks, kNcclInt64, kNcclSum));
+    CU(cudaMemcpyAsync(sizes.data(), d, sizeof(long long) * h->n_ranks, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->rank; ++r) rank_offset += sizes[r];
+  }
+  RelocParams rp{};
+  rp.x = h->x.p; rp.y = h->y.p; rp.z = h->z.p; rp.n = h->n;
+  rp.labels = h->labels.p; rp.wide = kb.wide ? 1 : 0;
+  rp.table = h->table.p; rp.kpad = kb.kpad; rp.k = kb.k;
+  rp.f = h->ff;
+  rp.scratch = h->reloc.p;
+  rp.acc = h->acc.p;
+  rp.rank_offset = rank_offset;
+  const int g = grid_for(h, (h->n + 1023) / 1024, 4);
+  for (int e = 0; e < n_empty; ++e) {
+    rp.round = e;
+    CU(cudaMemsetAsync(h->reloc.p, 0, 6 * 8, h->stream));
+    CU(cudaMemsetAsync(h->reloc.p + 1, 0xff, 8, h->stream));
+    reloc_maxdist_kernel<<<g, kThreads, 0, h->stream>>>(rp);
+    ++h->launches;
+    OK(allreduce(h, h->reloc.p, 1, kNcclUint64, kNcclMax));
+    reloc_argidx_kernel<<<g, kThreads, 0, h->stream>>>(rp);
+    ++h->launches;
+    OK(allreduce(h, h->reloc.p + 1, 1, kNcclUint64, kNcclMin));
+    reloc_payload_kernel<<<1, 32, 0, h->stream>>>(rp);
+    ++h->launches;
+    OK(allreduce(h, h->reloc.p + 2, 4, kNcclUint64, kNcclSum));
+    reloc_apply_kernel<<<1, 32, 0, h->stream>>>(rp, h->d_status);
+    ++h->launches;
+    CU(cudaGetLastError());
+  }
+  return MDKM_OK;
+}
+
+int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_assign) {
+  CU(cudaMemsetAsync(h->uscratch.p, 0, 4, h->stream));
+  FinalParams fp{};
+  fp.x = h->x.p; fp.y = h->y.p; fp.z = h->z.p; fp.n = h->n;
+  fp.labels = h->labels.p;
+  fp.labels_out = labels_dev;
+  fp.table = h->table.p;
+  fp.partials = h->partials.p;
+  fp.ticket = h->uscratch.p;
+  fp.st = h->d_status;
+  fp.f = h->ff;
+  fp.k = kb.k; fp.kpad = kb.kpad;
+  fp.force_assign = force_assign;
+  if (kb.wide) OK(launch_final_t<unsigned short>(h, fp, kb.final_smem, kb.final_grid));
+  else OK(launch_final_t<unsigned char>(h, fp, kb.final_smem, kb.final_grid));
+  return MDKM_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* mdkm_version(void) { return "mdkm 0.1 sm_100a"; }
+
+int mdkm_create(mdkm_handle** out, int device, void* cuda_stream) {
+  if (!out) return MDKM_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return MDKM_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return MDKM_ERR_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MDKM_ERR_CUDA;
+  if (prop.major != 10) return MDKM_ERR_NO_DEVICE;  // kernels are sm_100a only; no fallback
+  if (cudaSetDevice(device) != cudaSuccess) return MDKM_ERR_CUDA;
+  mdkm_handle* h = new mdkm_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  if (cuda_stream) {
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete h;
+      return MDKM_ERR_CUDA;
+    }
+    h->own_stream = true;
+  }
+  if (cudaMallocHost(&h->h_total, 64) != cudaSuccess) {
+    delete h;
+    return MDKM_ERR_CUDA;
+  }
+  *out = h;
+  return MDKM_OK;
+}
+
+void mdkm_destroy(mdkm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
+  release(h->x); release(h->y); release(h->z);
+  release(h->labels); release(h->table); release(h->acc); release(h->labels32);
+  release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
+  release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
+  if (h->d_status) cudaFree(h->d_status);
+  if (h->h_status) cudaFreeHost(h->h_status);
+  if (h->h_total) cudaFreeHost(h->h_total);
+  for (auto e : h->batch_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto e : h->prof_ev) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* mdkm_last_error(const mdkm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int mdkm_comm_unique_id(unsigned char out[MDKM_NCCL_UNIQUE_ID_BYTES]) {
+  if (!out) return MDKM_ERR_INVALID;
+  NcclApi& api = nccl_api();
+  if (!api.ok) return MDKM_ERR_NCCL;
+  ncclUniqueId id;
+  if (api.GetUniqueId(&id) != 0) return MDKM_ERR_NCCL;
+  memcpy(out, id.internal, MDKM_NCCL_UNIQUE_ID_BYTES);
+  return MDKM_OK;
+}
+
+int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank, const unsigned char id[MDKM_NCCL_UNIQUE_ID_BYTES]) {
+  if (!h || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, MDKM_ERR_INVALID, "bad rank/world size");
+  CU(cudaSetDevice(h->device));
+  if (h->comm) {
+    nccl_api().CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->n_ranks = n_ranks;
+  h->rank = rank;
+  h->frame_ok = false;
+  if (n_ranks == 1) return MDKM_OK;
+  if (!id) return fail(h, MDKM_ERR_INVALID, "unique id required");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(h, MDKM_ERR_NCCL, "libnccl.so.2 not found (set MDKM_NCCL_LIB)");
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, MDKM_NCCL_UNIQUE_ID_BYTES);
+  NC(api.CommInitRank(&h->comm, n_ranks, uid, rank));
+  if (h->have_points) OK(compute_frame(h));
+  return MDKM_OK;
+}
+
+int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int mem) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (n < 0 || (n > 0 && !xyz)) return fail(h, MDKM_ERR_INVALID, "bad points argument");
+  CU(cudaSetDevice(h->device));
+  OK(alloc_points(h, n));
+  h->n = n;
+  const cudaMemcpyKind kind = mem == MDKM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (n > 0) {
+    if (layout == MDKM_POINTS_SOA) {
+      CU(cudaMemcpyAsync(h->x.p, xyz, (size_t)n * 4, kind, h->stream));
+      CU(cudaMemcpyAsync(h->y.p, xyz + n, (size_t)n * 4, kind, h->stream));
+      CU(cudaMemcpyAsync(h->z.p, xyz + 2 * n, (size_t)n * 4, kind, h->stream));
+    } else {
+      const float* src = xyz;
+      if (mem != MDKM_MEM_DEVICE) {
+        OK(ensure(h, h->staging, (size_t)n * 12));
+        CU(cudaMemcpyAsync(h->staging.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+        src = reinterpret_cast<const float*>(h->staging.p);
+      }
+      aos_to_soa_kernel<<<grid_for(h, (n + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+          src, n, h->x.p, h->y.p, h->z.p);
+      ++h->launches;
+      CU(cudaGetLastError());
+    }
+  }
+  OK(zero_tail(h));
+  h->have_points = true;
+  h->frame_ok = false;
+  OK(compute_frame(h));
+  return MDKM_OK;
+}
+
+int64_t mdkm_num_points(const mdkm_handle* h) { return h ? h->n : -1; }
+
+int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz) {
+  if (!h || !idx || !out_xyz || m < 0) return fail(h, MDKM_ERR_INVALID, "bad gather argument");
+  if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
+  CU(cudaSetDevice(h->device));
+  for (int i = 0; i < m; ++i) {
+    if (idx[i] < 0 || idx[i] >= h->n) return fail(h, MDKM_ERR_INVALID, "gather index %lld out of range", (long long)idx[i]);
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 0, h->x.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 1, h->y.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 2, h->z.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return MDKM_OK;
+}
+
+int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale, const uint8_t* mask, int D, int H,
+                   int W, int64_t pix_begin, int64_t pix_count, float max_abs, int detrend, int mem,
+                   int64_t* n_points_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (D < 0 || H <= 0 || W <= 0 || pix_begin < 0 || pix_count < 0 ||
+      pix_begin + pix_count > (int64_t)D * H * W || (pix_count > 0 && !hm))
+    return fail(h, MDKM_ERR_INVALID, "bad stack geometry");
+  if (hm_dtype != MDKM_HM_F32 && hm_dtype != MDKM_HM_I16) return fail(h, MDKM_ERR_INVALID, "bad hm_dtype");
+  const long long HW = (long long)H * W;
+  if (detrend && ((pix_begin % HW) != 0 || (pix_count % HW) != 0))
+    return fail(h, MDKM_ERR_INVALID, "detrend needs whole days in [pix_begin, pix_begin+pix_count)");
+  CU(cudaSetDevice(h->device));
+  const size_t esz = hm_dtype == MDKM_HM_F32 ? 4 : 2;
+  const void* d_hm = hm;
+  const uint8_t* d_mask = mask;
+  if (mem != MDKM_MEM_DEVICE && pix_count > 0) {
+    // stage host rasters (pinned or pageable) in device memory
+    const size_t hm_bytes = (size_t)pix_count * esz;
+    const size_t hm_pad = (hm_bytes + 255) / 256 * 256;
+    OK(ensure(h, h->staging, hm_pad + (mask ? (size_t)pix_count : 0) + 256));
+    CU(cudaMemcpyAsync(h->staging.p, hm, hm_bytes, cudaMemcpyHostToDevice, h->stream));
+    d_hm = h->staging.p;
+    if (mask) {
+      CU(cudaMemcpyAsync(h->staging.p + hm_pad, mask, (size_t)pix_count, cudaMemcpyHostToDevice, h->stream));
+      d_mask = h->staging.p + hm_pad;
+    }
+  }
+  OK(alloc_points(h, pix_count));
+  const long long n_chunks = (pix_count + kChunk - 1) / kChunk;
+  OK(ensure(h, h->chunk_counts, (size_t)n_chunks + 1));
+  OK(ensure(h, h->chunk_offsets, (size_t)n_chunks + 2));
+  UnprojParams up{};
+  up.hm = d_hm; up.mask = d_mask;
+  up.pix_begin = pix_begin; up.pix_count = pix_count; up.HW = HW; up.W = W; up.H = H;
+  up.dtype = hm_dtype;
+  up.vec_ok = ((reinterpret_cast<uintptr_t>(d_hm) & 15) == 0) && (!d_mask || (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
+  up.scale = hm_scale; up.max_abs = max_abs;
+  up.chunk_counts = h->chunk_counts.p;
+  up.chunk_offsets = h->chunk_offsets.p;
+  up.x = h->x.p; up.y = h->y.p; up.z = h->z.p;
+  up.planes = nullptr;
+  up.day0 = (int)(pix_begin / HW);
+  long long n_out = 0;
+  if (pix_count > 0) {
+    if (detrend) {
+      const int n_days = (int)(pix_count / HW);
+      OK(ensure(h, h->planes, (size_t)n_days * 8));
+      OK(ensure(h, h->partials, (size_t)n_days * kPlaneBlocks * 10 + 16));
+      plane_moments_kernel<<<dim3(kPlaneBlocks, n_days), kThreads, 0, h->stream>>>(up, n_days, h->partials.p);
+      plane_solve_kernel<<<n_days, 32, 0, h->stream>>>(h->partials.p, kPlaneBlocks, W, H, h->planes.p);
+      h->launches += 2;
+      CU(cudaGetLastError());
+      up.planes = h->planes.p;
+    }
+    const int g = grid_for(h, (n_chunks + 7) / 8, 8);
+    unproject_count_kernel<<<g, kThreads, 0, h->stream>>>(up);
+    scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->chunk_counts.p, n_chunks, h->chunk_offsets.p,
+                                                  h->chunk_offsets.p + n_chunks + 1);
+    unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_total, h->chunk_offsets.p + n_chunks + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    n_out = *h->h_total;
+  }
+  h->n = n_out;
+  OK(zero_tail(h));
+  h->have_points = true;
+  h->frame_ok = false;
+  OK(compute_frame(h));
+  if (n_points_out) *n_points_out = n_out;
+  return MDKM_OK;
+}
+
+int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem) {
+  if (!h || !out) return fail(h, MDKM_ERR_INVALID, "null argument");
+  if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
+  CU(cudaSetDevice(h->device));
+  if (h->n == 0) return MDKM_OK;
+  float* dst = out;
+  if (mem != MDKM_MEM_DEVICE) {
+    OK(ensure(h, h->staging, (size_t)h->n * 12));
+    dst = reinterpret_cast<float*>(h->staging.p);
+  }
+  soa_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+      h->x.p, h->y.p, h->z.p, h->n, napari_order, 0.0f, dst);
+  ++h->launches;
+  CU(cudaGetLastError());
+  if (mem != MDKM_MEM_DEVICE) CU(cudaMemcpyAsync(out, dst, (size_t)h->n * 12, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MDKM_OK;
+}
+
+int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol, int32_t* labels_out,
+             int labels_mem, double* centroids_out, int* n_iter_out, double* inertia_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (!init) return fail(h, MDKM_ERR_INVALID, "init centroids required");
+  if (max_iter < 1) return fail(h, MDKM_ERR_INVALID, "max_iter must be >= 1");
+  if (tol < 0) return fail(h, MDKM_ERR_INVALID, "tol must be >= 0");
+  CU(cudaSetDevice(h->device));
+  KmBuffers kb{};
+  OK(prepare_kmeans(h, k, kb));
+
+  // sklearn/_kmeans.py:285-293: _tol = mean(var(X, axis=0)) * tol  (0 when tol == 0)
+  double tol_scaled = 0.0;
+  if (tol > 0) {
+    double mv = 0.0;
+    OK(compute_moments(h, &mv));
+    tol_scaled = mv * tol;
+  }
+  h->stat_tol = tol_scaled;
+
+  DevStatus st0{};
+  st0.max_iter = max_iter;
+  st0.k = k;
+  st0.first = 1;
+  st0.tol = tol_scaled;
+  h->h_status[0] = st0;
+  CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
+  OK(upload_table(h, kb, init));
+
+  // Lloyd loop: batches of iterations are enqueued back to back; the host only looks at the
+  // device status between batches, one batch behind the GPU (no per-iteration sync).
+  int enq = 0;  // iterations enqueued that can still complete
+  int inflight = 0, head = 0, tail = 0;
+  long long relocs = 0;
+  int guard = 0;
+  while (true) {
+    while (inflight < 2 && enq < max_iter) {
+      const int nb = std::min(kBatch, max_iter - enq);
+      for (int b = 0; b < nb; ++b) {
+        OK(launch_step(h, kb, 0));
+        OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
+        OK(launch_update(h, kb, /*allow_pause=*/1, 0));
+      }
+      CU(cudaMemcpyAsync(&h->h_status[tail], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaEventRecord(h->batch_ev[tail], h->stream));
+      tail ^= 1;
+      ++inflight;
+      enq += nb;
+    }
+    if (inflight == 0) break;
+    CU(cudaEventSynchronize(h->batch_ev[head]));
+    const DevStatus s = h->h_status[head];
+    head ^= 1;
+    --inflight;
+    if (s.paused && !s.done) {
+      // rare path (empty cluster): everything behind the pause exits early; drain, relocate
+      // on the device, finish the paused iteration, resume enqueueing after it
+      CU(cudaStreamSynchronize(h->stream));
+      inflight = 0;
+      head = tail = 0;
+      if (!h->mean_ok) OK(compute_moments(h, nullptr));
+      OK(relocate_empty(h, kb, s.n_empty));
+      relocs += s.n_empty;
+      OK(launch_update(h, kb, /*allow_pause=*/0, 0));
+      enq = s.iter + 1;
+      if (++guard > max_iter + 8) return fail(h, MDKM_ERR_STATE, "relocation loop did not terminate");
+      continue;
+    }
+    if (s.done) break;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+
+  // final E-step (unless strict) + inertia + int32 labels
+  int* labels_dev = nullptr;
+  if (labels_out) {
+    if (labels_mem == MDKM_MEM_DEVICE) {
+      labels_dev = labels_out;
+    } else {
+      OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
+      labels_dev = h->labels32.p;
+    }
+  }
+  OK(run_final(h, kb, labels_dev, 0));
+  OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
+  read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
+  ++h->launches;
+  CU(cudaGetLastError());
+  if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
+  if (centroids_out)
+    CU(cudaMemcpyAsync(centroids_out, h->dscratch.p, (size_t)k * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&h->h_status[0], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+  if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
+    CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const DevStatus& fin = h->h_status[0];
+  if (n_iter_out) *n_iter_out = fin.iter;
+  if (inertia_out) *inertia_out = fin.inertia;
+  h->stat_refined = (long long)fin.n_refined;
+  h->stat_reloc = relocs;
+  OK(collect_profile(h));
+  return MDKM_OK;
+}
+
+int mdkm_fit_stats(const mdkm_handle* h, int64_t* n_refined, int64_t* n_relocations, double* tol_scaled) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (n_refined) *n_refined = h->stat_refined;
+  if (n_relocations) *n_relocations = h->stat_reloc;
+  if (tol_scaled) *tol_scaled = h->stat_tol;
+  return MDKM_OK;
+}
+
+int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* labels_out, int labels_mem,
+                    double* sums_out, int64_t* counts_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (!centroids) return fail(h, MDKM_ERR_INVALID, "centroids required");
+  CU(cudaSetDevice(h->device));
+  KmBuffers kb{};
+  OK(prepare_kmeans(h, k, kb));
+  DevStatus st0{};
+  st0.max_iter = 1;
+  st0.k = k;
+  st0.first = 1;
+  h->h_status[0] = st0;
+  CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
+  OK(upload_table(h, kb, centroids));
+  OK(launch_step(h, kb, 1));
+  OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
+  OK(ensure(h, h->dscratch, (size_t)k * 4 + 16));
+  long long* d_counts = reinterpret_cast<long long*>(h->dscratch.p + (size_t)k * 3);
+  read_sums_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->acc.p, k, h->fr, h->dscratch.p, d_counts);
+  ++h->launches;
+  CU(cudaGetLastError());
+  if (sums_out)
+    CU(cudaMemcpyAsync(sums_out, h->dscratch.p, (size_t)k * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (counts_out) CU(cudaMemcpyAsync(counts_out, d_counts, (size_t)k * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (labels_out) {
+    // widen the stored labels: the final kernel in "use stored labels" mode
+    int* labels_dev = labels_out;
+    if (labels_mem != MDKM_MEM_DEVICE) {
+      OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
+      labels_dev = h->labels32.p;
+    }
+    h->h_status[1] = st0;
+    h->h_status[1].strict = 1;
+    CU(cudaMemcpyAsync(&h->d_status->strict, &h->h_status[1].strict, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    OK(run_final(h, kb, labels_dev, 0));
+    if (labels_mem != MDKM_MEM_DEVICE && h->n > 0)
+      CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaMemcpyAsync(&h->h_status[0], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stat_refined = (long long)h->h_status[0].n_refined;
+  h->stat_reloc = 0;
+  OK(collect_profile(h));
+  return MDKM_OK;
+}
+
+int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h_min_out, double* h_max_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
+  if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_ground_level is single-rank");
+  CU(cudaSetDevice(h->device));
+  return ground_level_impl(h->stream, h->x.p, h->y.p, h->z.p, h->n, height_norm_out, mem, h_min_out, h_max_out,
+                           &h->launches) == 0
+             ? (h->frame_ok = false, compute_frame(h))
+             : fail(h, MDKM_ERR_CUDA, "ground_level failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals, int n_local_trials,
+                         double* centers_out, int64_t* indices_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
+  if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_kmeans_plusplus is single-rank");
+  if (k < 1 || k > kMaxK || (long long)k > h->n) return fail(h, MDKM_ERR_INVALID, "bad k");
+  if (first_index < 0 || first_index >= h->n) return fail(h, MDKM_ERR_INVALID, "first_index out of range");
+  if (k > 1 && (!rand_vals || n_local_trials < 1)) return fail(h, MDKM_ERR_INVALID, "rand_vals required");
+  CU(cudaSetDevice(h->device));
+  if (!h->frame_ok) OK(compute_frame(h));
+  const int rc = kmeanspp_impl(h->stream, h->sm_count, h->x.p, h->y.p, h->z.p, h->n, h->ff, k, (long long)first_index, rand_vals,
+                               n_local_trials, centers_out, reinterpret_cast<long long*>(indices_out), &h->launches);
+  if (rc != 0) return fail(h, MDKM_ERR_CUDA, "kmeans++ failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return MDKM_OK;
+}
+
+int mdkm_profile_enable(mdkm_handle* h, int on) {
+  if (!h) return MDKM_ERR_INVALID;
+  h->prof = on != 0;
+  h->prof_used = 0;
+  h->prof_ms = 0.0;
+  h->prof_steps = 0;
+  return MDKM_OK;
+}
+
+int mdkm_profile_read(mdkm_handle* h, double* step_kernel_ms, int* n_step_launches, int* n_kernel_launches_total) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (step_kernel_ms) *step_kernel_ms = h->prof_ms;
+  if (n_step_launches) *n_step_launches = h->prof_steps;
+  if (n_kernel_launches_total) *n_kernel_launches_total = h->launches;
+  h->prof_ms = 0.0;
+  h->prof_steps = 0;
+  h->launches = 0;
+  return MDKM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,434 @@
+// K1: height-map stack -> XYZ points with NaN / nodata / range masking fused in, stable
+// (np.where-order) compaction, optional per-day plane detrend.
+//
+// Replaces members/rafael/disparity/plugin.py:148 (h = -disp/16), :151-152 (validity),
+// :157-160 (np.where + stack), :161-171 (SVD plane fit, via 9 moments + a 3x3 symmetric
+// eigen-solve) for every day of the stack, and concatenates the days (absent in the
+// reference).
+//
+// Work unit: a warp-chunk of kChunk = 4096 consecutive pixels (32 rounds of 32 lanes x 4 px,
+// 16 B per lane per round).  Pass 1 counts the valid pixels of every chunk, a single-CTA scan
+// turns the counts into offsets, pass 2 re-reads the pixels and writes x, y, z at
+// offset + warp-exclusive-rank, so the output order is exactly np.where's.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mdkm {
+
+constexpr int kChunk = 4096;
+
+struct UnprojParams {
+  const void* hm;         // points at pixel pix_begin
+  const uint8_t* mask;    // idem, or nullptr
+  long long pix_begin;    // global flat index of the first pixel
+  long long pix_count;
+  long long HW;
+  int W, H;
+  int dtype;              // MDKM_HM_F32 / MDKM_HM_I16
+  int vec_ok;             // hm (and mask) aligned for 16 B / 4 B vector loads
+  float scale;            // for I16
+  float max_abs;
+  unsigned int* chunk_counts;
+  const long long* chunk_offsets;
+  float* x;
+  float* y;
+  float* z;
+  const double* planes;   // [n_days][8]: centre xyz, normal xyz, pad -- or nullptr
+  int day0;               // day index of planes[0]
+};
+
+// Loads 4 consecutive pixel heights starting at local index i (i % 4 == 0); invalid -> NaN.
+__device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i, float (&h)[4],
+                                              unsigned int& valid_bits) {
+  valid_bits = 0;
+  const bool full = (i + 3 < p.pix_count);
+  if (p.dtype == 0) {
+    const float* src = reinterpret_cast<const float*>(p.hm);
+    if (full && p.vec_ok) {
+      const float4 v = ldg_stream_f4(src + i);
+      h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = (i + e < p.pix_count) ? __ldg(src + i + e) : __int_as_float(0x7fc00000);
+    }
+  } else {
+    const short* src = reinterpret_cast<const short*>(p.hm);
+    if (full && p.vec_ok) {
+      const uint2 v = ldg_stream_u64(src + i);
+      h[0] = p.scale * (float)(short)(v.x & 0xffff);
+      h[1] = p.scale * (float)(short)(v.x >> 16);
+      h[2] = p.scale * (float)(short)(v.y & 0xffff);
+      h[3] = p.scale * (float)(short)(v.y >> 16);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = (i + e < p.pix_count) ? p.scale * (float)__ldg(src + i + e) : __int_as_float(0x7fc00000);
+    }
+  }
+  unsigned int m4 = 0x01010101u;
+  if (p.mask) {
+    if (full && p.vec_ok) {
+      m4 = ldg_stream_u32(p.mask + i);
+    } else {
+      m4 = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i + e < p.pix_count && __ldg(p.mask + i + e)) m4 |= (1u << (8 * e));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    // plugin.py:151-152: isfinite(h) & (|h| <= limit) & validity_mask
+    const bool ok = (i + e < p.pix_count) && (fabsf(h[e]) <= p.max_abs) && ((m4 >> (8 * e)) & 0xff);
+    valid_bits |= ok ? (1u << e) : 0u;  // NaN and inf fail the <= test
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) unproject_count_kernel(const UnprojParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (kThreads / 32);
+  const long long n_chunks = (p.pix_count + kChunk - 1) / kChunk;
+  for (long long c = warp; c < n_chunks; c += n_warps) {
+    unsigned int cnt = 0;
+#pragma unroll 4
+    for (int r = 0; r < kChunk / 128; ++r) {
+      const long long i = c * kChunk + r * 128 + lane * 4;
+      float h[4];
+      unsigned int vb;
+      load_heights4(p, i, h, vb);
+      cnt += __popc(vb);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) p.chunk_counts[c] = cnt;
+  }
+}
+
+// Exclusive scan of the chunk counts (single CTA of 1024 threads); writes the total.
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(const unsigned int* counts, long long n,
+                                                           long long* offsets, long long* total) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + tid;
+    const long long v = (i < n) ? (long long)counts[i] : 0;
+    long long s = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) s_warp[w] = s;
+    __syncthreads();
+    if (w == 0) {
+      long long ws = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      s_warp[lane] = ws;
+    }
+    __syncthreads();
+    const long long carry = s_carry;
+    const long long excl = carry + (w ? s_warp[w - 1] : 0) + (s - v);
+    if (i < n) offsets[i] = excl;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const UnprojParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (kThreads / 32);
+  const long long n_chunks = (p.pix_count + kChunk - 1) / kChunk;
+  for (long long c = warp; c < n_chunks; c += n_warps) {
+    long long out = p.chunk_offsets[c];
+    for (int r = 0; r < kChunk / 128; ++r) {
+      const long long i = c * kChunk + r * 128 + lane * 4;
+      float h[4];
+      unsigned int vb;
+      load_heights4(p, i, h, vb);
+      const int cnt = __popc(vb);
+      int incl = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (vb) {
+        // pixel coordinates of the first of the four pixels
+        const long long gp = p.pix_begin + i;
+        const long long day = gp / p.HW;
+        const long long rem = gp - day * p.HW;
+        int row = (int)(rem / p.W);
+        int col = (int)(rem - (long long)row * p.W);
+        int dcur = (int)day;
+        long long o = out + (incl - cnt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (vb & (1u << e)) {
+            float zz = h[e];
+            if (p.planes) {
+              // plugin.py:171: height_rel = dot(P - center, normal)
+              const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
+              zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] +
+                           ((double)h[e] - pl[2]) * pl[5]);
+            }
+            p.x[o] = (float)col;
+            p.y[o] = (float)row;
+            p.z[o] = zz;
+            ++o;
+          }
+          if (++col == p.W) {
+            col = 0;
+            if (++row == p.H) {
+              row = 0;
+              ++dcur;
+            }
+          }
+        }
+      }
+      out += total;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-day plane fit (plugin.py:161-171) from 9 moments.  Grid (kPlaneBlocks, n_days): CTA b of
+// day d reduces a fixed slice of the day's pixels in a fixed order -> deterministic partials;
+// plane_solve_kernel adds them in order and solves the 3x3 symmetric eigenproblem (Jacobi).
+// ---------------------------------------------------------------------------------------
+constexpr int kPlaneBlocks = 64;
+
+__global__ void __launch_bounds__(kThreads) plane_moments_kernel(const UnprojParams p, int n_days,
+                                                                 double* partials /*[d][b][10]*/) {
+  __shared__ double s_red[kThreads / 32];
+  const int d = blockIdx.y;
+  const long long day_begin = (long long)(p.day0 + d) * p.HW - p.pix_begin;  // local index
+  const long long quads = (p.HW + 3) / 4;
+  const double px = 0.5 * (double)(p.W - 1), py = 0.5 * (double)(p.H - 1);
+  double m[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = 0.0;
+  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * kThreads) {
+    const long long li = q * 4;  // index inside the day
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long l = li + e;
+      if (l >= p.HW) break;
+      const long long i = day_begin + l;
+      float hv;
+      if (p.dtype == 0) hv = __ldg(reinterpret_cast<const float*>(p.hm) + i);
+      else hv = p.scale * (float)__ldg(reinterpret_cast<const short*>(p.hm) + i);
+      bool ok = fabsf(hv) <= p.max_abs;
+      if (p.mask) ok = ok && (__ldg(p.mask + i) != 0);
+      if (ok) {
+        const int row = (int)(l / p.W);
+        const int col = (int)(l - (long long)row * p.W);
+        const double X = (double)col - px, Y = (double)row - py, Z = (double)hv;
+        m[0] += 1.0; m[1] += X; m[2] += Y; m[3] += Z;
+        m[4] += X * X; m[5] += X * Y; m[6] += X * Z; m[7] += Y * Y; m[8] += Y * Z; m[9] += Z * Z;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    double v = m[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) t += s_red[w];
+      partials[((size_t)d * gridDim.x + blockIdx.x) * 10 + i] = t;
+    }
+  }
+}
+
+__global__ void plane_solve_kernel(const double* partials, int n_blocks, int W, int H,
+                                   double* planes /*[d][8]*/) {
+  const int d = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double m[10];
+  for (int i = 0; i < 10; ++i) {
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += partials[((size_t)d * n_blocks + b) * 10 + i];
+    m[i] = t;
+  }
+  double* pl = planes + (size_t)d * 8;
+  const double px = 0.5 * (double)(W - 1), py = 0.5 * (double)(H - 1);
+  const double n = m[0];
+  if (n < 3.0) {  // oracle skips the fit for < 3 points: identity plane z_rel = z
+    pl[0] = px; pl[1] = py; pl[2] = 0.0; pl[3] = 0.0; pl[4] = 0.0; pl[5] = 1.0; pl[6] = n; pl[7] = 0.0;
+    return;
+  }
+  const double cx = m[1] / n, cy = m[2] / n, cz = m[3] / n;
+  // scatter matrix of the centred points
+  double A[3][3];
+  A[0][0] = m[4] - n * cx * cx; A[0][1] = m[5] - n * cx * cy; A[0][2] = m[6] - n * cx * cz;
+  A[1][1] = m[7] - n * cy * cy; A[1][2] = m[8] - n * cy * cz; A[2][2] = m[9] - n * cz * cz;
+  A[1][0] = A[0][1]; A[2][0] = A[0][2]; A[2][1] = A[1][2];
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+    for (int pi = 0; pi < 2; ++pi)
+      for (int qi = pi + 1; qi < 3; ++qi) {
+        if (fabs(A[pi][qi]) < 1e-300) continue;
+        const double theta = (A[qi][qi] - A[pi][pi]) / (2.0 * A[pi][qi]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = A[k][pi], akq = A[k][qi];
+          A[k][pi] = c * akp - s * akq;
+          A[k][qi] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = A[pi][k], aqk = A[qi][k];
+          A[pi][k] = c * apk - s * aqk;
+          A[qi][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][pi], vkq = V[k][qi];
+          V[k][pi] = c * vkp - s * vkq;
+          V[k][qi] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int mi = 0;
+  if (A[1][1] < A[mi][mi]) mi = 1;
+  if (A[2][2] < A[mi][mi]) mi = 2;
+  double nx = V[0][mi], ny = V[1][mi], nz = V[2][mi];
+  const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+  nx /= nn; ny /= nn; nz /= nn;
+  if (nz < 0) { nx = -nx; ny = -ny; nz = -nz; }  // plugin.py:167-168
+  pl[0] = cx + px; pl[1] = cy + py; pl[2] = cz; pl[3] = nx; pl[4] = ny; pl[5] = nz; pl[6] = n; pl[7] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Cloud statistics: per-dimension min / max (frame + error bound) and first/second moments
+// about the frame origin (mean, and var(X) for sklearn's tolerance, _kmeans.py:285-293).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(unsigned int u) {
+  const unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+
+// out[0..2] = ordered min x,y,z ; out[3..5] = ordered max.  Caller pre-fills min with
+// 0xffffffff and max with 0.
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* x, const float* y, const float* z,
+                                                          long long n, unsigned int* out) {
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  const long long n4 = (n + 3) / 4;
+  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < n4; q += (long long)gridDim.x * kThreads) {
+    const float4 vx = ldg_stream_f4(x + q * 4), vy = ldg_stream_f4(y + q * 4), vz = ldg_stream_f4(z + q * 4);
+    const float ax[4] = {vx.x, vx.y, vx.z, vx.w}, ay[4] = {vy.x, vy.y, vy.z, vy.w}, az[4] = {vz.x, vz.y, vz.z, vz.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (q * 4 + e < n) {
+        mn[0] = fminf(mn[0], ax[e]); mx[0] = fmaxf(mx[0], ax[e]);
+        mn[1] = fminf(mn[1], ay[e]); mx[1] = fmaxf(mx[1], ay[e]);
+        mn[2] = fminf(mn[2], az[e]); mx[2] = fmaxf(mx[2], az[e]);
+      }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const unsigned int a = __reduce_min_sync(0xffffffffu, f2ord(mn[d]));
+    const unsigned int b = __reduce_max_sync(0xffffffffu, f2ord(mx[d]));
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&out[d], a);
+      atomicMax(&out[3 + d], b);
+    }
+  }
+}
+
+// partials[b][6] = sum (x-o), sum (x-o)^2 per dim, in FP64, fixed order inside the CTA;
+// the last CTA adds the partials in CTA order into out[6].
+__global__ void __launch_bounds__(kThreads) moments_kernel(const float* x, const float* y, const float* z,
+                                                           long long n, FrameF f, double* partials,
+                                                           unsigned int* ticket, double* out) {
+  __shared__ double s_red[kThreads / 32];
+  __shared__ bool s_last;
+  double m[6] = {0, 0, 0, 0, 0, 0};
+  const long long n4 = (n + 3) / 4;
+  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < n4; q += (long long)gridDim.x * kThreads) {
+    const float4 vx = ldg_stream_f4(x + q * 4), vy = ldg_stream_f4(y + q * 4), vz = ldg_stream_f4(z + q * 4);
+    const float ax[4] = {vx.x, vx.y, vx.z, vx.w}, ay[4] = {vy.x, vy.y, vy.z, vy.w}, az[4] = {vz.x, vz.y, vz.z, vz.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (q * 4 + e < n) {
+        const double X = (double)ax[e] - (double)f.ox, Y = (double)ay[e] - (double)f.oy,
+                     Z = (double)az[e] - (double)f.oz;
+        m[0] += X; m[1] += Y; m[2] += Z;
+        m[3] += X * X; m[4] += Y * Y; m[5] += Z * Z;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = m[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) t += s_red[w];
+      partials[(size_t)blockIdx.x * 6 + i] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 6) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += partials[(size_t)b * 6 + threadIdx.x];
+    out[threadIdx.x] = t;
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// AoS [n][3] -> SoA, or SoA -> [n][3] in (x,y,z) or napari (z,y,x) order.
+__global__ void __launch_bounds__(kThreads) aos_to_soa_kernel(const float* xyz, long long n, float* x, float* y,
+                                                              float* z) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    x[i] = xyz[3 * i + 0];
+    y[i] = xyz[3 * i + 1];
+    z[i] = xyz[3 * i + 2];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) soa_to_aos_kernel(const float* x, const float* y, const float* z,
+                                                              long long n, int napari, float zshift, float* out) {
+  // each thread writes one float of the interleaved output: fully coalesced stores
+  const long long total = n * 3;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+    const long long i = t / 3;
+    const int c = (int)(t - i * 3);
+    const int src = napari ? 2 - c : c;
+    out[t] = src == 0 ? x[i] : (src == 1 ? y[i] : z[i] - zshift);
+  }
+}
+
+}  // namespace mdkm

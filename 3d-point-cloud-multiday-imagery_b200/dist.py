@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: one process per GPU, points sharded by contiguous pixel ranges.
+
+torch.distributed is used only to ship the 128-byte NCCL unique id and for barriers; the
+per-iteration exchange (K x 4 int64 partial sums + the changed-label count, one
+ncclAllReduce on the kernels' own stream) lives inside libmdkm.so.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(total: int, rank: int, world: int, align: int = 1) -> Tuple[int, int]:
+    """Contiguous [begin, end) of ``total`` items for ``rank`` of ``world``.
+
+    Items are split as evenly as possible in units of ``align`` (e.g. one raster row, so that
+    a rank's slice starts on a row boundary; SURVEY.md section 8(e) "whole days / row bands").
+    The concatenation over ranks is exactly [0, total).
+    """
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    units = (total + align - 1) // align
+    base, rem = divmod(units, world)
+    b = rank * base + min(rank, rem)
+    e = b + base + (1 if rank < rem else 0)
+    return min(b * align, total), min(e * align, total)
+
+
+def exchange_unique_id(make_id, rank: int, world: int, device=None) -> bytes:
+    """Rank 0 calls ``make_id()``; the bytes are broadcast through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return b""
+    backend = dist.get_backend()
+    dev = torch.device("cuda", device) if (backend == "nccl" and device is not None) else torch.device("cpu")
+    if rank == 0:
+        raw = make_id()
+        t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+    else:
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
+def init_engine_comm(engine, rank: int, world: int):
+    """Give ``engine`` a NCCL communicator spanning the torch.distributed world."""
+    from .engine import Engine
+
+    if world == 1:
+        engine.init_comm(1, 0, None)
+        return
+    uid = exchange_unique_id(Engine.make_unique_id, rank, world, device=engine.device)
+    engine.init_comm(world, rank, uid)

@@ -1,0 +1,269 @@
+"""`Engine`: one libmdkm handle (one B200, one rank) with numpy / torch friendly methods.
+
+Thin by design: every method is one C-ABI call (include/mdkm.h); arrays are passed as raw
+host or device pointers.  torch is only used to recognise CUDA tensors and to exchange the
+NCCL unique id between ranks.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_float, c_int, c_int64, c_ubyte, c_void_p
+
+import numpy as np
+
+from . import _cabi as C
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+def _as_buffer(a, dtype=None):
+    """-> (pointer:int, mem_kind, keepalive, shape, np_dtype) for numpy arrays / torch tensors."""
+    if _is_torch(a):
+        import torch
+
+        t = a
+        if dtype is not None:
+            want = {np.float32: torch.float32, np.int16: torch.int16, np.uint8: torch.uint8,
+                    np.float64: torch.float64, np.int32: torch.int32}[dtype]
+            if t.dtype == torch.bool and want == torch.uint8:
+                t = t.to(torch.uint8)
+            elif t.dtype != want:
+                t = t.to(want)
+        t = t.contiguous()
+        mem = C.MEM_DEVICE if t.is_cuda else C.MEM_HOST
+        return t.data_ptr(), mem, t, tuple(t.shape), None
+    arr = np.asarray(a)
+    if dtype is not None and arr.dtype != np.dtype(dtype):
+        arr = arr.astype(dtype)
+    arr = np.ascontiguousarray(arr)
+    return arr.ctypes.data, C.MEM_HOST, arr, arr.shape, arr.dtype
+
+
+class Engine:
+    """Owns one ``mdkm_handle``.  Use as a context manager or call ``close()``."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._lib = C.load()
+        self._h = c_void_p()
+        sptr = None
+        if stream is not None:
+            sptr = c_void_p(int(getattr(stream, "cuda_stream", stream)))
+        rc = self._lib.mdkm_create(byref(self._h), int(device), sptr)
+        if rc != C.MDKM_OK:
+            self._h = c_void_p()
+            raise C.MdkmError(rc, "mdkm_create failed (needs a visible sm_100 GPU; there is no CPU fallback)")
+        self.device = int(device)
+        self.n_ranks = 1
+        self.rank = 0
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mdkm_destroy(self._h)
+            self._h = c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != C.MDKM_OK:
+            msg = self._lib.mdkm_last_error(self._h)
+            raise C.MdkmError(rc, msg.decode() if msg else "")
+
+    # -- multi-GPU ---------------------------------------------------------------------
+    def init_comm(self, n_ranks: int, rank: int, unique_id: bytes | None):
+        buf = None
+        if n_ranks > 1:
+            assert unique_id is not None and len(unique_id) == C.NCCL_UNIQUE_ID_BYTES
+            buf = (c_ubyte * C.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.mdkm_comm_init(self._h, int(n_ranks), int(rank), buf))
+        self.n_ranks, self.rank = int(n_ranks), int(rank)
+
+    @staticmethod
+    def make_unique_id() -> bytes:
+        lib = C.load()
+        buf = (c_ubyte * C.NCCL_UNIQUE_ID_BYTES)()
+        rc = lib.mdkm_comm_unique_id(buf)
+        if rc != C.MDKM_OK:
+            raise C.MdkmError(rc, "mdkm_comm_unique_id failed (libnccl.so.2 not loadable)")
+        return bytes(buf)
+
+    # -- data ----------------------------------------------------------------------------
+    def unproject(self, height_maps, valid_masks=None, *, max_abs_height=144.0, detrend=False,
+                  disparity_scale=None, pix_begin=0, stack_shape=None) -> int:
+        """Height rasters -> resident XYZ cloud (plugin.py:148-171).  Returns the point count.
+
+        ``height_maps``: float32 ``[D,H,W]`` (NaN = nodata) or, with ``disparity_scale``
+        (the reference uses -1/16), int16 OpenCV fixed-point disparity.  For a sharded
+        stack pass this rank's flat slice plus ``stack_shape=(D,H,W)`` and ``pix_begin``.
+        """
+        is_i16 = disparity_scale is not None
+        ptr, mem, keep, shape, _ = _as_buffer(height_maps, np.int16 if is_i16 else np.float32)
+        if stack_shape is None:
+            if len(shape) == 2:
+                shape = (1,) + tuple(shape)
+            if len(shape) != 3:
+                raise ValueError("height_maps must be [D,H,W] or [H,W]")
+            D, H, W = shape
+            count = D * H * W
+        else:
+            D, H, W = stack_shape
+            count = int(np.prod(shape))
+        mptr, keep_m = None, None
+        if valid_masks is not None:
+            mptr, mmem, keep_m, mshape, _ = _as_buffer(valid_masks, np.uint8)
+            if int(np.prod(mshape)) != count:
+                raise ValueError("valid_masks must match height_maps")
+            if mmem != mem:
+                raise ValueError("height_maps and valid_masks must live in the same memory space")
+        n = c_int64(0)
+        self._check(self._lib.mdkm_unproject(
+            self._h, c_void_p(ptr), C.HM_I16 if is_i16 else C.HM_F32,
+            float(disparity_scale) if is_i16 else 1.0, c_void_p(mptr) if mptr else None,
+            int(D), int(H), int(W), int(pix_begin), int(count), float(max_abs_height),
+            1 if detrend else 0, mem, byref(n)))
+        del keep, keep_m
+        return int(n.value)
+
+    def set_points(self, points, layout="aos") -> int:
+        """Load an ``[N,3]`` (x,y,z) float32 cloud (or SoA ``[3,N]`` with layout="soa")."""
+        ptr, mem, keep, shape, _ = _as_buffer(points, np.float32)
+        if layout == "aos":
+            if len(shape) != 2 or shape[1] != 3:
+                raise ValueError("points must be [N,3]")
+            n = shape[0]
+            lay = C.POINTS_AOS
+        else:
+            if len(shape) != 2 or shape[0] != 3:
+                raise ValueError("SoA points must be [3,N]")
+            n = shape[1]
+            lay = C.POINTS_SOA
+        self._check(self._lib.mdkm_set_points(self._h, c_void_p(ptr), int(n), lay, mem))
+        del keep
+        return int(n)
+
+    @property
+    def n_points(self) -> int:
+        return int(self._lib.mdkm_num_points(self._h))
+
+    def gather_points(self, idx) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty((idx.shape[0], 3), dtype=np.float32)
+        self._check(self._lib.mdkm_gather_points(
+            self._h, idx.ctypes.data_as(POINTER(c_int64)), int(idx.shape[0]),
+            out.ctypes.data_as(POINTER(c_float))))
+        return out
+
+    def get_cloud(self, napari_order=True, out=None):
+        """Resident cloud as float32 ``[N,3]``; (z,y,x) columns when ``napari_order``."""
+        n = self.n_points
+        if out is None:
+            out = np.empty((n, 3), dtype=np.float32)
+        ptr, mem, keep, shape, _ = _as_buffer(out)
+        if int(np.prod(shape)) != n * 3:
+            raise ValueError("out must hold N*3 float32")
+        self._check(self._lib.mdkm_get_cloud(self._h, c_void_p(ptr), 1 if napari_order else 0, mem))
+        return out
+
+    def ground_level(self, want_height_norm=True):
+        """plugin.py:181-192.  Returns (h_min, h_max, height_norm or None)."""
+        n = self.n_points
+        hn = np.empty(n, dtype=np.float32) if want_height_norm else None
+        lo, hi = c_double(0), c_double(0)
+        self._check(self._lib.mdkm_ground_level(
+            self._h, c_void_p(hn.ctypes.data) if hn is not None else None, C.MEM_HOST, byref(lo), byref(hi)))
+        return float(lo.value), float(hi.value), hn
+
+    # -- k-means -------------------------------------------------------------------------
+    def fit(self, init, max_iter=300, tol=1e-4, want_labels=True, labels_out=None):
+        """One Lloyd run from explicit centroids.  Returns dict(labels, centers, n_iter, inertia, ...)."""
+        init = np.ascontiguousarray(init, dtype=np.float64)
+        if init.ndim != 2 or init.shape[1] != 3:
+            raise ValueError("init must be [K,3]")
+        k = init.shape[0]
+        n = self.n_points
+        lab_ptr, lab_mem, labels = None, C.MEM_HOST, None
+        if labels_out is not None:
+            lab_ptr, lab_mem, labels, shape, _ = _as_buffer(labels_out)
+            if int(np.prod(shape)) != n:
+                raise ValueError("labels_out must hold N int32")
+        elif want_labels:
+            labels = np.empty(n, dtype=np.int32)
+            lab_ptr = labels.ctypes.data
+        centers = np.empty((k, 3), dtype=np.float64)
+        n_iter = c_int(0)
+        inertia = c_double(0.0)
+        self._check(self._lib.mdkm_fit(
+            self._h, int(k), init.ctypes.data_as(POINTER(c_double)), int(max_iter), float(tol),
+            c_void_p(lab_ptr) if lab_ptr else None, lab_mem,
+            centers.ctypes.data_as(POINTER(c_double)), byref(n_iter), byref(inertia)))
+        nref, nrel, tols = c_int64(0), c_int64(0), c_double(0)
+        self._lib.mdkm_fit_stats(self._h, byref(nref), byref(nrel), byref(tols))
+        return {
+            "labels": labels, "centers": centers, "n_iter": int(n_iter.value),
+            "inertia": float(inertia.value), "n_refined": int(nref.value),
+            "n_relocations": int(nrel.value), "tol_scaled": float(tols.value),
+        }
+
+    def lloyd_step(self, centroids, want_labels=True):
+        """Single E-step + sums (test hook).  Returns (labels, sums[K,3], counts[K], n_refined)."""
+        c = np.ascontiguousarray(centroids, dtype=np.float64)
+        k = c.shape[0]
+        n = self.n_points
+        labels = np.empty(n, dtype=np.int32) if want_labels else None
+        sums = np.empty((k, 3), dtype=np.float64)
+        counts = np.empty(k, dtype=np.int64)
+        self._check(self._lib.mdkm_lloyd_step(
+            self._h, int(k), c.ctypes.data_as(POINTER(c_double)),
+            c_void_p(labels.ctypes.data) if labels is not None else None, C.MEM_HOST,
+            sums.ctypes.data_as(POINTER(c_double)), counts.ctypes.data_as(POINTER(c_int64))))
+        nref = c_int64(0)
+        self._lib.mdkm_fit_stats(self._h, byref(nref), None, None)
+        return labels, sums, counts, int(nref.value)
+
+    def kmeans_plusplus(self, n_clusters: int, random_state):
+        """k-means++ seeding (sklearn/_kmeans.py:180-278); RNG draws come from ``random_state``
+        (a ``numpy.random.RandomState``) in scikit-learn's order, distances run on the GPU."""
+        k = int(n_clusters)
+        n = self.n_points
+        n_local_trials = 2 + int(np.log(k))
+        # RandomState.choice(n, p=w/w.sum()) (sklearn/_kmeans.py:228): one uniform draw inverted
+        # through cdf = cumsum(p)/cdf[-1] with searchsorted(side="right") -- reproduced exactly
+        # while the cdf fits in host memory, floor(u*n) beyond that.
+        u = float(random_state.random_sample())
+        if n <= (1 << 26):
+            cdf = np.cumsum(np.full(n, 1.0 / n))
+            cdf /= cdf[-1]
+            first = int(min(np.searchsorted(cdf, u, side="right"), n - 1))
+            del cdf
+        else:
+            first = min(int(u * n), n - 1)
+        rv = np.ascontiguousarray(
+            [random_state.uniform(size=n_local_trials) for _ in range(k - 1)], dtype=np.float64
+        ).reshape(max(k - 1, 0), n_local_trials)
+        centers = np.empty((k, 3), dtype=np.float64)
+        idx = np.empty(k, dtype=np.int64)
+        self._check(self._lib.mdkm_kmeans_plusplus(
+            self._h, k, first, rv.ctypes.data_as(POINTER(c_double)) if k > 1 else None, n_local_trials,
+            centers.ctypes.data_as(POINTER(c_double)), idx.ctypes.data_as(POINTER(c_int64))))
+        return centers, idx
+
+    # -- profiling -----------------------------------------------------------------------
+    def profile(self, on: bool):
+        self._check(self._lib.mdkm_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        ms, ns, nl = c_double(0), c_int(0), c_int(0)
+        self._check(self._lib.mdkm_profile_read(self._h, byref(ms), byref(ns), byref(nl)))
+        return float(ms.value), int(ns.value), int(nl.value)

@@ -1,0 +1,149 @@
+/* mdkm.h -- C ABI of libmdkm.so: multi-day height-map -> XYZ unprojection + Lloyd k-means
+ * on one NVIDIA B200 (sm_100a) per handle.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * rafael-alani/3d-point-cloud-multiday-imagery that this project accelerates
+ * (SURVEY.md section 8).  The reference is pure Python and has no FFI of its own; each
+ * entry point below replaces the Python/NumPy/scikit-learn code it cites, and
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to
+ * members/rafael/disparity/plugin.py.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch types; every call returns MDKM_OK (0) or a negative
+ *     mdkm_status; mdkm_last_error(h) gives the text for the last failure on that handle.
+ *   - one handle == one CUDA device == one rank.  A handle is used by one host thread at a
+ *     time (the reference calls the path from a single napari worker thread,
+ *     members/rafael/disparity/widget.py:116-147).
+ *   - pointers are host pointers unless the call takes a `mem` argument, in which case
+ *     MDKM_MEM_DEVICE means "device pointer on the handle's device" (e.g. a torch tensor's
+ *     data_ptr()).  The library never keeps a caller pointer after the call returns.
+ *   - there is no CPU fallback: without a usable CUDA device mdkm_create fails.
+ */
+#ifndef MDKM_H_
+#define MDKM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdkm_handle mdkm_handle;
+
+typedef enum mdkm_status {
+  MDKM_OK = 0,
+  MDKM_ERR_INVALID = -1,   /* bad argument */
+  MDKM_ERR_CUDA = -2,      /* CUDA runtime error (see mdkm_last_error) */
+  MDKM_ERR_NO_DEVICE = -3, /* no CUDA device / wrong architecture */
+  MDKM_ERR_STATE = -4,     /* call order (e.g. fit before points are set) */
+  MDKM_ERR_NCCL = -5,      /* NCCL missing or failed */
+  MDKM_ERR_OOM = -6
+} mdkm_status;
+
+enum { MDKM_MEM_HOST = 0, MDKM_MEM_DEVICE = 1 };
+enum { MDKM_HM_F32 = 0, MDKM_HM_I16 = 1 };      /* height raster element type */
+enum { MDKM_POINTS_AOS = 0, MDKM_POINTS_SOA = 1 }; /* xyzxyz... or x[n] y[n] z[n] */
+
+#define MDKM_NCCL_UNIQUE_ID_BYTES 128
+
+/* Library / build identification ("mdkm <ver> sm_100a"). */
+const char* mdkm_version(void);
+
+/* Create a handle on CUDA device `device`.  `cuda_stream` is an optional cudaStream_t the
+ * library should enqueue on (NULL: it creates its own non-blocking stream). */
+int mdkm_create(mdkm_handle** out, int device, void* cuda_stream);
+void mdkm_destroy(mdkm_handle* h);
+const char* mdkm_last_error(const mdkm_handle* h);
+
+/* ---- multi-GPU: one rank per handle, NCCL over NVLink ------------------------------- */
+/* Rank 0 makes the id; the caller ships the 128 bytes to the other ranks (the Python
+ * host uses torch.distributed for that) and every rank calls mdkm_comm_init. */
+int mdkm_comm_unique_id(unsigned char out[MDKM_NCCL_UNIQUE_ID_BYTES]);
+int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank,
+                   const unsigned char id[MDKM_NCCL_UNIQUE_ID_BYTES]);
+
+/* ---- K1: unprojection ----------------------------------------------------------------
+ * Replaces members/rafael/disparity/plugin.py:148 (h = -disp/16), :151-152 (validity:
+ * isfinite & |h| <= max_abs & mask), :157-160 ((y,x)=np.where(valid), P=[x,y,z]) and the
+ * (absent in the reference) multi-day concatenation, for the pixel range
+ * [pix_begin, pix_begin+pix_count) of the flattened [D,H,W] stack.  `hm` / `mask` point at
+ * pixel `pix_begin`.  hm_dtype MDKM_HM_F32: heights, used as is (hm_scale ignored);
+ * MDKM_HM_I16: OpenCV fixed-point disparity, h = hm_scale * disp (the reference uses
+ * -1/16).  mask may be NULL.  detrend != 0 additionally applies the per-day plane fit of
+ * plugin.py:161-171 (z becomes the signed distance to the day's least-squares plane); it
+ * needs whole days in the range.  The points stay resident in the handle, in np.where
+ * order (day-major, row-major); *n_points_out receives how many there are on this rank. */
+int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
+                   const uint8_t* mask, int D, int H, int W, int64_t pix_begin,
+                   int64_t pix_count, float max_abs, int detrend, int mem,
+                   int64_t* n_points_out);
+
+/* Load an already unprojected cloud (this rank's shard).  Replaces the `X` argument of the
+ * reference's KMeans(...).fit_predict(X) call (members/jasraj/land_use_classification/
+ * core.py:227-228) for d = 3. */
+int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int mem);
+
+/* Number of resident points on this rank. */
+int64_t mdkm_num_points(const mdkm_handle* h);
+
+/* Fetch m resident points by local index as float32 [m,3] (x,y,z) into host memory (what
+ * `X[seeds]` does for init="random", sklearn/cluster/_kmeans.py:1014-1021). */
+int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz);
+
+/* Copy the resident cloud out as float32 [n,3].  napari_order != 0 gives (z,y,x) columns as
+ * plugin.py:192 builds `points_coords`; 0 gives (x,y,z). */
+int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem);
+
+/* Ground-levelling of plugin.py:181-192: h_min/h_max = percentile(z,[2,98]) with numpy's
+ * linear interpolation; z -= h_min in the resident cloud; height_norm_out (optional, n
+ * floats) = clip((z-h_min)/(h_max-h_min+1e-6),0,1).  Single rank only. */
+int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h_min_out,
+                      double* h_max_out);
+
+/* ---- K2..K4: Lloyd k-means -----------------------------------------------------------
+ * Replaces sklearn.cluster.KMeans(n_clusters=k, init=<array>, n_init=1,
+ * algorithm="lloyd", max_iter, tol).fit(X) as the reference calls it (core.py:227-228;
+ * algorithm in sklearn/cluster/_kmeans.py:630-758, 1436-1563 and _k_means_lloyd.pyx).
+ * init: k x 3 float64, row-major, same coordinates as the points.
+ * labels_out: int32[n_local] (may be NULL); centroids_out: float64[k*3]; n_iter_out,
+ * inertia_out as scikit-learn's n_iter_ / inertia_.  With a communicator the point set is
+ * the union of all ranks' shards and every rank gets the same centroids / n_iter /
+ * inertia and its own shard's labels.  No host synchronisation per iteration. */
+int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol,
+             int32_t* labels_out, int labels_mem, double* centroids_out, int* n_iter_out,
+             double* inertia_out);
+
+/* Diagnostics of the last mdkm_fit / mdkm_lloyd_step on this rank:
+ * n_refined = point-iterations whose FP32 distances were within the rounding-error bound
+ * of a tie and were re-decided in float64; n_relocations = empty-cluster relocations. */
+int mdkm_fit_stats(const mdkm_handle* h, int64_t* n_refined, int64_t* n_relocations,
+                   double* tol_scaled);
+
+/* One E-step + M-step sums with the given centroids (test hook for single-step parity;
+ * mirrors sklearn.cluster._k_means_lloyd.lloyd_iter_chunked_dense up to the sums,
+ * _k_means_lloyd.pyx:23-152).  sums_out: float64[k*3] = sum of member coordinates,
+ * counts_out: int64[k]; both GLOBAL over ranks when a communicator is set. */
+int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* labels_out,
+                    int labels_mem, double* sums_out, int64_t* counts_out);
+
+/* k-means++ seeding on the device (sklearn/cluster/_kmeans.py:180-278).  The random draws
+ * of numpy.random.RandomState stay on the host and are supplied by the caller in
+ * scikit-learn's order: `first_index` is the result of RandomState.choice(n) for the first
+ * centre, then for each further centre `n_local_trials` uniforms in [0,1) from rand_vals
+ * (row-major [(k-1), n_local_trials]); the device does the distance, min, potential and
+ * cumulative-sum search passes.  centers_out: float64[k*3]; indices_out: int64[k].
+ * Single rank only. */
+int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals,
+                         int n_local_trials, double* centers_out, int64_t* indices_out);
+
+/* Timing aid for bench.py: when enabled, CUDA events bracket every launch of the
+ * assignment+accumulate kernel inside mdkm_fit; mdkm_profile_read returns their summed
+ * duration and count and resets both. */
+int mdkm_profile_enable(mdkm_handle* h, int on);
+int mdkm_profile_read(mdkm_handle* h, double* step_kernel_ms, int* n_step_launches,
+                      int* n_kernel_launches_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDKM_H_ */
