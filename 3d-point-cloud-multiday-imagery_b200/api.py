@@ -122,7 +122,8 @@ def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_
 def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k-means++", n_init=1,
                          max_iter=300, tol=1e-4, random_state=None, max_abs_height=MAX_ABS_HEIGHT,
                          detrend=False, disparity_scale=None, ground_level=False, return_cloud=True,
-                         device=0, engine: Optional[Engine] = None) -> FusionResult:
+                         device=0, engine: Optional[Engine] = None, stack_shape=None,
+                         pix_begin=0) -> FusionResult:
     """Unproject a multi-day height-map stack into one XYZ cloud and cluster it (Lloyd).
 
     height_maps : float32 ``[D,H,W]`` (NaN = nodata), numpy or torch (CPU or CUDA); or int16
@@ -132,13 +133,18 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     detrend : apply the per-day plane fit of plugin.py:161-171 to z before clustering.
     ground_level : additionally shift z by the 2nd percentile and return the 'height'
         colour property of plugin.py:181-192 (after clustering; does not change labels).
+    engine : reuse an existing ``Engine`` (keeps device buffers, and with
+        ``Engine(pinned_results=True)`` page-locked result buffers, across calls); with a
+        multi-rank engine pass this rank's flat slice plus ``stack_shape`` / ``pix_begin``.
     Returns a FusionResult; ``fused_cloud`` is float32 ``[N,3]`` in napari (z,y,x) order.
     """
     own = engine is None
     eng = engine or Engine(device)
     try:
         n = eng.unproject(height_maps, valid_masks, max_abs_height=max_abs_height, detrend=detrend,
-                          disparity_scale=disparity_scale)
+                          disparity_scale=disparity_scale, stack_shape=stack_shape, pix_begin=pix_begin)
+        # the cloud is final once unprojected: start its device->host copy before the Lloyd loop
+        cloud = eng.get_cloud(napari_order=True) if (return_cloud and not ground_level) else None
         r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
                         tol=tol, random_state=random_state)
         hn = None
@@ -148,7 +154,8 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
             extra["h_min"], extra["h_max"] = lo, hi
             r["centers"] = r["centers"].copy()
             r["centers"][:, 2] -= lo
-        cloud = eng.get_cloud(napari_order=True) if return_cloud else None
+        if return_cloud and cloud is None:
+            cloud = eng.get_cloud(napari_order=True)
         return FusionResult(labels=r["labels"], centroids=r["centers"], fused_cloud=cloud,
                             n_iter=r["n_iter"], inertia=r["inertia"], n_points=n,
                             n_refined=r["n_refined"], n_relocations=r["n_relocations"],

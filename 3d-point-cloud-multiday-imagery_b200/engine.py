@@ -44,8 +44,13 @@ def _as_buffer(a, dtype=None):
 class Engine:
     """Owns one ``mdkm_handle``.  Use as a context manager or call ``close()``."""
 
-    def __init__(self, device: int = 0, stream=None):
+    def __init__(self, device: int = 0, stream=None, pinned_results: bool = False):
+        """``pinned_results``: result arrays (labels, cloud) are views of page-locked buffers
+        owned by the engine and REUSED by the next call -- fastest device->host path; copy them
+        if they must outlive the next call."""
         self._lib = C.load()
+        self.pinned_results = bool(pinned_results)
+        self._pinned = {}
         self._h = c_void_p()
         sptr = None
         if stream is not None:
@@ -75,6 +80,20 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def _result_buffer(self, name, shape, dtype):
+        """numpy result array; page-locked and cached when ``pinned_results``."""
+        if not self.pinned_results:
+            return np.empty(shape, dtype=dtype)
+        import torch
+
+        n = int(np.prod(shape))
+        t = self._pinned.get(name)
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+        if t is None or t.numel() < n or t.dtype != tdt:
+            t = torch.empty(max(n, 1), dtype=tdt, pin_memory=True)
+            self._pinned[name] = t
+        return t.numpy()[:n].reshape(shape)
 
     def _check(self, rc: int):
         if rc != C.MDKM_OK:
@@ -169,7 +188,7 @@ class Engine:
         """Resident cloud as float32 ``[N,3]``; (z,y,x) columns when ``napari_order``."""
         n = self.n_points
         if out is None:
-            out = np.empty((n, 3), dtype=np.float32)
+            out = self._result_buffer("cloud", (n, 3), np.float32)
         ptr, mem, keep, shape, _ = _as_buffer(out)
         if int(np.prod(shape)) != n * 3:
             raise ValueError("out must hold N*3 float32")
@@ -199,7 +218,7 @@ class Engine:
             if int(np.prod(shape)) != n:
                 raise ValueError("labels_out must hold N int32")
         elif want_labels:
-            labels = np.empty(n, dtype=np.int32)
+            labels = self._result_buffer("labels", (n,), np.int32)
             lab_ptr = labels.ctypes.data
         centers = np.empty((k, 3), dtype=np.float64)
         n_iter = c_int(0)

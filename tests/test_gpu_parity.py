@@ -1,0 +1,303 @@
+"""GPU parity tests: every call goes through the C ABI (libmdkm.so via ctypes) and is checked
+against the CPU oracle on identical inputs.  Bars (BASELINE.json north star): labels
+bit-exact except near-ties within 1e-6 relative (counted and reported), centroids within
+1e-5 relative (denominator max(|c|, per-dim data std))."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, kmeans_oracle as KO, unproject_oracle as UO
+
+pytestmark = pytest.mark.gpu
+
+synth = importlib.import_module("3d-point-cloud-multiday-imagery_b200.synth")
+
+LABEL_BAND = 1e-6
+CENTROID_TOL = 1e-5
+
+
+def check_labels(P, centers, labels_ref, labels_gpu, allow_near=None):
+    r = KO.compare_labels(P, centers, labels_ref, labels_gpu, rel_band=LABEL_BAND)
+    print("label parity:", r)
+    assert r["n_hard"] == 0, r
+    if allow_near is not None:
+        assert r["n_near_tie"] <= allow_near, r
+    return r
+
+
+def check_centroids(c_ref, c_gpu, P):
+    err = KO.centroid_rel_err(c_ref, c_gpu, P.std(axis=0))
+    print("centroid rel err:", err)
+    assert err <= CENTROID_TOL, err
+    return err
+
+
+# ---------------------------------------------------------------------------------------
+# K1 unprojection
+# ---------------------------------------------------------------------------------------
+def test_unproject_golden_disparity(engine, golden):
+    g = golden("unproject_small.npz")
+    n = engine.unproject(g["disparity"], g["mask"], disparity_scale=-1.0 / 16.0)
+    assert n == g["points"].shape[0]
+    cloud = engine.get_cloud(napari_order=False)
+    np.testing.assert_array_equal(cloud.astype(np.float64), g["points"])  # bit-exact
+    zyx = engine.get_cloud(napari_order=True)
+    np.testing.assert_array_equal(zyx, cloud[:, ::-1])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 5), (3, 17, 33), (2, 64, 64), (4, 130, 257), (1, 96, 4096)])
+def test_unproject_ragged_shapes(engine, shape):
+    D, H, W = shape
+    hm = synth.make_stack(D, H, W, seed=D * 1000 + W, n_buildings=5).numpy()
+    rs = np.random.RandomState(W)
+    mask = rs.rand(D, H, W) > 0.1
+    for m in (None, mask):
+        P = UO.unproject_stack(hm, m)
+        n = engine.unproject(hm, m)
+        assert n == P.shape[0]
+        if n:
+            np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), P)
+
+
+def test_unproject_all_invalid_and_empty(engine):
+    assert engine.unproject(np.full((2, 8, 8), np.nan, dtype=np.float32)) == 0
+    assert engine.unproject(np.full((1, 4, 4), 500.0, dtype=np.float32)) == 0
+    assert engine.n_points == 0
+
+
+def test_unproject_boundary_values(engine):
+    hm = np.array([[[144.0, -144.0, 144.00002, np.inf, -np.inf, np.nan, 0.0, -0.0]]], dtype=np.float32)
+    P = UO.unproject_stack(hm)
+    assert engine.unproject(hm) == P.shape[0] == 4
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), P)
+
+
+def test_unproject_device_input_and_sharded_slices(engine):
+    import torch
+
+    D, H, W = 3, 50, 70
+    hm = synth.make_stack(D, H, W, seed=5, n_buildings=4)
+    P = UO.unproject_stack(hm.numpy())
+    assert engine.unproject(hm.cuda()) == P.shape[0]
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), P)
+    # a rank's slice: rows [b, e) of the flattened stack, unaligned start
+    flat = hm.numpy().reshape(-1)
+    b, e = 70 * 13 + 0, 70 * 97
+    n = engine.unproject(flat[b:e], stack_shape=(D, H, W), pix_begin=b)
+    ys, xs = np.divmod(np.arange(b, e) % (H * W), W)
+    ok = UO.valid_mask(flat[b:e])
+    ref = np.stack([xs[ok], ys[ok], flat[b:e][ok]], axis=1).astype(np.float64)
+    assert n == ref.shape[0]
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), ref)
+
+
+def test_unproject_detrend(engine, golden):
+    g = golden("unproject_small.npz")
+    n = engine.unproject(g["disparity"], g["mask"], disparity_scale=-1.0 / 16.0, detrend=True)
+    ref = g["points_detrended"]
+    assert n == ref.shape[0]
+    cloud = engine.get_cloud(False).astype(np.float64)
+    np.testing.assert_array_equal(cloud[:, :2], ref[:, :2])
+    # z is the FP64 plane distance rounded to FP32 (tolerance: 1e-5 absolute on ~100 m heights)
+    np.testing.assert_allclose(cloud[:, 2], ref[:, 2], rtol=0, atol=1e-4)
+    hm = synth.make_stack(2, 200, 300, seed=9).numpy()
+    ref = UO.unproject_stack(hm, detrend=True)
+    assert engine.unproject(hm, detrend=True) == ref.shape[0]
+    np.testing.assert_allclose(engine.get_cloud(False)[:, 2], ref[:, 2], rtol=0, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------
+# K2+K3 single step
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["kmeans_stack_small.npz", "kmeans_c1_like.npz", "kmeans_tol.npz"])
+def test_single_step_golden(engine, golden, name):
+    g = golden(name)
+    n = engine.unproject(g["height_maps"])
+    assert n == int(g["n_points"])
+    labels, sums, counts, n_ref = engine.lloyd_step(g["init"])
+    P = UO.unproject_stack(g["height_maps"])
+    check_labels(P, g["init"], g["step_labels"], labels, allow_near=0)
+    np.testing.assert_array_equal(counts, g["step_counts"].astype(np.int64))
+    c_gpu = sums / np.maximum(counts, 1)[:, None]
+    check_centroids(g["step_centers"], c_gpu, P)
+    print("refined in FP64:", n_ref)
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 16, 64, 255, 256, 257, 300])
+def test_single_step_vs_oracle_many_k(engine, k):
+    hm = synth.make_stack(2, 160, 200, seed=k, n_buildings=8).numpy()
+    P = UO.unproject_stack(hm)
+    P32 = P.astype(np.float32)
+    n = engine.unproject(hm)
+    assert n == P.shape[0]
+    rs = np.random.RandomState(k)
+    C = P[np.sort(rs.choice(n, k, replace=False))] + rs.normal(0, 0.37, size=(k, 3))
+    labels, sums, counts, _ = engine.lloyd_step(C)
+    lab_ref, sums_ref, counts_ref, _ = c_oracle.lloyd_step_f32soa(P32[:, 0], P32[:, 1], P32[:, 2], C)
+    check_labels(P, C, lab_ref, labels)
+    agree = labels == lab_ref
+    if agree.all():
+        np.testing.assert_array_equal(counts, counts_ref.astype(np.int64))
+        scale = np.abs(P).max(axis=0) * np.maximum(counts_ref, 1)[:, None]
+        assert (np.abs(sums - sums_ref) / scale).max() < 1e-6
+
+
+def test_single_step_exact_ties_lowest_index(engine):
+    # points exactly equidistant from two centroids: strict '<' keeps the lower index (pyx:205-213)
+    pts = np.array([[0.0, 0, 0], [2.0, 0, 0], [1.0, 0, 0], [1.0, 5, 0], [1.0, -3, 2]], dtype=np.float32)
+    engine.set_points(pts)
+    C = np.array([[0.0, 0, 0], [2.0, 0, 0]])
+    labels, sums, counts, n_ref = engine.lloyd_step(C)
+    assert labels.tolist() == [0, 1, 0, 0, 0]
+    assert n_ref >= 3  # the three ties were decided by the FP64 refine
+    labels, _, _, _ = engine.lloyd_step(C[::-1].copy())
+    assert labels.tolist() == [1, 0, 0, 0, 0]
+    # duplicated centroids: all points go to the first copy
+    labels, _, counts, _ = engine.lloyd_step(np.array([[1.0, 0, 0], [1.0, 0, 0], [1.0, 0, 0]]))
+    assert labels.tolist() == [0] * 5 and counts.tolist() == [5, 0, 0]
+
+
+def test_generic_float_cloud_random_order(engine):
+    rs = np.random.RandomState(4)
+    X32 = np.concatenate([rs.normal(c, 3.0, (5000, 3)) for c in rs.uniform(-1e3, 1e3, size=(9, 3))]).astype(np.float32)
+    X32 = X32[rs.permutation(X32.shape[0])]
+    X32 += np.array([2.5e4, -3.1e4, 512.0], dtype=np.float32)  # far from the origin
+    X = X32.astype(np.float64)
+    engine.set_points(X32)
+    C = X[rs.choice(X.shape[0], 33, replace=False)]
+    labels, sums, counts, _ = engine.lloyd_step(C)
+    lab_ref, sums_ref, counts_ref, _ = c_oracle.lloyd_step_f32soa(X32[:, 0], X32[:, 1], X32[:, 2], C)
+    check_labels(X, C, lab_ref, labels)
+    if (labels == lab_ref).all():
+        np.testing.assert_array_equal(counts, counts_ref.astype(np.int64))
+    c_gpu = sums / np.maximum(counts, 1)[:, None]
+    c_ref = sums_ref / np.maximum(counts_ref, 1)[:, None]
+    check_centroids(c_ref, c_gpu, X)
+
+
+# ---------------------------------------------------------------------------------------
+# full fit
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["kmeans_stack_small.npz", "kmeans_c1_like.npz", "kmeans_tol.npz"])
+def test_fit_golden(engine, golden, name):
+    g = golden(name)
+    engine.unproject(g["height_maps"])
+    r = engine.fit(g["init"], max_iter=int(g["max_iter"]), tol=float(g["tol"]))
+    P = UO.unproject_stack(g["height_maps"])
+    assert r["n_iter"] == int(g["n_iter"])
+    check_labels(P, g["centers"], g["labels"], r["labels"])
+    check_centroids(g["centers"], r["centers"], P)
+    np.testing.assert_allclose(r["inertia"], float(g["inertia"]), rtol=1e-6)
+
+
+def test_fit_relocation_golden(engine, golden):
+    g = golden("kmeans_relocate.npz")
+    engine.set_points(g["X"])
+    r = engine.fit(g["init"], max_iter=100, tol=0.0)
+    assert r["n_relocations"] >= 1
+    X = g["X"].astype(np.float64)
+    assert r["n_iter"] == int(g["n_iter"])
+    np.testing.assert_allclose(r["inertia"], float(g["inertia"]), rtol=1e-6)
+    check_labels(X, g["centers"], g["labels"], r["labels"])
+    check_centroids(g["centers"], r["centers"], X)
+
+
+def test_fit_sklearn_known_answers(engine):
+    # sklearn/cluster/tests/test_k_means.py:85-111, padded to d = 3 (unit weights)
+    X = np.array([[0, 0, 0], [0.5, 0, 0], [0.5, 1, 0], [1, 1, 0]], dtype=np.float32)
+    engine.set_points(X)
+    r = engine.fit(np.array([[0.5, 0.5, 0], [3, 3, 0]], dtype=np.float64), max_iter=300, tol=1e-4)
+    np.testing.assert_allclose(r["inertia"], 0.25, rtol=1e-9)
+    assert r["n_iter"] == 3
+    a = r["labels"].tolist() == [0, 0, 1, 1] and np.allclose(r["centers"], [[0.25, 0, 0], [0.75, 1, 0]])
+    b = r["labels"].tolist() == [1, 1, 0, 0] and np.allclose(r["centers"], [[0.75, 1, 0], [0.25, 0, 0]])
+    assert a or b
+
+
+def test_fit_config1_vs_oracle(engine):
+    """BASELINE.json configs[0]: 3-day 512x512 stack, k=8, 20 Lloyd iterations."""
+    hm = synth.make_stack(3, 512, 512, seed=0).numpy()
+    P = UO.unproject_stack(hm)
+    n = engine.unproject(hm)
+    assert n == P.shape[0]
+    init = synth.init_from_points(P.astype(np.float32), 8, 0)
+    r = engine.fit(init, max_iter=20, tol=0.0)
+    ref = KO.kmeans_fit(P, init, max_iter=20, tol=0.0)
+    assert r["n_iter"] == ref["n_iter"]
+    check_labels(P, ref["centers"], ref["labels"], r["labels"])
+    check_centroids(ref["centers"], r["centers"], P)
+    np.testing.assert_allclose(r["inertia"], ref["inertia"], rtol=1e-6)
+    print("n_refined", r["n_refined"], "of", n * r["n_iter"])
+
+
+def test_fit_is_deterministic_and_idempotent(engine):
+    hm = synth.make_stack(2, 300, 400, seed=3).numpy()
+    n = engine.unproject(hm)
+    P32 = engine.get_cloud(False)
+    init = synth.init_from_points(P32, 12, 3)
+    a = engine.fit(init, max_iter=15, tol=0.0)
+    b = engine.fit(init, max_iter=15, tol=0.0)
+    assert np.array_equal(a["labels"], b["labels"])
+    assert a["centers"].tobytes() == b["centers"].tobytes()  # bitwise
+    assert a["inertia"] == b["inertia"] and a["n_iter"] == b["n_iter"]
+    # converge, then restart from the converged centroids: one iteration, nothing moves
+    c = engine.fit(init, max_iter=300, tol=0.0)
+    d = engine.fit(c["centers"], max_iter=300, tol=0.0)
+    assert d["n_iter"] <= 2
+    assert np.array_equal(c["labels"], d["labels"])
+    np.testing.assert_allclose(c["centers"], d["centers"], rtol=0, atol=1e-9)
+    assert n == a["labels"].shape[0]
+
+
+def test_fit_errors(engine):
+    engine.set_points(np.zeros((3, 3), dtype=np.float32))
+    with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):
+        engine.fit(np.zeros((4, 3)))
+    with pytest.raises(Exception):
+        engine.fit(np.zeros((2, 3)), max_iter=0)
+    r = engine.fit(np.array([[1.0, 1, 1]]), max_iter=5, tol=0.0)  # k = 1
+    assert r["labels"].tolist() == [0, 0, 0] and np.allclose(r["centers"], 0)
+
+
+# ---------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: 10 x 2048 x 2048, k = 16)
+# ---------------------------------------------------------------------------------------
+def test_config2_full_size_single_step(engine):
+    import torch
+
+    D, H, W, k = 10, 2048, 2048, 16
+    hm = synth.make_stack(D, H, W, seed=0, device="cuda")
+    n = engine.unproject(hm)
+    hm_h = hm.cpu().numpy()
+    del hm
+    torch.cuda.empty_cache()
+    ok = UO.valid_mask(hm_h)
+    assert n == int(ok.sum())
+    cloud = engine.get_cloud(False)
+    # np.where order: spot-check against the oracle on the first and last day
+    P0 = UO.unproject_stack(hm_h[:1])
+    np.testing.assert_array_equal(cloud[: P0.shape[0]].astype(np.float64), P0)
+    Pl = UO.unproject_stack(hm_h[-1:])
+    np.testing.assert_array_equal(cloud[-Pl.shape[0]:].astype(np.float64), Pl)
+    init = synth.init_from_points(cloud, k, 0)
+    labels, sums, counts, n_ref = engine.lloyd_step(init)
+    lab_ref, sums_ref, counts_ref, _ = c_oracle.lloyd_step_f32soa(
+        np.ascontiguousarray(cloud[:, 0]), np.ascontiguousarray(cloud[:, 1]),
+        np.ascontiguousarray(cloud[:, 2]), init)
+    bad = np.nonzero(labels != lab_ref)[0]
+    print("full-size step: mismatches", bad.size, "refined", n_ref, "of", n)
+    r = KO.compare_labels(cloud[bad].astype(np.float64), init, lab_ref[bad], labels[bad])
+    assert r["n_hard"] == 0, r
+    assert counts.sum() == n
+    if bad.size == 0:
+        np.testing.assert_array_equal(counts, counts_ref.astype(np.int64))
+    c_gpu = sums / counts[:, None]
+    c_ref = sums_ref / counts_ref[:, None]
+    std = np.array([cloud[:, i].std(dtype=np.float64) for i in range(3)])
+    err = (np.abs(c_gpu - c_ref) / np.maximum(np.abs(c_ref), std)).max()
+    print("full-size centroid rel err", err)
+    assert err < CENTROID_TOL
+    # checksum-of-sums property: total of the per-cluster sums equals the column sums
+    col = np.array([cloud[:, i].sum(dtype=np.float64) for i in range(3)])
+    np.testing.assert_allclose(sums.sum(axis=0), col, rtol=1e-9)
