@@ -9,7 +9,16 @@
 //   lloyd_final_kernel  final E-step when the exit was not strict + inertia + int32 labels
 //                       (sklearn/cluster/_kmeans.py:742-756, _k_means_common.pyx:94-124)
 //
+// Work unit: a warp-group of 128 consecutive points (32 lanes x one float4 per coordinate
+// array, 16 B per lane, fully coalesced).  Everything inside a group is warp-synchronous:
+// no CTA barrier in the streaming loop.
+//
 // Numerics (DESIGN.md "Exactness"):
+//   * candidate pruning: the group's bounding box gives, for every centroid, a lower and an
+//     upper bound of the distance to any point of the group; a centroid whose lower bound
+//     exceeds the smallest upper bound (plus a margin covering every FP32 rounding involved)
+//     cannot be the nearest of any point in the group and is skipped.  Conservative, so the
+//     result is identical to brute force; on raster-ordered clouds it leaves 1-3 candidates.
 //   * distances: FP32 CUDA cores, expanded form  ||c'||^2 - 2 x'.c'  (3 FFMA per pair) in a
 //     frame whose origin makes pixel-grid coordinates exact.  A rigorous bound E on the
 //     FP32 error of that expression is carried with every centroid table; a point whose best
@@ -25,12 +34,14 @@
 
 namespace mdkm {
 
+constexpr int kGroup = 128;  // points per warp-group
+
 struct StepParams {
   const float* x;
   const float* y;
   const float* z;
   long long n;
-  void* labels;               // uint8 (k <= 256) or uint16, n rounded up to the tile
+  void* labels;               // uint8 (k <= 256) or uint16, n rounded up to the group
   const unsigned char* table; // centroid table (see common.cuh)
   unsigned long long* acc;    // [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed
   DevStatus* st;
@@ -62,44 +73,126 @@ __device__ __forceinline__ double4 ld_c64(const double4* p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// ---------------------------------------------------------------------------------------
-// Assignment of P points held in registers.  xc/yc/zc are centred FP32 coordinates,
-// xo/yo/zo the original ones (for the FP64 refine).  Returns labels in lab[].
-// ---------------------------------------------------------------------------------------
-template <int P>
-__device__ __forceinline__ void assign_points(const float (&xc)[P], const float (&yc)[P],
-                                              const float (&zc)[P], const float (&xo)[P],
-                                              const float (&yo)[P], const float (&zo)[P],
-                                              const float4* __restrict__ s_c,
-                                              const double4* __restrict__ c64, int k, int kpad,
-                                              float thresh, const FrameF& f, int (&lab)[P],
-                                              unsigned int& n_refined) {
-  float best[P], second[P];
+// One warp-group of points in registers (4 consecutive points per lane).
+struct GroupRegs {
+  float x[4], y[4], z[4];
+};
+
+// Loads group g (points [128 g, 128 g + 128)).  Indices beyond n-1 are clamped to the last
+// point, so a partial tail group sees only real coordinates (its extra lanes are masked out
+// of the sums by the caller).
+__device__ __forceinline__ void load_group(const float* __restrict__ x, const float* __restrict__ y,
+                                           const float* __restrict__ z, long long n, long long g,
+                                           int lane, GroupRegs& r) {
+  const long long i0 = g * kGroup + lane * 4;
+  if (i0 + 3 < n) {
+    const float4 vx = ldg_stream_f4(x + i0), vy = ldg_stream_f4(y + i0), vz = ldg_stream_f4(z + i0);
+    r.x[0] = vx.x; r.x[1] = vx.y; r.x[2] = vx.z; r.x[3] = vx.w;
+    r.y[0] = vy.x; r.y[1] = vy.y; r.y[2] = vy.z; r.y[3] = vy.w;
+    r.z[0] = vz.x; r.z[1] = vz.y; r.z[2] = vz.z; r.z[3] = vz.w;
+  } else {
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    best[p] = __int_as_float(0x7f800000);
-    second[p] = __int_as_float(0x7f800000);
-    lab[p] = 0;
-  }
-#pragma unroll 4
-  for (int j = 0; j < kpad; ++j) {
-    const float4 c = s_c[j];  // LDS.128, warp broadcast
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float d = fmaf(xc[p], c.x, fmaf(yc[p], c.y, fmaf(zc[p], c.z, c.w)));
-      const bool lt = d < best[p];  // strict: lowest index wins ties (pyx:205-213)
-      second[p] = fminf(second[p], fmaxf(d, best[p]));
-      best[p] = fminf(best[p], d);
-      lab[p] = lt ? j : lab[p];
+    for (int e = 0; e < 4; ++e) {
+      long long i = i0 + e;
+      i = i < n ? i : n - 1;
+      r.x[e] = __ldg(x + i);
+      r.y[e] = __ldg(y + i);
+      r.z[e] = __ldg(z + i);
     }
   }
-  // FP64 refine of the points the FP32 pass cannot decide (rare; see file header).
+}
+
+// ---------------------------------------------------------------------------------------
+// Assignment of one warp-group.  s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0)
+// rows (padding rows hold 1e18 so that they are never candidates).  Warp-synchronous: all 32
+// lanes must call it.  Returns the 4 labels of this lane's points.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void assign_group(const GroupRegs& r, const float4* __restrict__ s_fast,
+                                             const float4* __restrict__ s_plain,
+                                             const double4* __restrict__ c64, int k, int kpad,
+                                             float thresh, const FrameF& f, int lane, int (&lab)[4],
+                                             unsigned int& n_refined) {
+  float xc[4], yc[4], zc[4];
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    if (!(second[p] - best[p] > thresh)) {
-      const double X = (double)xo[p] - (double)f.ox;
-      const double Y = (double)yo[p] - (double)f.oy;
-      const double Z = (double)zo[p] - (double)f.oz;
+  for (int e = 0; e < 4; ++e) {
+    xc[e] = r.x[e] - f.ox;
+    yc[e] = r.y[e] - f.oy;
+    zc[e] = r.z[e] - f.oz;
+  }
+  // bounding box of the group (FMNMX3 + CREDUX.F32)
+  const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
+  const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
+  const float by0 = redux_min_f32(fminf(fminf(yc[0], yc[1]), fminf(yc[2], yc[3])));
+  const float by1 = redux_max_f32(fmaxf(fmaxf(yc[0], yc[1]), fmaxf(yc[2], yc[3])));
+  const float bz0 = redux_min_f32(fminf(fminf(zc[0], zc[1]), fminf(zc[2], zc[3])));
+  const float bz1 = redux_max_f32(fmaxf(fmaxf(zc[0], zc[1]), fmaxf(zc[2], zc[3])));
+
+  // pass 1: smallest upper bound  min_j max_{x in box} |x - c_j|^2
+  float ub = __int_as_float(0x7f800000);
+  for (int j = lane; j < kpad; j += 32) {
+    const float4 c = s_plain[j];
+    const float hx = fmaxf(c.x - bx0, bx1 - c.x);
+    const float hy = fmaxf(c.y - by0, by1 - c.y);
+    const float hz = fmaxf(c.z - bz0, bz1 - c.z);
+    ub = fminf(ub, fmaf(hx, hx, fmaf(hy, hy, hz * hz)));
+  }
+  ub = redux_min_f32(ub);
+  // margin: relative slack for the FP32 box arithmetic + 2*thresh (= 4E) for the rounding of
+  // the centroid rows and of the fast distances themselves
+  const float bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
+
+  float best[4], second[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    best[e] = __int_as_float(0x7f800000);
+    second[e] = __int_as_float(0x7f800000);
+    lab[e] = 0;
+  }
+  int first = -1;
+  bool evaluated = false;
+  // pass 2: candidates by lower bound, evaluated in ascending index (strict '<' keeps the
+  // lowest index on ties, pyx:205-213)
+  for (int base = 0; base < kpad; base += 32) {
+    const float4 c = s_plain[base + lane];  // kpad is a multiple of 32 rows in shared memory
+    const float lx = fmaxf(fmaxf(bx0 - c.x, c.x - bx1), 0.0f);
+    const float ly = fmaxf(fmaxf(by0 - c.y, c.y - by1), 0.0f);
+    const float lz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
+    const float lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+    unsigned int mask = __ballot_sync(0xffffffffu, lb <= bound);
+    while (mask) {
+      const int jj = base + (__ffs(mask) - 1);
+      mask &= mask - 1;
+      if (first < 0) {
+        first = jj;  // evaluation deferred: a lone candidate needs none
+        continue;
+      }
+      for (int pass = evaluated ? 1 : 0; pass < 2; ++pass) {
+        const int j = pass ? jj : first;
+        const float4 cf = s_fast[j];  // LDS.128, warp broadcast
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
+          const bool lt = d < best[e];
+          second[e] = fminf(second[e], fmaxf(d, best[e]));
+          best[e] = fminf(best[e], d);
+          lab[e] = lt ? j : lab[e];
+        }
+      }
+      evaluated = true;
+    }
+  }
+  if (!evaluated) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lab[e] = first;
+    return;
+  }
+  // FP64 refine of the points the FP32 pass cannot decide (rare; see file header)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (!(second[e] - best[e] > thresh)) {
+      const double X = (double)r.x[e] - (double)f.ox;
+      const double Y = (double)r.y[e] - (double)f.oy;
+      const double Z = (double)r.z[e] - (double)f.oz;
       double bd = 1.0 / 0.0;
       int bi = 0;
       for (int j = 0; j < k; ++j) {
@@ -110,21 +203,9 @@ __device__ __forceinline__ void assign_points(const float (&xc)[P], const float 
           bi = j;
         }
       }
-      lab[p] = bi;
+      lab[e] = bi;
       ++n_refined;
     }
-  }
-}
-
-// Flush one per-thread run (label, biased sums, count) into the CTA's shared accumulators.
-__device__ __forceinline__ void flush_run(unsigned long long* s_acc, int lab, unsigned int ax,
-                                          unsigned int ay, unsigned int az, int an) {
-  if (an > 0) {
-    const unsigned int m = (unsigned int)an * kMagicBits;
-    atomicAdd(&s_acc[lab * 4 + 0], (unsigned long long)(long long)(int)(ax - m));
-    atomicAdd(&s_acc[lab * 4 + 1], (unsigned long long)(long long)(int)(ay - m));
-    atomicAdd(&s_acc[lab * 4 + 2], (unsigned long long)(long long)(int)(az - m));
-    atomicAdd(&s_acc[lab * 4 + 3], (unsigned long long)an);
   }
 }
 
@@ -136,10 +217,13 @@ struct LabPack<unsigned char> {
   static __device__ __forceinline__ V load(const unsigned char* p) {
     return *reinterpret_cast<const unsigned int*>(p);
   }
-  static __device__ __forceinline__ void store(unsigned char* p, const int (&l)[4]) {
-    *reinterpret_cast<unsigned int*>(p) =
-        (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
+  static __device__ __forceinline__ V pack(const int (&l)[4]) {
+    return (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
   }
+  static __device__ __forceinline__ void store(unsigned char* p, V v) {
+    *reinterpret_cast<unsigned int*>(p) = v;
+  }
+  static __device__ __forceinline__ bool same(V a, V b) { return a == b; }
   static __device__ __forceinline__ int get(V v, int e) { return (v >> (8 * e)) & 0xff; }
 };
 template <>
@@ -148,38 +232,66 @@ struct LabPack<unsigned short> {
   static __device__ __forceinline__ V load(const unsigned short* p) {
     return *reinterpret_cast<const uint2*>(p);
   }
-  static __device__ __forceinline__ void store(unsigned short* p, const int (&l)[4]) {
+  static __device__ __forceinline__ V pack(const int (&l)[4]) {
     uint2 v;
     v.x = (unsigned)l[0] | ((unsigned)l[1] << 16);
     v.y = (unsigned)l[2] | ((unsigned)l[3] << 16);
-    *reinterpret_cast<uint2*>(p) = v;
+    return v;
   }
+  static __device__ __forceinline__ void store(unsigned short* p, V v) { *reinterpret_cast<uint2*>(p) = v; }
+  static __device__ __forceinline__ bool same(V a, V b) { return a.x == b.x && a.y == b.y; }
   static __device__ __forceinline__ int get(V v, int e) {
     const unsigned w = (e < 2) ? v.x : v.y;
     return (w >> (16 * (e & 1))) & 0xffff;
   }
 };
 
+__device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long long sx, long long sy,
+                                        long long sz, unsigned int cnt) {
+  atomicAdd(&s_acc[lab * 4 + 0], (unsigned long long)sx);
+  atomicAdd(&s_acc[lab * 4 + 1], (unsigned long long)sy);
+  atomicAdd(&s_acc[lab * 4 + 2], (unsigned long long)sz);
+  atomicAdd(&s_acc[lab * 4 + 3], (unsigned long long)cnt);
+}
+
+// Segmented warp reduction for a group that is not label-uniform: one round per distinct label
+// among the lanes' values (v valid for lanes with `active`), leader lane adds to shared memory.
+__device__ __forceinline__ void warp_segmented_add(unsigned long long* s_acc, bool active, int l, int qx,
+                                                   int qy, int qz, int cnt, int lane) {
+  unsigned int todo = __ballot_sync(0xffffffffu, active);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int ll = __shfl_sync(0xffffffffu, l, leader);
+    const bool mine = active && (l == ll);
+    const unsigned int peers = __ballot_sync(0xffffffffu, mine);
+    const int sx = __reduce_add_sync(0xffffffffu, mine ? qx : 0);
+    const int sy = __reduce_add_sync(0xffffffffu, mine ? qy : 0);
+    const int sz = __reduce_add_sync(0xffffffffu, mine ? qz : 0);
+    const int sc = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
+    if (lane == leader) acc_add(s_acc, ll, sx, sy, sz, (unsigned int)sc);
+    todo &= ~peers;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
-// K2 + K3: assignment and per-cluster sums in one pass.  G float4 groups per thread.
-// Tile = kThreads * 4 * G consecutive points; group g of a tile is kThreads*4 consecutive
-// points, thread t owns points [4t, 4t+4) of each group (coalesced 16 B per lane).
+// K2 + K3: assignment and per-cluster sums in one pass.
 // ---------------------------------------------------------------------------------------
-template <typename LabT, int G>
+template <typename LabT>
 __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParams p) {
-  constexpr int P = 4 * G;
-  constexpr int TILE = kThreads * P;
   if (!p.ignore_status && (p.st->done | p.st->paused)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* s_c = reinterpret_cast<float4*>(smem_raw);
-  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)p.kpad * 16);
+  const int kp32 = (p.kpad + 31) & ~31;  // rows staged in shared memory (multiple of 32)
+  float4* s_fast = reinterpret_cast<float4*>(smem_raw);
+  float4* s_plain = s_fast + kp32;
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_plain + kp32);
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ unsigned int s_changed;
   __shared__ unsigned int s_refined;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
@@ -187,16 +299,35 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
     s_refined = 0;
   }
   for (int i = tid; i < p.kpad * 4; i += kThreads) s_acc[i] = 0ull;
+  // rows [kpad, kp32) are not covered by the bulk copies: make them non-candidates
+  for (int i = p.kpad + tid; i < kp32; i += kThreads) {
+    s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    s_plain[i] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+  }
   __syncthreads();
   if (tid == 0) {
-    // centroid fast rows: global -> shared through the TMA unit (1-D bulk copy)
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
-    tma_load_1d(s_c, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    // centroid rows: global -> shared through the TMA unit (two 1-D bulk copies, one barrier)
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 32u);
+    tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    tma_load_1d(s_plain, p.table + (size_t)p.kpad * 16, (uint32_t)p.kpad * 16u, &s_bar);
   }
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 16);
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);
   const float thresh = p.st->thresh;
-  const bool first = p.st->first != 0;
+  const bool first_iter = p.st->first != 0;
   const FrameF f = p.f;
+  LabT* labels = reinterpret_cast<LabT*>(p.labels);
+
+  const long long n_groups = (p.n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  long long g = (long long)blockIdx.x * (kThreads / 32) + warp;
+
+  // software pipeline: the next group's loads are in flight while the current one is processed
+  GroupRegs cur, nxt;
+  typename LabPack<LabT>::V old_cur = {}, old_nxt = {};
+  if (g < n_groups) {
+    load_group(p.x, p.y, p.z, p.n, g, lane, cur);
+    old_cur = LabPack<LabT>::load(labels + g * kGroup + lane * 4);
+  }
   mbar_wait(&s_bar, 0);
 
   // warp-level run accumulator (identical in every lane)
@@ -204,104 +335,71 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
   unsigned int wn = 0;
   int wlab = -1;
   unsigned int n_chg = 0, n_ref = 0;
-  LabT* labels = reinterpret_cast<LabT*>(p.labels);
 
-  const long long n_tiles = (p.n + TILE - 1) / TILE;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long base = tile * (long long)TILE;
-    float xo[P], yo[P], zo[P];
-    typename LabPack<LabT>::V oldl[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const long long i0 = base + (long long)g * (kThreads * 4) + tid * 4;
-      const float4 vx = ldg_stream_f4(p.x + i0);
-      const float4 vy = ldg_stream_f4(p.y + i0);
-      const float4 vz = ldg_stream_f4(p.z + i0);
-      xo[4 * g + 0] = vx.x; xo[4 * g + 1] = vx.y; xo[4 * g + 2] = vx.z; xo[4 * g + 3] = vx.w;
-      yo[4 * g + 0] = vy.x; yo[4 * g + 1] = vy.y; yo[4 * g + 2] = vy.z; yo[4 * g + 3] = vy.w;
-      zo[4 * g + 0] = vz.x; zo[4 * g + 1] = vz.y; zo[4 * g + 2] = vz.z; zo[4 * g + 3] = vz.w;
-      oldl[g] = LabPack<LabT>::load(labels + i0);
+  for (; g < n_groups; g += stride) {
+    const long long gn = g + stride;
+    if (gn < n_groups) {
+      load_group(p.x, p.y, p.z, p.n, gn, lane, nxt);
+      old_nxt = LabPack<LabT>::load(labels + gn * kGroup + lane * 4);
     }
-    float xc[P], yc[P], zc[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-      xc[q] = xo[q] - f.ox;
-      yc[q] = yo[q] - f.oy;
-      zc[q] = zo[q] - f.oz;
-    }
-    int lab[P];
-    assign_points<P>(xc, yc, zc, xo, yo, zo, s_c, c64, p.k, p.kpad, thresh, f, lab, n_ref);
+    int lab[4];
+    assign_group(cur, s_fast, s_plain, c64, p.k, p.kpad, thresh, f, lane, lab, n_ref);
 
-    const bool full_tile = (base + TILE <= p.n);
-    // labels out + changed count
+    const long long i0 = g * kGroup + lane * 4;
+    const bool full = (g + 1) * kGroup <= p.n;  // warp-uniform
+    const typename LabPack<LabT>::V newl = LabPack<LabT>::pack(lab);
+    LabPack<LabT>::store(labels + i0, newl);
+    if (first_iter) {
+      n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - i0));
+    } else if (!LabPack<LabT>::same(newl, old_cur)) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const long long i0 = base + (long long)g * (kThreads * 4) + tid * 4;
-      int l4[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        l4[e] = lab[4 * g + e];
-        const bool valid = full_tile || (i0 + e < p.n);
-        n_chg += (valid && (first || l4[e] != LabPack<LabT>::get(oldl[g], e))) ? 1u : 0u;
-      }
-      LabPack<LabT>::store(labels + i0, l4);
+      for (int e = 0; e < 4; ++e)
+        n_chg += ((full || i0 + e < p.n) && lab[e] != LabPack<LabT>::get(old_cur, e)) ? 1u : 0u;
     }
 
-    // per-thread runs of equal labels -> warp aggregate -> shared accumulators
-    int cur = lab[0];
-    unsigned int ax = 0, ay = 0, az = 0;
-    int an = 0;
-    bool single = true;
+    // fixed-point coordinates: q = rint(x' * scale) by mantissa alignment (|q| < 2^22):
+    // bits(x'*s + 1.5*2^23) - bits(1.5*2^23)
+    int qx[4], qy[4], qz[4];
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-      const long long i = base + (long long)(q >> 2) * (kThreads * 4) + tid * 4 + (q & 3);
-      if (full_tile || i < p.n) {
-        if (lab[q] != cur) {
-          flush_run(s_acc, cur, ax, ay, az, an);
-          single = false;
-          cur = lab[q];
-          ax = ay = az = 0;
-          an = 0;
+    for (int e = 0; e < 4; ++e) {
+      qx[e] = (int)(__float_as_uint(fmaf(cur.x[e] - f.ox, f.sx, kMagic)) - kMagicBits);
+      qy[e] = (int)(__float_as_uint(fmaf(cur.y[e] - f.oy, f.sy, kMagic)) - kMagicBits);
+      qz[e] = (int)(__float_as_uint(fmaf(cur.z[e] - f.oz, f.sz, kMagic)) - kMagicBits);
+    }
+    const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
+    const int l0 = __shfl_sync(0xffffffffu, lab[0], 0);
+    const bool all_t_uni = __all_sync(0xffffffffu, t_uni) && full;
+    if (all_t_uni) {
+      const int tx = qx[0] + qx[1] + qx[2] + qx[3];
+      const int ty = qy[0] + qy[1] + qy[2] + qy[3];
+      const int tz = qz[0] + qz[1] + qz[2] + qz[3];
+      if (__all_sync(0xffffffffu, lab[0] == l0)) {
+        // the whole group has one label: three REDUX + register accumulation
+        const int sx = __reduce_add_sync(0xffffffffu, tx);
+        const int sy = __reduce_add_sync(0xffffffffu, ty);
+        const int sz = __reduce_add_sync(0xffffffffu, tz);
+        if (l0 != wlab) {
+          if (lane == 0 && wn > 0) acc_add(s_acc, wlab, wx, wy, wz, wn);
+          wx = wy = wz = 0;
+          wn = 0;
+          wlab = l0;
         }
-        // q = rint(x' * scale) by mantissa alignment (|q| < 2^22): bits(x'*s + 1.5*2^23) - bits(1.5*2^23)
-        ax += __float_as_uint(fmaf(xc[q], f.sx, kMagic));
-        ay += __float_as_uint(fmaf(yc[q], f.sy, kMagic));
-        az += __float_as_uint(fmaf(zc[q], f.sz, kMagic));
-        ++an;
+        wx += sx;
+        wy += sy;
+        wz += sz;
+        wn += kGroup;
+      } else {
+        warp_segmented_add(s_acc, true, lab[0], tx, ty, tz, 4, lane);
       }
-    }
-    const int l0 = __shfl_sync(0xffffffffu, cur, 0);
-    const bool uni = __all_sync(0xffffffffu, single && cur == l0 && an == P);
-    if (uni) {
-      const unsigned int m = (unsigned int)P * kMagicBits;
-      const int sx = __reduce_add_sync(0xffffffffu, (int)(ax - m));
-      const int sy = __reduce_add_sync(0xffffffffu, (int)(ay - m));
-      const int sz = __reduce_add_sync(0xffffffffu, (int)(az - m));
-      if (l0 != wlab) {
-        if (lane == 0 && wn > 0) {
-          atomicAdd(&s_acc[wlab * 4 + 0], (unsigned long long)wx);
-          atomicAdd(&s_acc[wlab * 4 + 1], (unsigned long long)wy);
-          atomicAdd(&s_acc[wlab * 4 + 2], (unsigned long long)wz);
-          atomicAdd(&s_acc[wlab * 4 + 3], (unsigned long long)wn);
-        }
-        wx = wy = wz = 0;
-        wn = 0;
-        wlab = l0;
-      }
-      wx += sx;
-      wy += sy;
-      wz += sz;
-      wn += 32u * P;
     } else {
-      flush_run(s_acc, cur, ax, ay, az, an);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        warp_segmented_add(s_acc, full || (i0 + e < p.n), lab[e], qx[e], qy[e], qz[e], 1, lane);
     }
+    cur = nxt;
+    old_cur = old_nxt;
   }
-  if (lane == 0 && wn > 0) {
-    atomicAdd(&s_acc[wlab * 4 + 0], (unsigned long long)wx);
-    atomicAdd(&s_acc[wlab * 4 + 1], (unsigned long long)wy);
-    atomicAdd(&s_acc[wlab * 4 + 2], (unsigned long long)wz);
-    atomicAdd(&s_acc[wlab * 4 + 3], (unsigned long long)wn);
-  }
+  if (lane == 0 && wn > 0) acc_add(s_acc, wlab, wx, wy, wz, wn);
   n_chg = __reduce_add_sync(0xffffffffu, n_chg);
   n_ref = __reduce_add_sync(0xffffffffu, n_ref);
   if (lane == 0) {
@@ -392,7 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
   const int jmax = kMaxK * 2 - 1 - (int)(s_maxcnt & 0x1fffull);
 
   float4* fast = reinterpret_cast<float4*>(u.table);
-  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 16);
+  float4* plain = fast + u.kpad;
+  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 32);
 
   double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
   for (int j = tid; j < u.kpad; j += kThreads) {
@@ -429,12 +528,14 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
       const double cn = cx * cx + cy * cy + cz * cz;
       exact[j] = make_double4(cx, cy, cz, cn);
       fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
+      plain[j] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
       m_cn = fmax(m_cn, cn);
       m_cx = fmax(m_cx, fabs(cx));
       m_cy = fmax(m_cy, fabs(cy));
       m_cz = fmax(m_cz, fabs(cz));
     } else {
       fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+      plain[j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
@@ -481,7 +582,8 @@ struct InitTableParams {
 __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTableParams u) {
   __shared__ double s_red[kThreads / 32];
   float4* fast = reinterpret_cast<float4*>(u.table);
-  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 16);
+  float4* plain = fast + u.kpad;
+  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 32);
   double m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
   for (int j = threadIdx.x; j < u.kpad; j += kThreads) {
     if (j < u.k) {
@@ -491,12 +593,14 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
       const double cn = cx * cx + cy * cy + cz * cz;
       exact[j] = make_double4(cx, cy, cz, cn);
       fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
+      plain[j] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
       m_cn = fmax(m_cn, cn);
       m_cx = fmax(m_cx, fabs(cx));
       m_cy = fmax(m_cy, fabs(cy));
       m_cz = fmax(m_cz, fabs(cz));
     } else {
       fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+      plain[j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
@@ -515,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
 // Reads the table back as K x 3 float64 centroids in original coordinates.
 __global__ void read_table_kernel(const unsigned char* table, int k, int kpad, Frame fr,
                                   double* centers_out) {
-  const double4* exact = reinterpret_cast<const double4*>(table + (size_t)kpad * 16);
+  const double4* exact = reinterpret_cast<const double4*>(table + (size_t)kpad * 32);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const double4 c = exact[j];
     centers_out[3 * j + 0] = c.x + fr.origin[0];
@@ -540,27 +644,34 @@ __global__ void read_sums_kernel(const unsigned long long* acc, int k, Frame fr,
 // strict) and inertia in FP64 (direct form, fixed-order reduction).
 // ---------------------------------------------------------------------------------------
 template <typename LabT>
-__global__ void __launch_bounds__(kThreads, 2) lloyd_final_kernel(const FinalParams p) {
-  constexpr int P = 4;
-  constexpr int TILE = kThreads * P;
+__global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* s_c = reinterpret_cast<float4*>(smem_raw);
+  const int kp32 = (p.kpad + 31) & ~31;
+  float4* s_fast = reinterpret_cast<float4*>(smem_raw);
+  float4* s_plain = s_fast + kp32;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ double s_red[kThreads / 32];
   __shared__ unsigned int s_refined;
   __shared__ bool s_last;
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
     s_refined = 0;
   }
+  for (int i = p.kpad + tid; i < kp32; i += kThreads) {
+    s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    s_plain[i] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+  }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
-    tma_load_1d(s_c, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 32u);
+    tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    tma_load_1d(s_plain, p.table + (size_t)p.kpad * 16, (uint32_t)p.kpad * 16u, &s_bar);
   }
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 16);
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);
   const float thresh = p.st->thresh;
   const bool reassign = p.force_assign || !p.st->strict;
   const FrameF f = p.f;
@@ -569,37 +680,27 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_final_kernel(const FinalPar
 
   double inert = 0.0;
   unsigned int n_ref = 0;
-  const long long n_tiles = (p.n + TILE - 1) / TILE;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long i0 = tile * (long long)TILE + tid * 4;
-    const float4 vx = ldg_stream_f4(p.x + i0);
-    const float4 vy = ldg_stream_f4(p.y + i0);
-    const float4 vz = ldg_stream_f4(p.z + i0);
-    const float xo[P] = {vx.x, vx.y, vx.z, vx.w};
-    const float yo[P] = {vy.x, vy.y, vy.z, vy.w};
-    const float zo[P] = {vz.x, vz.y, vz.z, vz.w};
-    int lab[P];
+  const long long n_groups = (p.n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + warp; g < n_groups; g += stride) {
+    GroupRegs r;
+    load_group(p.x, p.y, p.z, p.n, g, lane, r);
+    const long long i0 = g * kGroup + lane * 4;
+    int lab[4];
     if (reassign) {
-      float xc[P], yc[P], zc[P];
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        xc[q] = xo[q] - f.ox;
-        yc[q] = yo[q] - f.oy;
-        zc[q] = zo[q] - f.oz;
-      }
-      assign_points<P>(xc, yc, zc, xo, yo, zo, s_c, c64, p.k, p.kpad, thresh, f, lab, n_ref);
+      assign_group(r, s_fast, s_plain, c64, p.k, p.kpad, thresh, f, lane, lab, n_ref);
     } else {
       const typename LabPack<LabT>::V v = LabPack<LabT>::load(labels + i0);
 #pragma unroll
-      for (int q = 0; q < P; ++q) lab[q] = LabPack<LabT>::get(v, q);
+      for (int e = 0; e < 4; ++e) lab[e] = LabPack<LabT>::get(v, e);
     }
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-      if (i0 + q < p.n) {
-        const double4 c = ld_c64(&c64[lab[q]]);
-        const double dx = ((double)xo[q] - (double)f.ox) - c.x;
-        const double dy = ((double)yo[q] - (double)f.oy) - c.y;
-        const double dz = ((double)zo[q] - (double)f.oz) - c.z;
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e < p.n) {
+        const double4 c = ld_c64(&c64[lab[e]]);
+        const double dx = ((double)r.x[e] - (double)f.ox) - c.x;
+        const double dy = ((double)r.y[e] - (double)f.oy) - c.y;
+        const double dz = ((double)r.z[e] - (double)f.oz) - c.z;
         inert += dx * dx + dy * dy + dz * dz;
       }
     }
@@ -608,14 +709,14 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_final_kernel(const FinalPar
         *reinterpret_cast<int4*>(p.labels_out + i0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
       } else {
 #pragma unroll
-        for (int q = 0; q < P; ++q)
-          if (i0 + q < p.n) p.labels_out[i0 + q] = lab[q];
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < p.n) p.labels_out[i0 + e] = lab[e];
       }
     }
   }
   const double bsum = block_sum_fixed(inert, s_red);
   n_ref = __reduce_add_sync(0xffffffffu, n_ref);
-  if ((tid & 31) == 0 && n_ref) atomicAdd(&s_refined, n_ref);
+  if (lane == 0 && n_ref) atomicAdd(&s_refined, n_ref);
   __syncthreads();
   if (tid == 0) {
     p.partials[blockIdx.x] = bsum;

@@ -24,8 +24,7 @@ using namespace mdkm;
 
 namespace {
 
-constexpr int kStepG = 2;                          // float4 groups per thread in the step kernel
-constexpr long long kTile = kThreads * 4 * kStepG;  // points per CTA tile (2048)
+constexpr long long kTile = 2048;  // capacity granularity of the point / label arrays
 constexpr int kBatch = 10;                          // Lloyd iterations enqueued between status polls
 
 template <typename T>
@@ -271,11 +270,11 @@ template <typename LabT>
 int launch_step_t(mdkm_handle* h, const StepParams& sp, size_t smem, int grid) {
   static bool attr_done = false;
   if (!attr_done) {
-    CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT, kStepG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             200 * 1024));
     attr_done = true;
   }
-  lloyd_step_kernel<LabT, kStepG><<<grid, kThreads, smem, h->stream>>>(sp);
+  lloyd_step_kernel<LabT><<<grid, kThreads, smem, h->stream>>>(sp);
   ++h->launches;
   CU(cudaGetLastError());
   return MDKM_OK;
@@ -309,19 +308,31 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.k = k;
   kb.kpad = pad_k(k);
   kb.wide = k > 256;
-  kb.step_smem = (size_t)kb.kpad * (16 + 32);
-  kb.final_smem = (size_t)kb.kpad * 16;
+  const size_t kp32 = (size_t)((kb.kpad + 31) & ~31);
+  kb.step_smem = kp32 * 32 + (size_t)kb.kpad * 32;
+  kb.final_smem = kp32 * 32;
   const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
   OK(ensure(h, h->table, table_bytes(kb.kpad)));
   OK(ensure(h, h->acc, (size_t)kb.kpad * 4 + 8));
   OK(ensure(h, h->dscratch, (size_t)std::max(64, k * 4 + 16)));
   OK(ensure(h, h->uscratch, 16));
-  const long long tiles = (h->n + kTile - 1) / kTile;
-  const int per_sm = kb.step_smem > 100 * 1024 ? 1 : 2;
-  kb.step_grid = grid_for(h, tiles, per_sm);
-  const long long ftiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);
-  kb.final_grid = grid_for(h, ftiles, 4);
+  const long long tiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);  // 8 warp-groups per CTA pass
+  // persistent grids: one full wave of resident CTAs (occupancy queried from the runtime)
+  int occ_step = 1, occ_final = 1;
+  if (kb.wide) {
+    CU(cudaFuncSetAttribute(lloyd_step_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(lloyd_final_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_step, lloyd_step_kernel<unsigned short>, kThreads, kb.step_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, lloyd_final_kernel<unsigned short>, kThreads, kb.final_smem));
+  } else {
+    CU(cudaFuncSetAttribute(lloyd_step_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(lloyd_final_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_step, lloyd_step_kernel<unsigned char>, kThreads, kb.step_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, lloyd_final_kernel<unsigned char>, kThreads, kb.final_smem));
+  }
+  kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
+  kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
   OK(ensure(h, h->partials, (size_t)std::max(kb.final_grid, h->sm_count * 8) * 8 + 16));
   if (!h->d_status) {
     CU(cudaMalloc(&h->d_status, sizeof(DevStatus)));

@@ -71,4 +71,16 @@ __device__ __forceinline__ uint2 ldg_stream_u64(const void* p) {
   return r;
 }
 
+// warp-wide float min / max in one instruction (sm_100a: CREDUX.MIN/MAX.F32)
+__device__ __forceinline__ float redux_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float redux_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 }  // namespace mdkm
