@@ -10,7 +10,7 @@
 namespace mdkm {
 
 constexpr int kThreads = 256;          // threads per CTA of the streaming kernels
-constexpr int kMaxK = 4096;            // largest supported cluster count
+constexpr int kMaxK = 2048;            // largest supported cluster count (shared-memory tables)
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float -> integer by mantissa alignment
 constexpr uint32_t kMagicBits = 0x4B400000u;
 constexpr int kQuantBits = 22;         // |quantised coordinate| < 2^22

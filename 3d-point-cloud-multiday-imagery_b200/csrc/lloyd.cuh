@@ -78,9 +78,9 @@ struct GroupRegs {
   float x[4], y[4], z[4];
 };
 
-// Loads group g (points [128 g, 128 g + 128)).  Indices beyond n-1 are clamped to the last
-// point, so a partial tail group sees only real coordinates (its extra lanes are masked out
-// of the sums by the caller).
+// Loads group g (points [128 g, 128 g + 128)) straight from global memory.  Indices beyond
+// n-1 are clamped to the last point (used by the final pass; the step kernel stages groups
+// through shared memory with TMA bulk copies instead).
 __device__ __forceinline__ void load_group(const float* __restrict__ x, const float* __restrict__ y,
                                            const float* __restrict__ z, long long n, long long g,
                                            int lane, GroupRegs& r) {
@@ -102,23 +102,31 @@ __device__ __forceinline__ void load_group(const float* __restrict__ x, const fl
   }
 }
 
+// Lower bound of |x - c|^2 over the box, and the candidate mask of one 32-row chunk.
+__device__ __forceinline__ unsigned int chunk_candidates(const float4* __restrict__ s_plain, int base, int lane,
+                                                         float bx0, float bx1, float by0, float by1,
+                                                         float bz0, float bz1, float bound) {
+  const float4 c = s_plain[base + lane];  // rows are padded to a multiple of 32 in shared memory
+  const float lx = fmaxf(fmaxf(bx0 - c.x, c.x - bx1), 0.0f);
+  const float ly = fmaxf(fmaxf(by0 - c.y, c.y - by1), 0.0f);
+  const float lz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
+  const float lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+  return __ballot_sync(0xffffffffu, lb <= bound);
+}
+
 // ---------------------------------------------------------------------------------------
-// Assignment of one warp-group.  s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0)
-// rows (padding rows hold 1e18 so that they are never candidates).  Warp-synchronous: all 32
-// lanes must call it.  Returns the 4 labels of this lane's points.
+// Assignment of one warp-group.  xc/yc/zc: centred FP32 coordinates of this lane's 4 points.
+// s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0) rows (padding rows hold 1e18 so
+// that they are never candidates); both padded to kp32 rows.  Warp-synchronous: all 32 lanes
+// must call it.  Returns the 4 labels of this lane's points.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void assign_group(const GroupRegs& r, const float4* __restrict__ s_fast,
+template <bool kOrigInSmem>
+__device__ __forceinline__ void assign_group(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
+                                             const float* orig_x, const float* orig_y, const float* orig_z,
+                                             const FrameF& f, const float4* __restrict__ s_fast,
                                              const float4* __restrict__ s_plain,
-                                             const double4* __restrict__ c64, int k, int kpad,
-                                             float thresh, const FrameF& f, int lane, int (&lab)[4],
-                                             unsigned int& n_refined) {
-  float xc[4], yc[4], zc[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    xc[e] = r.x[e] - f.ox;
-    yc[e] = r.y[e] - f.oy;
-    zc[e] = r.z[e] - f.oz;
-  }
+                                             const double4* __restrict__ c64, int k, int kp32, float thresh,
+                                             int lane, int (&lab)[4], unsigned int& n_refined) {
   // bounding box of the group (FMNMX3 + CREDUX.F32)
   const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
   const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
@@ -129,7 +137,7 @@ __device__ __forceinline__ void assign_group(const GroupRegs& r, const float4* _
 
   // pass 1: smallest upper bound  min_j max_{x in box} |x - c_j|^2
   float ub = __int_as_float(0x7f800000);
-  for (int j = lane; j < kpad; j += 32) {
+  for (int j = lane; j < kp32; j += 32) {
     const float4 c = s_plain[j];
     const float hx = fmaxf(c.x - bx0, bx1 - c.x);
     const float hy = fmaxf(c.y - by0, by1 - c.y);
@@ -141,6 +149,22 @@ __device__ __forceinline__ void assign_group(const GroupRegs& r, const float4* _
   // the centroid rows and of the fast distances themselves
   const float bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
 
+  // pass 2a: how many candidates, and the lowest one
+  int ncand = 0, first = 0;
+  unsigned int mask0 = 0;
+  for (int base = 0; base < kp32; base += 32) {
+    const unsigned int m = chunk_candidates(s_plain, base, lane, bx0, bx1, by0, by1, bz0, bz1, bound);
+    if (base == 0) mask0 = m;
+    if (ncand == 0 && m) first = base + __ffs(m) - 1;
+    ncand += __popc(m);
+  }
+  if (ncand <= 1) {  // interior group: one possible owner, no distance evaluation at all
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lab[e] = first;
+    return;
+  }
+  // pass 2b: evaluate the candidates in ascending index (strict '<' keeps the lowest index on
+  // ties, pyx:205-213), tracking best and second best per point
   float best[4], second[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -148,63 +172,49 @@ __device__ __forceinline__ void assign_group(const GroupRegs& r, const float4* _
     second[e] = __int_as_float(0x7f800000);
     lab[e] = 0;
   }
-  int first = -1;
-  bool evaluated = false;
-  // pass 2: candidates by lower bound, evaluated in ascending index (strict '<' keeps the
-  // lowest index on ties, pyx:205-213)
-  for (int base = 0; base < kpad; base += 32) {
-    const float4 c = s_plain[base + lane];  // kpad is a multiple of 32 rows in shared memory
-    const float lx = fmaxf(fmaxf(bx0 - c.x, c.x - bx1), 0.0f);
-    const float ly = fmaxf(fmaxf(by0 - c.y, c.y - by1), 0.0f);
-    const float lz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
-    const float lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
-    unsigned int mask = __ballot_sync(0xffffffffu, lb <= bound);
-    while (mask) {
-      const int jj = base + (__ffs(mask) - 1);
-      mask &= mask - 1;
-      if (first < 0) {
-        first = jj;  // evaluation deferred: a lone candidate needs none
-        continue;
-      }
-      for (int pass = evaluated ? 1 : 0; pass < 2; ++pass) {
-        const int j = pass ? jj : first;
-        const float4 cf = s_fast[j];  // LDS.128, warp broadcast
+  for (int base = 0; base < kp32; base += 32) {
+    unsigned int m = base == 0 ? mask0
+                               : chunk_candidates(s_plain, base, lane, bx0, bx1, by0, by1, bz0, bz1, bound);
+    while (m) {
+      const int j = base + __ffs(m) - 1;
+      m &= m - 1;
+      const float4 cf = s_fast[j];  // LDS.128, warp broadcast
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
-          const bool lt = d < best[e];
-          second[e] = fminf(second[e], fmaxf(d, best[e]));
-          best[e] = fminf(best[e], d);
-          lab[e] = lt ? j : lab[e];
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
+        const bool lt = d < best[e];
+        second[e] = fminf(second[e], fmaxf(d, best[e]));
+        best[e] = fminf(best[e], d);
+        lab[e] = lt ? j : lab[e];
       }
-      evaluated = true;
     }
   }
-  if (!evaluated) {
+  // FP64 refine of the points the FP32 pass cannot decide (rare; see file header), from the
+  // ORIGINAL coordinates (orig_* point at this lane's four floats: the shared-memory stage in
+  // the step kernel, registers in the final pass), so no FP32 rounding of x - origin enters.
+  bool amb = false;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) lab[e] = first;
-    return;
-  }
-  // FP64 refine of the points the FP32 pass cannot decide (rare; see file header)
+  for (int e = 0; e < 4; ++e) amb |= !(second[e] - best[e] > thresh);
+  if (amb) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (!(second[e] - best[e] > thresh)) {
-      const double X = (double)r.x[e] - (double)f.ox;
-      const double Y = (double)r.y[e] - (double)f.oy;
-      const double Z = (double)r.z[e] - (double)f.oz;
-      double bd = 1.0 / 0.0;
-      int bi = 0;
-      for (int j = 0; j < k; ++j) {
-        const double4 c = ld_c64(&c64[j]);
-        const double d = fma(-2.0, fma(X, c.x, fma(Y, c.y, Z * c.z)), c.w);
-        if (d < bd) {
-          bd = d;
-          bi = j;
+    for (int e = 0; e < 4; ++e) {
+      if (!(second[e] - best[e] > thresh)) {
+        const double X = (double)orig_x[e] - (double)f.ox;
+        const double Y = (double)orig_y[e] - (double)f.oy;
+        const double Z = (double)orig_z[e] - (double)f.oz;
+        double bd = 1.0 / 0.0;
+        int bi = 0;
+        for (int j = 0; j < k; ++j) {
+          const double4 c = ld_c64(&c64[j]);
+          const double d = fma(-2.0, fma(X, c.x, fma(Y, c.y, Z * c.z)), c.w);
+          if (d < bd) {
+            bd = d;
+            bi = j;
+          }
         }
+        lab[e] = bi;
+        ++n_refined;
       }
-      lab[e] = bi;
-      ++n_refined;
     }
   }
 }
@@ -214,12 +224,12 @@ struct LabPack;
 template <>
 struct LabPack<unsigned char> {
   using V = unsigned int;  // 4 labels
-  static __device__ __forceinline__ V load(const unsigned char* p) {
-    return *reinterpret_cast<const unsigned int*>(p);
-  }
+  static constexpr int kBytes = 4;
+  static __device__ __forceinline__ V load(const void* p) { return *reinterpret_cast<const unsigned int*>(p); }
   static __device__ __forceinline__ V pack(const int (&l)[4]) {
     return (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
   }
+  static __device__ __forceinline__ V splat(int l) { return (unsigned)l * 0x01010101u; }
   static __device__ __forceinline__ void store(unsigned char* p, V v) {
     *reinterpret_cast<unsigned int*>(p) = v;
   }
@@ -229,13 +239,17 @@ struct LabPack<unsigned char> {
 template <>
 struct LabPack<unsigned short> {
   using V = uint2;
-  static __device__ __forceinline__ V load(const unsigned short* p) {
-    return *reinterpret_cast<const uint2*>(p);
-  }
+  static constexpr int kBytes = 8;
+  static __device__ __forceinline__ V load(const void* p) { return *reinterpret_cast<const uint2*>(p); }
   static __device__ __forceinline__ V pack(const int (&l)[4]) {
     uint2 v;
     v.x = (unsigned)l[0] | ((unsigned)l[1] << 16);
     v.y = (unsigned)l[2] | ((unsigned)l[3] << 16);
+    return v;
+  }
+  static __device__ __forceinline__ V splat(int l) {
+    uint2 v;
+    v.x = v.y = (unsigned)l * 0x00010001u;
     return v;
   }
   static __device__ __forceinline__ void store(unsigned short* p, V v) { *reinterpret_cast<uint2*>(p) = v; }
@@ -246,59 +260,93 @@ struct LabPack<unsigned short> {
   }
 };
 
+// Adds (sx,sy,sz,cnt) to row `lab` of an accumulator slice.  kPrivate: the slice belongs to
+// this warp and only lane 0 ever touches it -> plain read-modify-write; otherwise the slice is
+// shared by the CTA -> shared-memory atomics.
+template <bool kPrivate>
 __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long long sx, long long sy,
                                         long long sz, unsigned int cnt) {
-  atomicAdd(&s_acc[lab * 4 + 0], (unsigned long long)sx);
-  atomicAdd(&s_acc[lab * 4 + 1], (unsigned long long)sy);
-  atomicAdd(&s_acc[lab * 4 + 2], (unsigned long long)sz);
-  atomicAdd(&s_acc[lab * 4 + 3], (unsigned long long)cnt);
+  unsigned long long* row = s_acc + lab * 4;
+  if (kPrivate) {
+    ulonglong2 a = *reinterpret_cast<ulonglong2*>(row);
+    ulonglong2 b = *reinterpret_cast<ulonglong2*>(row + 2);
+    a.x += (unsigned long long)sx;
+    a.y += (unsigned long long)sy;
+    b.x += (unsigned long long)sz;
+    b.y += (unsigned long long)cnt;
+    *reinterpret_cast<ulonglong2*>(row) = a;
+    *reinterpret_cast<ulonglong2*>(row + 2) = b;
+  } else {
+    atomicAdd(row + 0, (unsigned long long)sx);
+    atomicAdd(row + 1, (unsigned long long)sy);
+    atomicAdd(row + 2, (unsigned long long)sz);
+    atomicAdd(row + 3, (unsigned long long)cnt);
+  }
 }
 
 // Segmented warp reduction for a group that is not label-uniform: one round per distinct label
-// among the lanes' values (v valid for lanes with `active`), leader lane adds to shared memory.
+// among the active lanes; lane 0 adds the round's totals to the accumulator slice.
+template <bool kPrivate>
 __device__ __forceinline__ void warp_segmented_add(unsigned long long* s_acc, bool active, int l, int qx,
                                                    int qy, int qz, int cnt, int lane) {
   unsigned int todo = __ballot_sync(0xffffffffu, active);
   while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int ll = __shfl_sync(0xffffffffu, l, leader);
+    const int ll = __shfl_sync(0xffffffffu, l, __ffs(todo) - 1);
     const bool mine = active && (l == ll);
     const unsigned int peers = __ballot_sync(0xffffffffu, mine);
     const int sx = __reduce_add_sync(0xffffffffu, mine ? qx : 0);
     const int sy = __reduce_add_sync(0xffffffffu, mine ? qy : 0);
     const int sz = __reduce_add_sync(0xffffffffu, mine ? qz : 0);
-    const int sc = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
-    if (lane == leader) acc_add(s_acc, ll, sx, sy, sz, (unsigned int)sc);
+    if (lane == 0) acc_add<kPrivate>(s_acc, ll, sx, sy, sz, (unsigned int)(cnt * __popc(peers)));
     todo &= ~peers;
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // K2 + K3: assignment and per-cluster sums in one pass.
+//
+// Each warp streams its own sequence of 128-point groups through a kStages-deep ring in
+// shared memory: lane 0 issues four 1-D TMA bulk copies (x, y, z, previous labels) per group
+// and arms the stage's mbarrier with the byte count; the warp waits on the barrier, works on
+// the group from shared memory / registers, and re-arms the stage for the group kStages
+// ahead.  No CTA-wide barrier inside the loop; HBM latency is covered by the copies in
+// flight, not by occupancy.
 // ---------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+
 template <typename LabT>
-__global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParams p) {
+__host__ __device__ constexpr int stage_bytes() { return 3 * kGroup * 4 + kGroup * (int)sizeof(LabT); }
+
+template <typename LabT, bool kPrivate>
+__global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParams p) {
   if (!p.ignore_status && (p.st->done | p.st->paused)) return;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kStageB = stage_bytes<LabT>();
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kp32 = (p.kpad + 31) & ~31;  // rows staged in shared memory (multiple of 32)
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);
   float4* s_plain = s_fast + kp32;
-  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_plain + kp32);
+  unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_plain + kp32);
+  unsigned long long* s_acc_all = reinterpret_cast<unsigned long long*>(s_ring + kWarps * kStages * kStageB);
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_gbar[kWarps * kStages];
   __shared__ unsigned int s_changed;
   __shared__ unsigned int s_refined;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const int n_slices = kPrivate ? kWarps : 1;
+  unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
+    for (int i = 0; i < kWarps * kStages; ++i) mbar_init(&s_gbar[i], 1);
     fence_mbar_init();
     s_changed = 0;
     s_refined = 0;
   }
-  for (int i = tid; i < p.kpad * 4; i += kThreads) s_acc[i] = 0ull;
+  for (int i = tid; i < n_slices * p.kpad * 4; i += kThreads) s_acc_all[i] = 0ull;
   // rows [kpad, kp32) are not covered by the bulk copies: make them non-candidates
   for (int i = p.kpad + tid; i < kp32; i += kThreads) {
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
@@ -318,15 +366,24 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
   LabT* labels = reinterpret_cast<LabT*>(p.labels);
 
   const long long n_groups = (p.n + kGroup - 1) / kGroup;
-  const long long stride = (long long)gridDim.x * (kThreads / 32);
-  long long g = (long long)blockIdx.x * (kThreads / 32) + warp;
+  const long long n_full = p.n / kGroup;  // groups below this index have 128 real points
+  const long long stride = (long long)gridDim.x * kWarps;
+  const long long g0 = (long long)blockIdx.x * kWarps + warp;
+  unsigned char* ring = s_ring + warp * (kStages * kStageB);
+  uint64_t* gbar = s_gbar + warp * kStages;
 
-  // software pipeline: the next group's loads are in flight while the current one is processed
-  GroupRegs cur, nxt;
-  typename LabPack<LabT>::V old_cur = {}, old_nxt = {};
-  if (g < n_groups) {
-    load_group(p.x, p.y, p.z, p.n, g, lane, cur);
-    old_cur = LabPack<LabT>::load(labels + g * kGroup + lane * 4);
+  auto issue = [&](int stage, long long g) {  // lane 0 only
+    unsigned char* dst = ring + stage * kStageB;
+    mbar_expect_tx(&gbar[stage], (uint32_t)kStageB);
+    tma_load_1d(dst, p.x + g * kGroup, kGroup * 4, &gbar[stage]);
+    tma_load_1d(dst + kGroup * 4, p.y + g * kGroup, kGroup * 4, &gbar[stage]);
+    tma_load_1d(dst + kGroup * 8, p.z + g * kGroup, kGroup * 4, &gbar[stage]);
+    tma_load_1d(dst + kGroup * 12, labels + g * kGroup, kGroup * (int)sizeof(LabT), &gbar[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      if (g0 + s * stride < n_groups) issue(s, g0 + s * stride);
   }
   mbar_wait(&s_bar, 0);
 
@@ -335,51 +392,72 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
   unsigned int wn = 0;
   int wlab = -1;
   unsigned int n_chg = 0, n_ref = 0;
+  int stage = 0;
+  uint32_t parity = 0;
 
-  for (; g < n_groups; g += stride) {
-    const long long gn = g + stride;
-    if (gn < n_groups) {
-      load_group(p.x, p.y, p.z, p.n, gn, lane, nxt);
-      old_nxt = LabPack<LabT>::load(labels + gn * kGroup + lane * 4);
-    }
+  for (long long g = g0; g < n_groups; g += stride) {
+    mbar_wait(&gbar[stage], parity);
+    const unsigned char* src = ring + stage * kStageB;
+    const float4 vx = *reinterpret_cast<const float4*>(src + lane * 16);
+    const float4 vy = *reinterpret_cast<const float4*>(src + kGroup * 4 + lane * 16);
+    const float4 vz = *reinterpret_cast<const float4*>(src + kGroup * 8 + lane * 16);
+    const typename LabPack<LabT>::V oldl = LabPack<LabT>::load(src + kGroup * 12 + lane * LabPack<LabT>::kBytes);
+    const float xc[4] = {vx.x - f.ox, vx.y - f.ox, vx.z - f.ox, vx.w - f.ox};
+    const float yc[4] = {vy.x - f.oy, vy.y - f.oy, vy.z - f.oy, vy.w - f.oy};
+    const float zc[4] = {vz.x - f.oz, vz.y - f.oz, vz.z - f.oz, vz.w - f.oz};
     int lab[4];
-    assign_group(cur, s_fast, s_plain, c64, p.k, p.kpad, thresh, f, lane, lab, n_ref);
+    assign_group<true>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
+                       reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
+                       reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast, s_plain, c64, p.k,
+                       kp32, thresh, lane, lab, n_ref);
+    __syncwarp();
+    if (lane == 0) {
+      // every lane is done with the stage: refill it with the group kStages ahead
+      const long long gn = g + (long long)kStages * stride;
+      if (gn < n_groups) {
+        fence_proxy_async();
+        issue(stage, gn);
+      }
+    }
+    if (++stage == kStages) {
+      stage = 0;
+      parity ^= 1u;
+    }
 
     const long long i0 = g * kGroup + lane * 4;
-    const bool full = (g + 1) * kGroup <= p.n;  // warp-uniform
+    const bool full = g < n_full;  // warp-uniform
     const typename LabPack<LabT>::V newl = LabPack<LabT>::pack(lab);
     LabPack<LabT>::store(labels + i0, newl);
     if (first_iter) {
       n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - i0));
-    } else if (!LabPack<LabT>::same(newl, old_cur)) {
+    } else if (!LabPack<LabT>::same(newl, oldl)) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        n_chg += ((full || i0 + e < p.n) && lab[e] != LabPack<LabT>::get(old_cur, e)) ? 1u : 0u;
+        n_chg += ((full || i0 + e < p.n) && lab[e] != LabPack<LabT>::get(oldl, e)) ? 1u : 0u;
     }
 
     // fixed-point coordinates: q = rint(x' * scale) by mantissa alignment (|q| < 2^22):
-    // bits(x'*s + 1.5*2^23) - bits(1.5*2^23)
-    int qx[4], qy[4], qz[4];
+    // bits(x'*s + 1.5*2^23) - bits(1.5*2^23); the bias is removed once per sum
+    unsigned int ux[4], uy[4], uz[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      qx[e] = (int)(__float_as_uint(fmaf(cur.x[e] - f.ox, f.sx, kMagic)) - kMagicBits);
-      qy[e] = (int)(__float_as_uint(fmaf(cur.y[e] - f.oy, f.sy, kMagic)) - kMagicBits);
-      qz[e] = (int)(__float_as_uint(fmaf(cur.z[e] - f.oz, f.sz, kMagic)) - kMagicBits);
+      ux[e] = __float_as_uint(fmaf(xc[e], f.sx, kMagic));
+      uy[e] = __float_as_uint(fmaf(yc[e], f.sy, kMagic));
+      uz[e] = __float_as_uint(fmaf(zc[e], f.sz, kMagic));
     }
     const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
-    const int l0 = __shfl_sync(0xffffffffu, lab[0], 0);
-    const bool all_t_uni = __all_sync(0xffffffffu, t_uni) && full;
-    if (all_t_uni) {
-      const int tx = qx[0] + qx[1] + qx[2] + qx[3];
-      const int ty = qy[0] + qy[1] + qy[2] + qy[3];
-      const int tz = qz[0] + qz[1] + qz[2] + qz[3];
+    if (full && __all_sync(0xffffffffu, t_uni)) {
+      const int tx = (int)(ux[0] + ux[1] + ux[2] + ux[3] - 4u * kMagicBits);
+      const int ty = (int)(uy[0] + uy[1] + uy[2] + uy[3] - 4u * kMagicBits);
+      const int tz = (int)(uz[0] + uz[1] + uz[2] + uz[3] - 4u * kMagicBits);
+      const int l0 = __shfl_sync(0xffffffffu, lab[0], 0);
       if (__all_sync(0xffffffffu, lab[0] == l0)) {
         // the whole group has one label: three REDUX + register accumulation
         const int sx = __reduce_add_sync(0xffffffffu, tx);
         const int sy = __reduce_add_sync(0xffffffffu, ty);
         const int sz = __reduce_add_sync(0xffffffffu, tz);
         if (l0 != wlab) {
-          if (lane == 0 && wn > 0) acc_add(s_acc, wlab, wx, wy, wz, wn);
+          if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
           wx = wy = wz = 0;
           wn = 0;
           wlab = l0;
@@ -389,17 +467,16 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
         wz += sz;
         wn += kGroup;
       } else {
-        warp_segmented_add(s_acc, true, lab[0], tx, ty, tz, 4, lane);
+        warp_segmented_add<kPrivate>(s_acc, true, lab[0], tx, ty, tz, 4, lane);
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        warp_segmented_add(s_acc, full || (i0 + e < p.n), lab[e], qx[e], qy[e], qz[e], 1, lane);
+        warp_segmented_add<kPrivate>(s_acc, full || (i0 + e < p.n), lab[e], (int)(ux[e] - kMagicBits),
+                                     (int)(uy[e] - kMagicBits), (int)(uz[e] - kMagicBits), 1, lane);
     }
-    cur = nxt;
-    old_cur = old_nxt;
   }
-  if (lane == 0 && wn > 0) acc_add(s_acc, wlab, wx, wy, wz, wn);
+  if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
   n_chg = __reduce_add_sync(0xffffffffu, n_chg);
   n_ref = __reduce_add_sync(0xffffffffu, n_ref);
   if (lane == 0) {
@@ -409,7 +486,8 @@ __global__ void __launch_bounds__(kThreads, 2) lloyd_step_kernel(const StepParam
   __syncthreads();
   // CTA partials -> global int64 accumulators (RED.ADD.64; order-independent, exact)
   for (int i = tid; i < p.kpad * 4; i += kThreads) {
-    const unsigned long long v = s_acc[i];
+    unsigned long long v = 0ull;
+    for (int s = 0; s < n_slices; ++s) v += s_acc_all[s * p.kpad * 4 + i];
     if (v) atomicAdd(&p.acc[i], v);
   }
   if (tid == 0) {
@@ -688,7 +766,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
     const long long i0 = g * kGroup + lane * 4;
     int lab[4];
     if (reassign) {
-      assign_group(r, s_fast, s_plain, c64, p.k, p.kpad, thresh, f, lane, lab, n_ref);
+      const float xc[4] = {r.x[0] - f.ox, r.x[1] - f.ox, r.x[2] - f.ox, r.x[3] - f.ox};
+      const float yc[4] = {r.y[0] - f.oy, r.y[1] - f.oy, r.y[2] - f.oy, r.y[3] - f.oy};
+      const float zc[4] = {r.z[0] - f.oz, r.z[1] - f.oz, r.z[2] - f.oz, r.z[3] - f.oz};
+      assign_group<false>(xc, yc, zc, r.x, r.y, r.z, f, s_fast, s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
     } else {
       const typename LabPack<LabT>::V v = LabPack<LabT>::load(labels + i0);
 #pragma unroll

@@ -266,27 +266,31 @@ int compute_moments(mdkm_handle* h, double* mean_var_out) {
   return MDKM_OK;
 }
 
-template <typename LabT>
+template <typename LabT, bool kPrivate>
 int launch_step_t(mdkm_handle* h, const StepParams& sp, size_t smem, int grid) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            200 * 1024));
-    attr_done = true;
-  }
-  lloyd_step_kernel<LabT><<<grid, kThreads, smem, h->stream>>>(sp);
+  lloyd_step_kernel<LabT, kPrivate><<<grid, kThreads, smem, h->stream>>>(sp);
   ++h->launches;
   CU(cudaGetLastError());
   return MDKM_OK;
 }
 
+template <typename LabT, bool kPrivate>
+int step_occupancy(mdkm_handle* h, size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT, kPrivate>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lloyd_step_kernel<LabT, kPrivate>, kThreads, smem));
+  return MDKM_OK;
+}
+
+template <typename LabT>
+int final_occupancy(mdkm_handle* h, size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(lloyd_final_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lloyd_final_kernel<LabT>, kThreads, smem));
+  return MDKM_OK;
+}
+
 template <typename LabT>
 int launch_final_t(mdkm_handle* h, const FinalParams& fp, size_t smem, int grid) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(lloyd_final_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   lloyd_final_kernel<LabT><<<grid, kThreads, smem, h->stream>>>(fp);
   ++h->launches;
   CU(cudaGetLastError());
@@ -297,7 +301,8 @@ struct KmBuffers {
   int k, kpad;
   size_t step_smem, final_smem;
   int step_grid, final_grid;
-  bool wide;  // uint16 labels
+  bool wide;     // uint16 labels
+  bool priv;     // per-warp accumulator slices in shared memory
 };
 
 int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
@@ -309,7 +314,9 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.kpad = pad_k(k);
   kb.wide = k > 256;
   const size_t kp32 = (size_t)((kb.kpad + 31) & ~31);
-  kb.step_smem = kp32 * 32 + (size_t)kb.kpad * 32;
+  kb.priv = !kb.wide && kb.kpad <= 128;
+  const size_t ring = (size_t)(kThreads / 32) * kStages * (kb.wide ? stage_bytes<unsigned short>() : stage_bytes<unsigned char>());
+  kb.step_smem = kp32 * 32 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1);
   kb.final_smem = kp32 * 32;
   const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
@@ -321,16 +328,14 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   // persistent grids: one full wave of resident CTAs (occupancy queried from the runtime)
   int occ_step = 1, occ_final = 1;
   if (kb.wide) {
-    CU(cudaFuncSetAttribute(lloyd_step_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(lloyd_final_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_step, lloyd_step_kernel<unsigned short>, kThreads, kb.step_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, lloyd_final_kernel<unsigned short>, kThreads, kb.final_smem));
+    OK((step_occupancy<unsigned short, false>(h, kb.step_smem, &occ_step)));
+    OK(final_occupancy<unsigned short>(h, kb.final_smem, &occ_final));
   } else {
-    CU(cudaFuncSetAttribute(lloyd_step_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(lloyd_final_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_step, lloyd_step_kernel<unsigned char>, kThreads, kb.step_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, lloyd_final_kernel<unsigned char>, kThreads, kb.final_smem));
+    if (kb.priv) OK((step_occupancy<unsigned char, true>(h, kb.step_smem, &occ_step)));
+    else OK((step_occupancy<unsigned char, false>(h, kb.step_smem, &occ_step)));
+    OK(final_occupancy<unsigned char>(h, kb.final_smem, &occ_final));
   }
+  if (occ_step < 1) return fail(h, MDKM_ERR_INVALID, "k=%d does not fit the shared-memory tables", k);
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
   OK(ensure(h, h->partials, (size_t)std::max(kb.final_grid, h->sm_count * 8) * 8 + 16));
@@ -365,8 +370,9 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
     e1 = h->prof_ev[h->prof_used++];
     CU(cudaEventRecord(e0, h->stream));
   }
-  if (kb.wide) OK(launch_step_t<unsigned short>(h, sp, kb.step_smem, kb.step_grid));
-  else OK(launch_step_t<unsigned char>(h, sp, kb.step_smem, kb.step_grid));
+  if (kb.wide) OK((launch_step_t<unsigned short, false>(h, sp, kb.step_smem, kb.step_grid)));
+  else if (kb.priv) OK((launch_step_t<unsigned char, true>(h, sp, kb.step_smem, kb.step_grid)));
+  else OK((launch_step_t<unsigned char, false>(h, sp, kb.step_smem, kb.step_grid)));
   if (h->prof) CU(cudaEventRecord(e1, h->stream));
   return MDKM_OK;
 }

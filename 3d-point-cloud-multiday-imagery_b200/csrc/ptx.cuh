@@ -50,6 +50,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Order this thread's generic-proxy shared-memory accesses before later async-proxy (TMA) ones.
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // Streaming (read-once) 128-bit load: read-only path, do not allocate in L1.
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   float4 r;
