@@ -15,6 +15,14 @@ constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float -> integer by mantis
 constexpr uint32_t kMagicBits = 0x4B400000u;
 constexpr int kQuantBits = 22;         // |quantised coordinate| < 2^22
 
+// Resident cloud layout ("blocked SoA"): consecutive blocks of kGroup = 128 points, each block
+// x[128] y[128] z[128] (1536 contiguous bytes), so that one warp-group is ONE 1-D TMA bulk
+// copy and every lane still reads 16 B-aligned float4s.  Capacity is whole blocks; the unused
+// tail of the last block is zero.
+constexpr int kGroup = 128;
+constexpr int kBlockFloats = 3 * kGroup;
+__host__ __device__ inline long long pt_off(long long i) { return (i >> 7) * kBlockFloats + (i & (kGroup - 1)); }
+
 // Device-resident control block.  Written by the update / finalize kernels, read by every
 // kernel of the Lloyd loop (early exit once `done`), mirrored to pinned host memory between
 // batches of iterations only.

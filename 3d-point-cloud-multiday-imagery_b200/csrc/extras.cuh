@@ -20,9 +20,7 @@ namespace mdkm {
 //          [8 .. 8+kMaxK) taken indices  [8+kMaxK .. 8+2kMaxK) empty-cluster list
 // ---------------------------------------------------------------------------------------
 struct RelocParams {
-  const float* x;
-  const float* y;
-  const float* z;
+  const float* pts;  // blocked cloud
   long long n;
   const void* labels;
   const unsigned char* table;
@@ -46,9 +44,10 @@ __device__ __forceinline__ bool reloc_taken(const RelocParams& p, long long gi) 
 
 __device__ __forceinline__ double reloc_dist(const RelocParams& p, const double4* c64, long long i) {
   const double4 c = c64[reloc_label(p, i)];
-  const double dx = ((double)p.x[i] - (double)p.f.ox) - c.x;
-  const double dy = ((double)p.y[i] - (double)p.f.oy) - c.y;
-  const double dz = ((double)p.z[i] - (double)p.f.oz) - c.z;
+  const float* q = p.pts + pt_off(i);
+  const double dx = ((double)q[0] - (double)p.f.ox) - c.x;
+  const double dy = ((double)q[kGroup] - (double)p.f.oy) - c.y;
+  const double dz = ((double)q[2 * kGroup] - (double)p.f.oz) - c.z;
   return dx * dx + dy * dy + dz * dz;
 }
 
@@ -89,7 +88,8 @@ __global__ void reloc_payload_kernel(const RelocParams p) {
   const long long gi = (long long)p.scratch[1];
   const long long i = gi - p.rank_offset;
   if (p.scratch[1] == ~0ull || i < 0 || i >= p.n) return;  // another rank owns the point
-  const float xc = p.x[i] - p.f.ox, yc = p.y[i] - p.f.oy, zc = p.z[i] - p.f.oz;
+  const float* q = p.pts + pt_off(i);
+  const float xc = q[0] - p.f.ox, yc = q[kGroup] - p.f.oy, zc = q[2 * kGroup] - p.f.oz;
   const int qx = (int)(__float_as_uint(fmaf(xc, p.f.sx, kMagic)) - kMagicBits);
   const int qy = (int)(__float_as_uint(fmaf(yc, p.f.sy, kMagic)) - kMagicBits);
   const int qz = (int)(__float_as_uint(fmaf(zc, p.f.sz, kMagic)) - kMagicBits);
@@ -124,9 +124,9 @@ __global__ void reloc_apply_kernel(const RelocParams p, DevStatus* st) {
 // ---------------------------------------------------------------------------------------
 // Placeholders wired to the C ABI; implemented in extras_impl (ground level, k-means++).
 // ---------------------------------------------------------------------------------------
-int ground_level_impl(cudaStream_t stream, float* x, float* y, float* z, long long n, float* height_norm_out,
+int ground_level_impl(cudaStream_t stream, float* pts, long long n, float* height_norm_out,
                       int mem, double* h_min_out, double* h_max_out, int* launches);
-int kmeanspp_impl(cudaStream_t stream, int sm_count, const float* x, const float* y, const float* z, long long n,
+int kmeanspp_impl(cudaStream_t stream, int sm_count, const float* pts, long long n,
                   FrameF f, int k, long long first_index, const double* rand_vals, int n_local_trials, double* centers_out,
                   long long* indices_out, int* launches);
 

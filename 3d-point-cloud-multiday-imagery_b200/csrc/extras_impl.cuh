@@ -4,11 +4,11 @@
 
 namespace mdkm {
 
-inline int ground_level_impl(cudaStream_t, float*, float*, float*, long long, float*, int, double*, double*, int*) {
+inline int ground_level_impl(cudaStream_t, float*, long long, float*, int, double*, double*, int*) {
   return -1;  // TODO(next row f2)
 }
 
-inline int kmeanspp_impl(cudaStream_t, int, const float*, const float*, const float*, long long, FrameF, int, long long,
+inline int kmeanspp_impl(cudaStream_t, int, const float*, long long, FrameF, int, long long,
                          const double*, int, double*, long long*, int*) {
   return -1;  // TODO(next row f1)
 }

@@ -9,9 +9,9 @@
 //   lloyd_final_kernel  final E-step when the exit was not strict + inertia + int32 labels
 //                       (sklearn/cluster/_kmeans.py:742-756, _k_means_common.pyx:94-124)
 //
-// Work unit: a warp-group of 128 consecutive points (32 lanes x one float4 per coordinate
-// array, 16 B per lane, fully coalesced).  Everything inside a group is warp-synchronous:
-// no CTA barrier in the streaming loop.
+// Work unit: a warp-group of 128 consecutive points = one 1536-byte block of the resident
+// cloud (common.cuh: x[128] y[128] z[128]), fetched with ONE 1-D TMA bulk copy.  Everything
+// inside a group is warp-synchronous: no CTA barrier in the streaming loop.
 //
 // Numerics (DESIGN.md "Exactness"):
 //   * candidate pruning: the group's bounding box gives, for every centroid, a lower and an
@@ -34,14 +34,10 @@
 
 namespace mdkm {
 
-constexpr int kGroup = 128;  // points per warp-group
-
 struct StepParams {
-  const float* x;
-  const float* y;
-  const float* z;
+  const float* pts;           // blocked cloud (common.cuh)
   long long n;
-  void* labels;               // uint8 (k <= 256) or uint16, n rounded up to the group
+  void* labels;               // uint8 (k <= 256) or uint16, capacity = whole groups
   const unsigned char* table; // centroid table (see common.cuh)
   unsigned long long* acc;    // [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed
   DevStatus* st;
@@ -51,9 +47,7 @@ struct StepParams {
 };
 
 struct FinalParams {
-  const float* x;
-  const float* y;
-  const float* z;
+  const float* pts;
   long long n;
   const void* labels;         // stored labels of the last step
   int* labels_out;            // int32[n] or nullptr
@@ -73,60 +67,33 @@ __device__ __forceinline__ double4 ld_c64(const double4* p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// One warp-group of points in registers (4 consecutive points per lane).
-struct GroupRegs {
-  float x[4], y[4], z[4];
-};
-
-// Loads group g (points [128 g, 128 g + 128)) straight from global memory.  Indices beyond
-// n-1 are clamped to the last point (used by the final pass; the step kernel stages groups
-// through shared memory with TMA bulk copies instead).
-__device__ __forceinline__ void load_group(const float* __restrict__ x, const float* __restrict__ y,
-                                           const float* __restrict__ z, long long n, long long g,
-                                           int lane, GroupRegs& r) {
-  const long long i0 = g * kGroup + lane * 4;
-  if (i0 + 3 < n) {
-    const float4 vx = ldg_stream_f4(x + i0), vy = ldg_stream_f4(y + i0), vz = ldg_stream_f4(z + i0);
-    r.x[0] = vx.x; r.x[1] = vx.y; r.x[2] = vx.z; r.x[3] = vx.w;
-    r.y[0] = vy.x; r.y[1] = vy.y; r.y[2] = vy.z; r.y[3] = vy.w;
-    r.z[0] = vz.x; r.z[1] = vz.y; r.z[2] = vz.z; r.z[3] = vz.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      long long i = i0 + e;
-      i = i < n ? i : n - 1;
-      r.x[e] = __ldg(x + i);
-      r.y[e] = __ldg(y + i);
-      r.z[e] = __ldg(z + i);
-    }
-  }
-}
-
-// Lower bound of |x - c|^2 over the box, and the candidate mask of one 32-row chunk.
-__device__ __forceinline__ unsigned int chunk_candidates(const float4* __restrict__ s_plain, int base, int lane,
-                                                         float bx0, float bx1, float by0, float by1,
-                                                         float bz0, float bz1, float bound) {
-  const float4 c = s_plain[base + lane];  // rows are padded to a multiple of 32 in shared memory
-  const float lx = fmaxf(fmaxf(bx0 - c.x, c.x - bx1), 0.0f);
-  const float ly = fmaxf(fmaxf(by0 - c.y, c.y - by1), 0.0f);
-  const float lz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
-  const float lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
-  return __ballot_sync(0xffffffffu, lb <= bound);
+// Bounds of |x - c|^2 over the box [b0, b1] for one centroid row.
+__device__ __forceinline__ void box_bounds(const float4 c, float bx0, float bx1, float by0, float by1, float bz0,
+                                           float bz1, float& lb, float& ub) {
+  const float ax = c.x - bx0, ay = c.y - by0, az = c.z - bz0;  // >= 0 when c is right of the low face
+  const float dx = bx1 - c.x, dy = by1 - c.y, dz = bz1 - c.z;  // >= 0 when c is left of the high face
+  const float hx = fmaxf(ax, dx), hy = fmaxf(ay, dy), hz = fmaxf(az, dz);
+  ub = fmaf(hx, hx, fmaf(hy, hy, hz * hz));
+  const float lx = fmaxf(fmaxf(-ax, -dx), 0.0f), ly = fmaxf(fmaxf(-ay, -dy), 0.0f), lz = fmaxf(fmaxf(-az, -dz), 0.0f);
+  lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
 }
 
 // ---------------------------------------------------------------------------------------
-// Assignment of one warp-group.  xc/yc/zc: centred FP32 coordinates of this lane's 4 points.
-// s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0) rows (padding rows hold 1e18 so
-// that they are never candidates); both padded to kp32 rows.  Warp-synchronous: all 32 lanes
-// must call it.  Returns the 4 labels of this lane's points.
+// Assignment of one warp-group.  xc/yc/zc: centred FP32 coordinates of this lane's 4 points;
+// orig_*: this lane's four ORIGINAL coordinates (shared-memory stage or registers), read only
+// by the FP64 refine.  s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0) rows, both
+// padded to a multiple of 32 rows (padding rows are never candidates).  kChunks = rows/32 when
+// known at compile time (straight-line code), 0 = run-time loop.  Warp-synchronous: all 32
+// lanes must call it.  Returns the number of candidate centroids of the group; the labels of
+// this lane's points are in lab[].
 // ---------------------------------------------------------------------------------------
-template <bool kOrigInSmem>
-__device__ __forceinline__ void assign_group(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
-                                             const float* orig_x, const float* orig_y, const float* orig_z,
-                                             const FrameF& f, const float4* __restrict__ s_fast,
-                                             const float4* __restrict__ s_plain,
-                                             const double4* __restrict__ c64, int k, int kp32, float thresh,
-                                             int lane, int (&lab)[4], unsigned int& n_refined) {
+template <int kChunks>
+__device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
+                                            const float* orig_x, const float* orig_y, const float* orig_z,
+                                            const FrameF& f, const float4* __restrict__ s_fast,
+                                            const float4* __restrict__ s_plain,
+                                            const double4* __restrict__ c64, int k, int kp32, float thresh,
+                                            int lane, int (&lab)[4], unsigned int& n_refined) {
   // bounding box of the group (FMNMX3 + CREDUX.F32)
   const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
   const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
@@ -135,36 +102,55 @@ __device__ __forceinline__ void assign_group(const float (&xc)[4], const float (
   const float bz0 = redux_min_f32(fminf(fminf(zc[0], zc[1]), fminf(zc[2], zc[3])));
   const float bz1 = redux_max_f32(fmaxf(fmaxf(zc[0], zc[1]), fmaxf(zc[2], zc[3])));
 
-  // pass 1: smallest upper bound  min_j max_{x in box} |x - c_j|^2
-  float ub = __int_as_float(0x7f800000);
-  for (int j = lane; j < kp32; j += 32) {
-    const float4 c = s_plain[j];
-    const float hx = fmaxf(c.x - bx0, bx1 - c.x);
-    const float hy = fmaxf(c.y - by0, by1 - c.y);
-    const float hz = fmaxf(c.z - bz0, bz1 - c.z);
-    ub = fminf(ub, fmaf(hx, hx, fmaf(hy, hy, hz * hz)));
-  }
-  ub = redux_min_f32(ub);
-  // margin: relative slack for the FP32 box arithmetic + 2*thresh (= 4E) for the rounding of
-  // the centroid rows and of the fast distances themselves
-  const float bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
-
-  // pass 2a: how many candidates, and the lowest one
+  constexpr int kM = kChunks > 0 ? kChunks : 1;
+  unsigned int masks[kM];
   int ncand = 0, first = 0;
-  unsigned int mask0 = 0;
-  for (int base = 0; base < kp32; base += 32) {
-    const unsigned int m = chunk_candidates(s_plain, base, lane, bx0, bx1, by0, by1, bz0, bz1, bound);
-    if (base == 0) mask0 = m;
-    if (ncand == 0 && m) first = base + __ffs(m) - 1;
-    ncand += __popc(m);
+  float bound;
+  if (kChunks > 0) {
+    // one pass: lower and upper bound of every centroid, then the candidate ballots
+    float lb[kM];
+    float ub = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int c = 0; c < kM; ++c) {
+      float u;
+      box_bounds(s_plain[c * 32 + lane], bx0, bx1, by0, by1, bz0, bz1, lb[c], u);
+      ub = fminf(ub, u);
+    }
+    ub = redux_min_f32(ub);
+    // margin: relative slack for the FP32 box arithmetic + 2*thresh (= 4E) for the rounding of
+    // the centroid rows and of the fast distances themselves
+    bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
+#pragma unroll
+    for (int c = kM - 1; c >= 0; --c) {
+      masks[c] = __ballot_sync(0xffffffffu, lb[c] <= bound);
+      ncand += __popc(masks[c]);
+      if (masks[c]) first = c * 32 + __ffs(masks[c]) - 1;
+    }
+  } else {
+    float ub = __int_as_float(0x7f800000);
+    for (int j = lane; j < kp32; j += 32) {
+      float l, u;
+      box_bounds(s_plain[j], bx0, bx1, by0, by1, bz0, bz1, l, u);
+      ub = fminf(ub, u);
+    }
+    ub = redux_min_f32(ub);
+    bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
+    for (int base = 0; base < kp32; base += 32) {
+      float l, u;
+      box_bounds(s_plain[base + lane], bx0, bx1, by0, by1, bz0, bz1, l, u);
+      const unsigned int m = __ballot_sync(0xffffffffu, l <= bound);
+      if (ncand == 0 && m) first = base + __ffs(m) - 1;
+      ncand += __popc(m);
+    }
+    masks[0] = 0;
   }
   if (ncand <= 1) {  // interior group: one possible owner, no distance evaluation at all
 #pragma unroll
     for (int e = 0; e < 4; ++e) lab[e] = first;
-    return;
+    return ncand;
   }
-  // pass 2b: evaluate the candidates in ascending index (strict '<' keeps the lowest index on
-  // ties, pyx:205-213), tracking best and second best per point
+  // evaluate the candidates in ascending index (strict '<' keeps the lowest index on ties,
+  // pyx:205-213), tracking best and second best per point
   float best[4], second[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -172,26 +158,39 @@ __device__ __forceinline__ void assign_group(const float (&xc)[4], const float (
     second[e] = __int_as_float(0x7f800000);
     lab[e] = 0;
   }
-  for (int base = 0; base < kp32; base += 32) {
-    unsigned int m = base == 0 ? mask0
-                               : chunk_candidates(s_plain, base, lane, bx0, bx1, by0, by1, bz0, bz1, bound);
-    while (m) {
-      const int j = base + __ffs(m) - 1;
-      m &= m - 1;
-      const float4 cf = s_fast[j];  // LDS.128, warp broadcast
+  auto eval = [&](int j) {
+    const float4 cf = s_fast[j];  // LDS.128, warp broadcast
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
-        const bool lt = d < best[e];
-        second[e] = fminf(second[e], fmaxf(d, best[e]));
-        best[e] = fminf(best[e], d);
-        lab[e] = lt ? j : lab[e];
+    for (int e = 0; e < 4; ++e) {
+      const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
+      const bool lt = d < best[e];
+      second[e] = fminf(second[e], fmaxf(d, best[e]));
+      best[e] = fminf(best[e], d);
+      lab[e] = lt ? j : lab[e];
+    }
+  };
+  if (kChunks > 0) {
+#pragma unroll
+    for (int c = 0; c < kM; ++c) {
+      unsigned int m = masks[c];
+      while (m) {
+        eval(c * 32 + __ffs(m) - 1);
+        m &= m - 1;
+      }
+    }
+  } else {
+    for (int base = 0; base < kp32; base += 32) {
+      float l, u;
+      box_bounds(s_plain[base + lane], bx0, bx1, by0, by1, bz0, bz1, l, u);
+      unsigned int m = __ballot_sync(0xffffffffu, l <= bound);
+      while (m) {
+        eval(base + __ffs(m) - 1);
+        m &= m - 1;
       }
     }
   }
   // FP64 refine of the points the FP32 pass cannot decide (rare; see file header), from the
-  // ORIGINAL coordinates (orig_* point at this lane's four floats: the shared-memory stage in
-  // the step kernel, registers in the final pass), so no FP32 rounding of x - origin enters.
+  // ORIGINAL coordinates, so no FP32 rounding of x - origin enters.
   bool amb = false;
 #pragma unroll
   for (int e = 0; e < 4; ++e) amb |= !(second[e] - best[e] > thresh);
@@ -217,6 +216,7 @@ __device__ __forceinline__ void assign_group(const float (&xc)[4], const float (
       }
     }
   }
+  return ncand;
 }
 
 template <typename LabT>
@@ -229,7 +229,6 @@ struct LabPack<unsigned char> {
   static __device__ __forceinline__ V pack(const int (&l)[4]) {
     return (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
   }
-  static __device__ __forceinline__ V splat(int l) { return (unsigned)l * 0x01010101u; }
   static __device__ __forceinline__ void store(unsigned char* p, V v) {
     *reinterpret_cast<unsigned int*>(p) = v;
   }
@@ -245,11 +244,6 @@ struct LabPack<unsigned short> {
     uint2 v;
     v.x = (unsigned)l[0] | ((unsigned)l[1] << 16);
     v.y = (unsigned)l[2] | ((unsigned)l[3] << 16);
-    return v;
-  }
-  static __device__ __forceinline__ V splat(int l) {
-    uint2 v;
-    v.x = v.y = (unsigned)l * 0x00010001u;
     return v;
   }
   static __device__ __forceinline__ void store(unsigned short* p, V v) { *reinterpret_cast<uint2*>(p) = v; }
@@ -306,25 +300,26 @@ __device__ __forceinline__ void warp_segmented_add(unsigned long long* s_acc, bo
 // K2 + K3: assignment and per-cluster sums in one pass.
 //
 // Each warp streams its own sequence of 128-point groups through a kStages-deep ring in
-// shared memory: lane 0 issues four 1-D TMA bulk copies (x, y, z, previous labels) per group
-// and arms the stage's mbarrier with the byte count; the warp waits on the barrier, works on
-// the group from shared memory / registers, and re-arms the stage for the group kStages
-// ahead.  No CTA-wide barrier inside the loop; HBM latency is covered by the copies in
-// flight, not by occupancy.
+// shared memory: lane 0 issues two 1-D TMA bulk copies per group (the 1536-byte xyz block
+// and the previous labels) and arms the stage's mbarrier with the byte count; the warp waits
+// on the barrier, works on the group from shared memory / registers, and re-arms the stage
+// for the group kStages ahead.  No CTA-wide barrier inside the loop; HBM latency is covered
+// by the copies in flight, not by occupancy.
 // ---------------------------------------------------------------------------------------
 constexpr int kStages = 3;
 
 template <typename LabT>
-__host__ __device__ constexpr int stage_bytes() { return 3 * kGroup * 4 + kGroup * (int)sizeof(LabT); }
+__host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGroup * (int)sizeof(LabT); }
 
-template <typename LabT, bool kPrivate>
+template <typename LabT, bool kPrivate, int kChunks>
 __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParams p) {
   if (!p.ignore_status && (p.st->done | p.st->paused)) return;
   constexpr int kWarps = kThreads / 32;
   constexpr int kStageB = stage_bytes<LabT>();
+  constexpr int kLabB = kGroup * (int)sizeof(LabT);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int kp32 = (p.kpad + 31) & ~31;  // rows staged in shared memory (multiple of 32)
+  const int kp32 = kChunks > 0 ? kChunks * 32 : ((p.kpad + 31) & ~31);  // rows staged in shared memory
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);
   float4* s_plain = s_fast + kp32;
   unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_plain + kp32);
@@ -363,27 +358,35 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const float thresh = p.st->thresh;
   const bool first_iter = p.st->first != 0;
   const FrameF f = p.f;
-  LabT* labels = reinterpret_cast<LabT*>(p.labels);
 
   const long long n_groups = (p.n + kGroup - 1) / kGroup;
   const long long n_full = p.n / kGroup;  // groups below this index have 128 real points
   const long long stride = (long long)gridDim.x * kWarps;
   const long long g0 = (long long)blockIdx.x * kWarps + warp;
-  unsigned char* ring = s_ring + warp * (kStages * kStageB);
-  uint64_t* gbar = s_gbar + warp * kStages;
+  // per-warp stage addresses / source cursors (advanced by one stride per group)
+  const uint32_t ring_a = smem_u32(s_ring + warp * (kStages * kStageB));
+  const uint32_t gbar_a = smem_u32(s_gbar + warp * kStages);
+  const unsigned char* ring = s_ring + warp * (kStages * kStageB);
+  const float* src_pts = p.pts + g0 * kBlockFloats;         // next group to FETCH
+  const LabT* src_lab = reinterpret_cast<const LabT*>(p.labels) + g0 * kGroup;
+  LabT* dst_lab = reinterpret_cast<LabT*>(p.labels) + g0 * kGroup + lane * 4;  // group being PROCESSED
+  const long long pts_step = stride * kBlockFloats, lab_step = stride * kGroup;
+  long long g_fetch = g0;
 
-  auto issue = [&](int stage, long long g) {  // lane 0 only
-    unsigned char* dst = ring + stage * kStageB;
-    mbar_expect_tx(&gbar[stage], (uint32_t)kStageB);
-    tma_load_1d(dst, p.x + g * kGroup, kGroup * 4, &gbar[stage]);
-    tma_load_1d(dst + kGroup * 4, p.y + g * kGroup, kGroup * 4, &gbar[stage]);
-    tma_load_1d(dst + kGroup * 8, p.z + g * kGroup, kGroup * 4, &gbar[stage]);
-    tma_load_1d(dst + kGroup * 12, labels + g * kGroup, kGroup * (int)sizeof(LabT), &gbar[stage]);
+  auto issue = [&](int stage) {  // lane 0 only: fetch group g_fetch into `stage`
+    const uint32_t dst = ring_a + stage * kStageB, bar = gbar_a + stage * 8;
+    mbar_expect_tx_a(bar, (uint32_t)kStageB);
+    tma_load_1d_a(dst, src_pts, kBlockFloats * 4, bar);
+    tma_load_1d_a(dst + kBlockFloats * 4, src_lab, kLabB, bar);
   };
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s)
-      if (g0 + s * stride < n_groups) issue(s, g0 + s * stride);
+    for (int s = 0; s < kStages; ++s) {
+      if (g_fetch < n_groups) issue(s);
+      g_fetch += stride;
+      src_pts += pts_step;
+      src_lab += lab_step;
+    }
   }
   mbar_wait(&s_bar, 0);
 
@@ -396,41 +399,44 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   uint32_t parity = 0;
 
   for (long long g = g0; g < n_groups; g += stride) {
-    mbar_wait(&gbar[stage], parity);
+    mbar_wait_a(gbar_a + stage * 8, parity);
     const unsigned char* src = ring + stage * kStageB;
     const float4 vx = *reinterpret_cast<const float4*>(src + lane * 16);
     const float4 vy = *reinterpret_cast<const float4*>(src + kGroup * 4 + lane * 16);
     const float4 vz = *reinterpret_cast<const float4*>(src + kGroup * 8 + lane * 16);
-    const typename LabPack<LabT>::V oldl = LabPack<LabT>::load(src + kGroup * 12 + lane * LabPack<LabT>::kBytes);
+    const typename LabPack<LabT>::V oldl = LabPack<LabT>::load(src + kBlockFloats * 4 + lane * LabPack<LabT>::kBytes);
     const float xc[4] = {vx.x - f.ox, vx.y - f.ox, vx.z - f.ox, vx.w - f.ox};
     const float yc[4] = {vy.x - f.oy, vy.y - f.oy, vy.z - f.oy, vy.w - f.oy};
     const float zc[4] = {vz.x - f.oz, vz.y - f.oz, vz.z - f.oz, vz.w - f.oz};
     int lab[4];
-    assign_group<true>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
-                       reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
-                       reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast, s_plain, c64, p.k,
-                       kp32, thresh, lane, lab, n_ref);
+    const int ncand = assign_group<kChunks>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
+                                            reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
+                                            reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast,
+                                            s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
     __syncwarp();
     if (lane == 0) {
       // every lane is done with the stage: refill it with the group kStages ahead
-      const long long gn = g + (long long)kStages * stride;
-      if (gn < n_groups) {
+      if (g_fetch < n_groups) {
         fence_proxy_async();
-        issue(stage, gn);
+        issue(stage);
       }
+      g_fetch += stride;
+      src_pts += pts_step;
+      src_lab += lab_step;
     }
     if (++stage == kStages) {
       stage = 0;
       parity ^= 1u;
     }
 
-    const long long i0 = g * kGroup + lane * 4;
     const bool full = g < n_full;  // warp-uniform
     const typename LabPack<LabT>::V newl = LabPack<LabT>::pack(lab);
-    LabPack<LabT>::store(labels + i0, newl);
+    LabPack<LabT>::store(dst_lab, newl);
+    dst_lab += lab_step;
     if (first_iter) {
-      n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - i0));
+      n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - (g * kGroup + lane * 4)));
     } else if (!LabPack<LabT>::same(newl, oldl)) {
+      const long long i0 = g * kGroup + lane * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         n_chg += ((full || i0 + e < p.n) && lab[e] != LabPack<LabT>::get(oldl, e)) ? 1u : 0u;
@@ -445,31 +451,39 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       uy[e] = __float_as_uint(fmaf(yc[e], f.sy, kMagic));
       uz[e] = __float_as_uint(fmaf(zc[e], f.sz, kMagic));
     }
-    const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
-    if (full && __all_sync(0xffffffffu, t_uni)) {
-      const int tx = (int)(ux[0] + ux[1] + ux[2] + ux[3] - 4u * kMagicBits);
-      const int ty = (int)(uy[0] + uy[1] + uy[2] + uy[3] - 4u * kMagicBits);
-      const int tz = (int)(uz[0] + uz[1] + uz[2] + uz[3] - 4u * kMagicBits);
-      const int l0 = __shfl_sync(0xffffffffu, lab[0], 0);
-      if (__all_sync(0xffffffffu, lab[0] == l0)) {
-        // the whole group has one label: three REDUX + register accumulation
-        const int sx = __reduce_add_sync(0xffffffffu, tx);
-        const int sy = __reduce_add_sync(0xffffffffu, ty);
-        const int sz = __reduce_add_sync(0xffffffffu, tz);
-        if (l0 != wlab) {
-          if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
-          wx = wy = wz = 0;
-          wn = 0;
-          wlab = l0;
-        }
-        wx += sx;
-        wy += sy;
-        wz += sz;
-        wn += kGroup;
-      } else {
-        warp_segmented_add<kPrivate>(s_acc, true, lab[0], tx, ty, tz, 4, lane);
+    const int tx = (int)(ux[0] + ux[1] + ux[2] + ux[3] - 4u * kMagicBits);
+    const int ty = (int)(uy[0] + uy[1] + uy[2] + uy[3] - 4u * kMagicBits);
+    const int tz = (int)(uz[0] + uz[1] + uz[2] + uz[3] - 4u * kMagicBits);
+    bool uniform = full && (ncand <= 1);  // a lone candidate labels the whole group
+    int l0 = lab[0];
+    bool t_all = uniform;
+    if (!uniform && full) {
+      const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
+      t_all = __all_sync(0xffffffffu, t_uni);
+      if (t_all) {
+        l0 = __shfl_sync(0xffffffffu, lab[0], 0);
+        uniform = __all_sync(0xffffffffu, lab[0] == l0);
       }
+    }
+    if (uniform) {
+      // the whole group has one label: three REDUX + register accumulation
+      const int sx = __reduce_add_sync(0xffffffffu, tx);
+      const int sy = __reduce_add_sync(0xffffffffu, ty);
+      const int sz = __reduce_add_sync(0xffffffffu, tz);
+      if (l0 != wlab) {
+        if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
+        wx = wy = wz = 0;
+        wn = 0;
+        wlab = l0;
+      }
+      wx += sx;
+      wy += sy;
+      wz += sz;
+      wn += kGroup;
+    } else if (t_all) {
+      warp_segmented_add<kPrivate>(s_acc, true, lab[0], tx, ty, tz, 4, lane);
     } else {
+      const long long i0 = g * kGroup + lane * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         warp_segmented_add<kPrivate>(s_acc, full || (i0 + e < p.n), lab[e], (int)(ux[e] - kMagicBits),
@@ -761,15 +775,16 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   const long long n_groups = (p.n + kGroup - 1) / kGroup;
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long g = (long long)blockIdx.x * (kThreads / 32) + warp; g < n_groups; g += stride) {
-    GroupRegs r;
-    load_group(p.x, p.y, p.z, p.n, g, lane, r);
+    const float* blk = p.pts + g * kBlockFloats + lane * 4;
+    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
+    const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
     const long long i0 = g * kGroup + lane * 4;
     int lab[4];
     if (reassign) {
-      const float xc[4] = {r.x[0] - f.ox, r.x[1] - f.ox, r.x[2] - f.ox, r.x[3] - f.ox};
-      const float yc[4] = {r.y[0] - f.oy, r.y[1] - f.oy, r.y[2] - f.oy, r.y[3] - f.oy};
-      const float zc[4] = {r.z[0] - f.oz, r.z[1] - f.oz, r.z[2] - f.oz, r.z[3] - f.oz};
-      assign_group<false>(xc, yc, zc, r.x, r.y, r.z, f, s_fast, s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
+      const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
+      const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
+      const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
+      assign_group<0>(xc, yc, zc, xo, yo, zo, f, s_fast, s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
     } else {
       const typename LabPack<LabT>::V v = LabPack<LabT>::load(labels + i0);
 #pragma unroll
@@ -779,9 +794,9 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
     for (int e = 0; e < 4; ++e) {
       if (i0 + e < p.n) {
         const double4 c = ld_c64(&c64[lab[e]]);
-        const double dx = ((double)r.x[e] - (double)f.ox) - c.x;
-        const double dy = ((double)r.y[e] - (double)f.oy) - c.y;
-        const double dz = ((double)r.z[e] - (double)f.oz) - c.z;
+        const double dx = ((double)xo[e] - (double)f.ox) - c.x;
+        const double dy = ((double)yo[e] - (double)f.oy) - c.y;
+        const double dz = ((double)zo[e] - (double)f.oz) - c.z;
         inert += dx * dx + dy * dy + dz * dz;
       }
     }

@@ -43,7 +43,7 @@ struct mdkm_handle {
   std::string err;
 
   // resident cloud (SoA, capacity padded to the tile)
-  DevBuf<float> x, y, z;
+  DevBuf<float> pts;  // blocked cloud (common.cuh), capacity = whole 128-point blocks
   long long n = 0;        // points on this rank
   long long n_total = 0;  // points over all ranks
   bool have_points = false;
@@ -153,21 +153,21 @@ int grid_for(const mdkm_handle* h, long long work_items, int per_sm) {
 }
 
 int alloc_points(mdkm_handle* h, long long n) {
-  const size_t cap = (size_t)round_up(std::max<long long>(n, 1), kTile);
-  OK(ensure(h, h->x, cap));
-  OK(ensure(h, h->y, cap));
-  OK(ensure(h, h->z, cap));
+  const size_t cap = (size_t)round_up(std::max<long long>(n, 1), kGroup);
+  OK(ensure(h, h->pts, cap * 3));
   return MDKM_OK;
 }
 
-// zero the padding behind the last point so the tail tile reads finite values
+// zero the unused tail of the last block so that it only loosens that group's bounding box
 int zero_tail(mdkm_handle* h) {
-  const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
-  const size_t tail = (size_t)(cap - h->n);
-  if (tail) {
-    CU(cudaMemsetAsync(h->x.p + h->n, 0, tail * 4, h->stream));
-    CU(cudaMemsetAsync(h->y.p + h->n, 0, tail * 4, h->stream));
-    CU(cudaMemsetAsync(h->z.p + h->n, 0, tail * 4, h->stream));
+  if (h->n % kGroup != 0 || h->n == 0) {
+    if (h->n == 0) {
+      CU(cudaMemsetAsync(h->pts.p, 0, kBlockFloats * 4, h->stream));
+    } else {
+      zero_tail_kernel<<<1, 128, 0, h->stream>>>(h->pts.p, h->n);
+      ++h->launches;
+      CU(cudaGetLastError());
+    }
   }
   return MDKM_OK;
 }
@@ -186,8 +186,8 @@ int compute_frame(mdkm_handle* h) {
   unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   if (h->n > 0) {
-    minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, 0, h->stream>>>(
-        h->x.p, h->y.p, h->z.p, h->n, h->uscratch.p + 4);
+    minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, 0, h->stream>>>(h->pts.p, h->n,
+                                                                                     h->uscratch.p + 4);
     ++h->launches;
     CU(cudaGetLastError());
   }
@@ -245,8 +245,8 @@ int compute_moments(mdkm_handle* h, double* mean_var_out) {
   CU(cudaMemsetAsync(h->uscratch.p, 0, 4, h->stream));
   CU(cudaMemsetAsync(h->dscratch.p, 0, 8 * sizeof(double), h->stream));
   if (h->n > 0) {
-    moments_kernel<<<g, kThreads, 0, h->stream>>>(h->x.p, h->y.p, h->z.p, h->n, h->ff, h->partials.p,
-                                                  h->uscratch.p, h->dscratch.p);
+    moments_kernel<<<g, kThreads, 0, h->stream>>>(h->pts.p, h->n, h->ff, h->partials.p, h->uscratch.p,
+                                                  h->dscratch.p);
     ++h->launches;
     CU(cudaGetLastError());
   }
@@ -266,19 +266,22 @@ int compute_moments(mdkm_handle* h, double* mean_var_out) {
   return MDKM_OK;
 }
 
-template <typename LabT, bool kPrivate>
-int launch_step_t(mdkm_handle* h, const StepParams& sp, size_t smem, int grid) {
-  lloyd_step_kernel<LabT, kPrivate><<<grid, kThreads, smem, h->stream>>>(sp);
-  ++h->launches;
-  CU(cudaGetLastError());
-  return MDKM_OK;
+// Step-kernel variants: label width x accumulator slices x compile-time table chunks.
+typedef void (*StepKernel)(const StepParams);
+StepKernel pick_step_kernel(bool wide, bool priv, int kpad) {
+  const int chunks = kpad <= 32 ? 1 : (kpad <= 64 ? 2 : 0);
+  if (wide) return lloyd_step_kernel<unsigned short, false, 0>;
+  if (priv) {
+    if (chunks == 1) return lloyd_step_kernel<unsigned char, true, 1>;
+    if (chunks == 2) return lloyd_step_kernel<unsigned char, true, 2>;
+    return lloyd_step_kernel<unsigned char, true, 0>;
+  }
+  return lloyd_step_kernel<unsigned char, false, 0>;
 }
 
-template <typename LabT, bool kPrivate>
-int step_occupancy(mdkm_handle* h, size_t smem, int* occ) {
-  CU(cudaFuncSetAttribute(lloyd_step_kernel<LabT, kPrivate>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lloyd_step_kernel<LabT, kPrivate>, kThreads, smem));
+int step_occupancy(mdkm_handle* h, StepKernel fn, size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fn, kThreads, smem));
   return MDKM_OK;
 }
 
@@ -303,6 +306,7 @@ struct KmBuffers {
   int step_grid, final_grid;
   bool wide;     // uint16 labels
   bool priv;     // per-warp accumulator slices in shared memory
+  StepKernel step_fn;
 };
 
 int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
@@ -318,7 +322,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   const size_t ring = (size_t)(kThreads / 32) * kStages * (kb.wide ? stage_bytes<unsigned short>() : stage_bytes<unsigned char>());
   kb.step_smem = kp32 * 32 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1);
   kb.final_smem = kp32 * 32;
-  const long long cap = round_up(std::max<long long>(h->n, 1), kTile);
+  const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
   OK(ensure(h, h->table, table_bytes(kb.kpad)));
   OK(ensure(h, h->acc, (size_t)kb.kpad * 4 + 8));
@@ -327,14 +331,10 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   const long long tiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);  // 8 warp-groups per CTA pass
   // persistent grids: one full wave of resident CTAs (occupancy queried from the runtime)
   int occ_step = 1, occ_final = 1;
-  if (kb.wide) {
-    OK((step_occupancy<unsigned short, false>(h, kb.step_smem, &occ_step)));
-    OK(final_occupancy<unsigned short>(h, kb.final_smem, &occ_final));
-  } else {
-    if (kb.priv) OK((step_occupancy<unsigned char, true>(h, kb.step_smem, &occ_step)));
-    else OK((step_occupancy<unsigned char, false>(h, kb.step_smem, &occ_step)));
-    OK(final_occupancy<unsigned char>(h, kb.final_smem, &occ_final));
-  }
+  kb.step_fn = pick_step_kernel(kb.wide, kb.priv, kb.kpad);
+  OK(step_occupancy(h, kb.step_fn, kb.step_smem, &occ_step));
+  if (kb.wide) OK(final_occupancy<unsigned short>(h, kb.final_smem, &occ_final));
+  else OK(final_occupancy<unsigned char>(h, kb.final_smem, &occ_final));
   if (occ_step < 1) return fail(h, MDKM_ERR_INVALID, "k=%d does not fit the shared-memory tables", k);
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
@@ -351,7 +351,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
 
 int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
   StepParams sp{};
-  sp.x = h->x.p; sp.y = h->y.p; sp.z = h->z.p; sp.n = h->n;
+  sp.pts = h->pts.p; sp.n = h->n;
   sp.labels = h->labels.p;
   sp.table = h->table.p;
   sp.acc = h->acc.p;
@@ -370,9 +370,9 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
     e1 = h->prof_ev[h->prof_used++];
     CU(cudaEventRecord(e0, h->stream));
   }
-  if (kb.wide) OK((launch_step_t<unsigned short, false>(h, sp, kb.step_smem, kb.step_grid)));
-  else if (kb.priv) OK((launch_step_t<unsigned char, true>(h, sp, kb.step_smem, kb.step_grid)));
-  else OK((launch_step_t<unsigned char, false>(h, sp, kb.step_smem, kb.step_grid)));
+  kb.step_fn<<<kb.step_grid, kThreads, kb.step_smem, h->stream>>>(sp);
+  ++h->launches;
+  CU(cudaGetLastError());
   if (h->prof) CU(cudaEventRecord(e1, h->stream));
   return MDKM_OK;
 }
@@ -440,7 +440,7 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
     for (int r = 0; r < h->rank; ++r) rank_offset += sizes[r];
   }
   RelocParams rp{};
-  rp.x = h->x.p; rp.y = h->y.p; rp.z = h->z.p; rp.n = h->n;
+  rp.pts = h->pts.p; rp.n = h->n;
   rp.labels = h->labels.p; rp.wide = kb.wide ? 1 : 0;
   rp.table = h->table.p; rp.kpad = kb.kpad; rp.k = kb.k;
   rp.f = h->ff;
@@ -471,7 +471,7 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
 int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_assign) {
   CU(cudaMemsetAsync(h->uscratch.p, 0, 4, h->stream));
   FinalParams fp{};
-  fp.x = h->x.p; fp.y = h->y.p; fp.z = h->z.p; fp.n = h->n;
+  fp.pts = h->pts.p; fp.n = h->n;
   fp.labels = h->labels.p;
   fp.labels_out = labels_dev;
   fp.table = h->table.p;
@@ -530,7 +530,7 @@ void mdkm_destroy(mdkm_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
-  release(h->x); release(h->y); release(h->z);
+  release(h->pts);
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
   release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
@@ -583,24 +583,17 @@ int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int
   CU(cudaSetDevice(h->device));
   OK(alloc_points(h, n));
   h->n = n;
-  const cudaMemcpyKind kind = mem == MDKM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (n > 0) {
-    if (layout == MDKM_POINTS_SOA) {
-      CU(cudaMemcpyAsync(h->x.p, xyz, (size_t)n * 4, kind, h->stream));
-      CU(cudaMemcpyAsync(h->y.p, xyz + n, (size_t)n * 4, kind, h->stream));
-      CU(cudaMemcpyAsync(h->z.p, xyz + 2 * n, (size_t)n * 4, kind, h->stream));
-    } else {
-      const float* src = xyz;
-      if (mem != MDKM_MEM_DEVICE) {
-        OK(ensure(h, h->staging, (size_t)n * 12));
-        CU(cudaMemcpyAsync(h->staging.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
-        src = reinterpret_cast<const float*>(h->staging.p);
-      }
-      aos_to_soa_kernel<<<grid_for(h, (n + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
-          src, n, h->x.p, h->y.p, h->z.p);
-      ++h->launches;
-      CU(cudaGetLastError());
+    const float* src = xyz;
+    if (mem != MDKM_MEM_DEVICE) {
+      OK(ensure(h, h->staging, (size_t)n * 12));
+      CU(cudaMemcpyAsync(h->staging.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+      src = reinterpret_cast<const float*>(h->staging.p);
     }
+    to_blocked_kernel<<<grid_for(h, (n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+        src, n, layout == MDKM_POINTS_SOA ? 1 : 0, h->pts.p);
+    ++h->launches;
+    CU(cudaGetLastError());
   }
   OK(zero_tail(h));
   h->have_points = true;
@@ -617,9 +610,10 @@ int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz
   CU(cudaSetDevice(h->device));
   for (int i = 0; i < m; ++i) {
     if (idx[i] < 0 || idx[i] >= h->n) return fail(h, MDKM_ERR_INVALID, "gather index %lld out of range", (long long)idx[i]);
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 0, h->x.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 1, h->y.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 2, h->z.p + idx[i], 4, cudaMemcpyDeviceToHost, h->stream));
+    const float* q = h->pts.p + pt_off(idx[i]);
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 0, q, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 1, q + kGroup, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_xyz + 3 * i + 2, q + 2 * kGroup, 4, cudaMemcpyDeviceToHost, h->stream));
   }
   CU(cudaStreamSynchronize(h->stream));
   return MDKM_OK;
@@ -664,7 +658,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   up.scale = hm_scale; up.max_abs = max_abs;
   up.chunk_counts = h->chunk_counts.p;
   up.chunk_offsets = h->chunk_offsets.p;
-  up.x = h->x.p; up.y = h->y.p; up.z = h->z.p;
+  up.pts = h->pts.p;
   up.planes = nullptr;
   up.day0 = (int)(pix_begin / HW);
   long long n_out = 0;
@@ -709,8 +703,8 @@ int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem) {
     OK(ensure(h, h->staging, (size_t)h->n * 12));
     dst = reinterpret_cast<float*>(h->staging.p);
   }
-  soa_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
-      h->x.p, h->y.p, h->z.p, h->n, napari_order, 0.0f, dst);
+  blocked_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+      h->pts.p, h->n, napari_order, dst);
   ++h->launches;
   CU(cudaGetLastError());
   if (mem != MDKM_MEM_DEVICE) CU(cudaMemcpyAsync(out, dst, (size_t)h->n * 12, cudaMemcpyDeviceToHost, h->stream));
@@ -881,7 +875,7 @@ int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
   if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_ground_level is single-rank");
   CU(cudaSetDevice(h->device));
-  return ground_level_impl(h->stream, h->x.p, h->y.p, h->z.p, h->n, height_norm_out, mem, h_min_out, h_max_out,
+  return ground_level_impl(h->stream, h->pts.p, h->n, height_norm_out, mem, h_min_out, h_max_out,
                            &h->launches) == 0
              ? (h->frame_ok = false, compute_frame(h))
              : fail(h, MDKM_ERR_CUDA, "ground_level failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -897,7 +891,7 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
   if (k > 1 && (!rand_vals || n_local_trials < 1)) return fail(h, MDKM_ERR_INVALID, "rand_vals required");
   CU(cudaSetDevice(h->device));
   if (!h->frame_ok) OK(compute_frame(h));
-  const int rc = kmeanspp_impl(h->stream, h->sm_count, h->x.p, h->y.p, h->z.p, h->n, h->ff, k, (long long)first_index, rand_vals,
+  const int rc = kmeanspp_impl(h->stream, h->sm_count, h->pts.p, h->n, h->ff, k, (long long)first_index, rand_vals,
                                n_local_trials, centers_out, reinterpret_cast<long long*>(indices_out), &h->launches);
   if (rc != 0) return fail(h, MDKM_ERR_CUDA, "kmeans++ failed: %s", cudaGetErrorString(cudaGetLastError()));
   return MDKM_OK;

@@ -31,9 +31,7 @@ struct UnprojParams {
   float max_abs;
   unsigned int* chunk_counts;
   const long long* chunk_offsets;
-  float* x;
-  float* y;
-  float* z;
+  float* pts;             // blocked cloud (common.cuh)
   const double* planes;   // [n_days][8]: centre xyz, normal xyz, pad -- or nullptr
   int day0;               // day index of planes[0]
 };
@@ -180,9 +178,10 @@ __global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const Unpro
               zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] +
                            ((double)h[e] - pl[2]) * pl[5]);
             }
-            p.x[o] = (float)col;
-            p.y[o] = (float)row;
-            p.z[o] = zz;
+            float* dst = p.pts + pt_off(o);
+            dst[0] = (float)col;
+            dst[kGroup] = (float)row;
+            dst[2 * kGroup] = zz;
             ++o;
           }
           if (++col == p.W) {
@@ -333,18 +332,20 @@ __host__ __device__ inline float ord2f(unsigned int u) {
 }
 
 // out[0..2] = ordered min x,y,z ; out[3..5] = ordered max.  Caller pre-fills min with
-// 0xffffffff and max with 0.
-__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* x, const float* y, const float* z,
-                                                          long long n, unsigned int* out) {
+// 0xffffffff and max with 0.  One warp per 128-point block of the blocked cloud.
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* pts, long long n, unsigned int* out) {
   float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
   float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
-  const long long n4 = (n + 3) / 4;
-  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < n4; q += (long long)gridDim.x * kThreads) {
-    const float4 vx = ldg_stream_f4(x + q * 4), vy = ldg_stream_f4(y + q * 4), vz = ldg_stream_f4(z + q * 4);
+  const int lane = threadIdx.x & 31;
+  const long long n_groups = (n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < n_groups; g += stride) {
+    const float* blk = pts + g * kBlockFloats + lane * 4;
+    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
     const float ax[4] = {vx.x, vx.y, vx.z, vx.w}, ay[4] = {vy.x, vy.y, vy.z, vy.w}, az[4] = {vz.x, vz.y, vz.z, vz.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (q * 4 + e < n) {
+      if (g * kGroup + lane * 4 + e < n) {
         mn[0] = fminf(mn[0], ax[e]); mx[0] = fmaxf(mx[0], ax[e]);
         mn[1] = fminf(mn[1], ay[e]); mx[1] = fmaxf(mx[1], ay[e]);
         mn[2] = fminf(mn[2], az[e]); mx[2] = fmaxf(mx[2], az[e]);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const float* x, const 
   for (int d = 0; d < 3; ++d) {
     const unsigned int a = __reduce_min_sync(0xffffffffu, f2ord(mn[d]));
     const unsigned int b = __reduce_max_sync(0xffffffffu, f2ord(mx[d]));
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       atomicMin(&out[d], a);
       atomicMax(&out[3 + d], b);
     }
@@ -363,19 +364,21 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const float* x, const 
 
 // partials[b][6] = sum (x-o), sum (x-o)^2 per dim, in FP64, fixed order inside the CTA;
 // the last CTA adds the partials in CTA order into out[6].
-__global__ void __launch_bounds__(kThreads) moments_kernel(const float* x, const float* y, const float* z,
-                                                           long long n, FrameF f, double* partials,
+__global__ void __launch_bounds__(kThreads) moments_kernel(const float* pts, long long n, FrameF f, double* partials,
                                                            unsigned int* ticket, double* out) {
   __shared__ double s_red[kThreads / 32];
   __shared__ bool s_last;
   double m[6] = {0, 0, 0, 0, 0, 0};
-  const long long n4 = (n + 3) / 4;
-  for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < n4; q += (long long)gridDim.x * kThreads) {
-    const float4 vx = ldg_stream_f4(x + q * 4), vy = ldg_stream_f4(y + q * 4), vz = ldg_stream_f4(z + q * 4);
+  const int lane = threadIdx.x & 31;
+  const long long n_groups = (n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < n_groups; g += stride) {
+    const float* blk = pts + g * kBlockFloats + lane * 4;
+    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
     const float ax[4] = {vx.x, vx.y, vx.z, vx.w}, ay[4] = {vy.x, vy.y, vy.z, vy.w}, az[4] = {vz.x, vz.y, vz.z, vz.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (q * 4 + e < n) {
+      if (g * kGroup + lane * 4 + e < n) {
         const double X = (double)ax[e] - (double)f.ox, Y = (double)ay[e] - (double)f.oy,
                      Z = (double)az[e] - (double)f.oz;
         m[0] += X; m[1] += Y; m[2] += Z;
@@ -409,25 +412,43 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const float* x, const
   }
 }
 
-// AoS [n][3] -> SoA, or SoA -> [n][3] in (x,y,z) or napari (z,y,x) order.
-__global__ void __launch_bounds__(kThreads) aos_to_soa_kernel(const float* xyz, long long n, float* x, float* y,
-                                                              float* z) {
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-    x[i] = xyz[3 * i + 0];
-    y[i] = xyz[3 * i + 1];
-    z[i] = xyz[3 * i + 2];
+// [n][3] (x,y,z) or SoA x[n] y[n] z[n]  ->  blocked cloud
+__global__ void __launch_bounds__(kThreads) to_blocked_kernel(const float* src, long long n, int soa, float* pts) {
+  const long long total = n * 3;
+  for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+    long long i;
+    int c;
+    if (soa) {
+      c = (int)(t / n);
+      i = t - (long long)c * n;
+    } else {
+      i = t / 3;
+      c = (int)(t - i * 3);
+    }
+    pts[pt_off(i) + c * kGroup] = src[t];  // coalesced reads
   }
 }
 
-__global__ void __launch_bounds__(kThreads) soa_to_aos_kernel(const float* x, const float* y, const float* z,
-                                                              long long n, int napari, float zshift, float* out) {
-  // each thread writes one float of the interleaved output: fully coalesced stores
+// zero the unused tail of the last block (and nothing else)
+__global__ void zero_tail_kernel(float* pts, long long n) {
+  const long long cap = (n + kGroup - 1) / kGroup * kGroup;
+  for (long long i = n + threadIdx.x; i < cap; i += blockDim.x) {
+    float* d = pts + pt_off(i);
+    d[0] = 0.f;
+    d[kGroup] = 0.f;
+    d[2 * kGroup] = 0.f;
+  }
+}
+
+// blocked cloud -> [n][3] in (x,y,z) or napari (z,y,x) order; coalesced stores
+__global__ void __launch_bounds__(kThreads) blocked_to_aos_kernel(const float* pts, long long n, int napari,
+                                                                  float* out) {
   const long long total = n * 3;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
     const long long i = t / 3;
     const int c = (int)(t - i * 3);
     const int src = napari ? 2 - c : c;
-    out[t] = src == 0 ? x[i] : (src == 1 ? y[i] : z[i] - zshift);
+    out[t] = pts[pt_off(i) + src * kGroup];
   }
 }
 
