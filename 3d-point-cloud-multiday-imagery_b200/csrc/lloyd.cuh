@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
   const int n_slices = kPrivate ? kWarps : 1;
   unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
   if (tid == 0) {
@@ -359,34 +359,30 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const bool first_iter = p.st->first != 0;
   const FrameF f = p.f;
 
-  const long long n_groups = (p.n + kGroup - 1) / kGroup;
-  const long long n_full = p.n / kGroup;  // groups below this index have 128 real points
-  const long long stride = (long long)gridDim.x * kWarps;
-  const long long g0 = (long long)blockIdx.x * kWarps + warp;
-  // per-warp stage addresses / source cursors (advanced by one stride per group)
-  const uint32_t ring_a = smem_u32(s_ring + warp * (kStages * kStageB));
-  const uint32_t gbar_a = smem_u32(s_gbar + warp * kStages);
-  const unsigned char* ring = s_ring + warp * (kStages * kStageB);
-  const float* src_pts = p.pts + g0 * kBlockFloats;         // next group to FETCH
-  const LabT* src_lab = reinterpret_cast<const LabT*>(p.labels) + g0 * kGroup;
-  LabT* dst_lab = reinterpret_cast<LabT*>(p.labels) + g0 * kGroup + lane * 4;  // group being PROCESSED
-  const long long pts_step = stride * kBlockFloats, lab_step = stride * kGroup;
-  long long g_fetch = g0;
+  // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
+  const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
+  const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
+  const int stride = (int)gridDim.x * kWarps;
+  const int g0 = (int)blockIdx.x * kWarps + warp;
+  const uint32_t ring_a = smem_u32(s_ring) + warp * (kStages * kStageB);
+  const uint32_t gbar_a = smem_u32(s_gbar) + warp * (kStages * 8);
+  const float* pts = p.pts;
+  LabT* labels = reinterpret_cast<LabT*>(p.labels);
+  int g_fetch = g0;
 
-  auto issue = [&](int stage) {  // lane 0 only: fetch group g_fetch into `stage`
-    const uint32_t dst = ring_a + stage * kStageB, bar = gbar_a + stage * 8;
-    mbar_expect_tx_a(bar, (uint32_t)kStageB);
-    tma_load_1d_a(dst, src_pts, kBlockFloats * 4, bar);
-    tma_load_1d_a(dst + kBlockFloats * 4, src_lab, kLabB, bar);
-  };
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      if (g_fetch < n_groups) issue(s);
-      g_fetch += stride;
-      src_pts += pts_step;
-      src_lab += lab_step;
+  // one elected lane fetches group `gf` into `stage`: the 1536-byte xyz block and its labels
+  auto issue = [&](int stage, int gf) {
+    if (elect_one()) {
+      const uint32_t dst = ring_a + stage * kStageB, bar = gbar_a + stage * 8;
+      mbar_expect_tx_a(bar, (uint32_t)kStageB);
+      tma_load_1d_a(dst, pts + (size_t)gf * kBlockFloats, kBlockFloats * 4, bar);
+      tma_load_1d_a(dst + kBlockFloats * 4, labels + (size_t)gf * kGroup, kLabB, bar);
     }
+  };
+#pragma unroll
+  for (int s = 0; s < kStages; ++s) {
+    if (g_fetch < n_groups) issue(s, g_fetch);
+    g_fetch += stride;
   }
   mbar_wait(&s_bar, 0);
 
@@ -398,12 +394,13 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   int stage = 0;
   uint32_t parity = 0;
 
-  for (long long g = g0; g < n_groups; g += stride) {
+  for (int g = g0; g < n_groups; g += stride) {
+    const uint32_t st_a = ring_a + stage * kStageB + lane * 16;
     mbar_wait_a(gbar_a + stage * 8, parity);
-    const unsigned char* src = ring + stage * kStageB;
-    const float4 vx = *reinterpret_cast<const float4*>(src + lane * 16);
-    const float4 vy = *reinterpret_cast<const float4*>(src + kGroup * 4 + lane * 16);
-    const float4 vz = *reinterpret_cast<const float4*>(src + kGroup * 8 + lane * 16);
+    const float4 vx = lds_f4(st_a);
+    const float4 vy = lds_f4(st_a + kGroup * 4);
+    const float4 vz = lds_f4(st_a + kGroup * 8);
+    const unsigned char* src = s_ring + warp * (kStages * kStageB) + stage * kStageB;
     const typename LabPack<LabT>::V oldl = LabPack<LabT>::load(src + kBlockFloats * 4 + lane * LabPack<LabT>::kBytes);
     const float xc[4] = {vx.x - f.ox, vx.y - f.ox, vx.z - f.ox, vx.w - f.ox};
     const float yc[4] = {vy.x - f.oy, vy.y - f.oy, vy.z - f.oy, vy.w - f.oy};
@@ -413,17 +410,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
                                             reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
                                             reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast,
                                             s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
+    // every value read from the stage has been consumed: refill it with the group kStages
+    // ahead (the reads completed before this point, so the async-proxy write cannot race)
     __syncwarp();
-    if (lane == 0) {
-      // every lane is done with the stage: refill it with the group kStages ahead
-      if (g_fetch < n_groups) {
-        fence_proxy_async();
-        issue(stage);
-      }
-      g_fetch += stride;
-      src_pts += pts_step;
-      src_lab += lab_step;
-    }
+    if (g_fetch < n_groups) issue(stage, g_fetch);
+    g_fetch += stride;
     if (++stage == kStages) {
       stage = 0;
       parity ^= 1u;
@@ -431,12 +422,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
 
     const bool full = g < n_full;  // warp-uniform
     const typename LabPack<LabT>::V newl = LabPack<LabT>::pack(lab);
-    LabPack<LabT>::store(dst_lab, newl);
-    dst_lab += lab_step;
+    LabPack<LabT>::store(labels + (size_t)g * kGroup + lane * 4, newl);
     if (first_iter) {
-      n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - (g * kGroup + lane * 4)));
+      n_chg += full ? 4u : (unsigned int)max(0LL, min(4LL, p.n - ((long long)g * kGroup + lane * 4)));
     } else if (!LabPack<LabT>::same(newl, oldl)) {
-      const long long i0 = g * kGroup + lane * 4;
+      const long long i0 = (long long)g * kGroup + lane * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         n_chg += ((full || i0 + e < p.n) && lab[e] != LabPack<LabT>::get(oldl, e)) ? 1u : 0u;
@@ -454,19 +444,23 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const int tx = (int)(ux[0] + ux[1] + ux[2] + ux[3] - 4u * kMagicBits);
     const int ty = (int)(uy[0] + uy[1] + uy[2] + uy[3] - 4u * kMagicBits);
     const int tz = (int)(uz[0] + uz[1] + uz[2] + uz[3] - 4u * kMagicBits);
-    bool uniform = full && (ncand <= 1);  // a lone candidate labels the whole group
+    // 0: one label for the whole group, 1: one label per lane, 2: mixed inside lanes / tail
+    int mode = 2;
     int l0 = lab[0];
-    bool t_all = uniform;
-    if (!uniform && full) {
-      const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
-      t_all = __all_sync(0xffffffffu, t_uni);
-      if (t_all) {
-        l0 = __shfl_sync(0xffffffffu, lab[0], 0);
-        uniform = __all_sync(0xffffffffu, lab[0] == l0);
+    if (full) {
+      if (ncand <= 1) {
+        mode = 0;  // a lone candidate labels the whole group
+      } else {
+        const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
+        if (__all_sync(0xffffffffu, t_uni)) {
+          l0 = __shfl_sync(0xffffffffu, lab[0], 0);
+          mode = __all_sync(0xffffffffu, lab[0] == l0) ? 0 : 1;
+        }
       }
     }
-    if (uniform) {
-      // the whole group has one label: three REDUX + register accumulation
+    if (mode == 0) {
+      // three REDUX + register accumulation; shared memory is touched only when the label of
+      // this warp's run of groups changes
       const int sx = __reduce_add_sync(0xffffffffu, tx);
       const int sy = __reduce_add_sync(0xffffffffu, ty);
       const int sz = __reduce_add_sync(0xffffffffu, tz);
@@ -480,10 +474,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       wy += sy;
       wz += sz;
       wn += kGroup;
-    } else if (t_all) {
+    } else if (mode == 1) {
       warp_segmented_add<kPrivate>(s_acc, true, lab[0], tx, ty, tz, 4, lane);
     } else {
-      const long long i0 = g * kGroup + lane * 4;
+      const long long i0 = (long long)g * kGroup + lane * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         warp_segmented_add<kPrivate>(s_acc, full || (i0 + e < p.n), lab[e], (int)(ux[e] - kMagicBits),

@@ -73,6 +73,25 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// One lane of the (converged) warp is elected; true in that lane only.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
 // Order this thread's generic-proxy shared-memory accesses before later async-proxy (TMA) ones.
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
