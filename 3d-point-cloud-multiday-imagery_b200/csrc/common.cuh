@@ -57,12 +57,11 @@ struct FrameF {
   float sx, sy, sz;    // fixed-point scales (powers of two)
 };
 
-// One centroid table in global memory: [Kpad] float4 fast rows, [Kpad] float4 plain rows, then
-// [Kpad] double4 exact rows.
+// One centroid table in global memory: [Kpad] float4 fast rows, then [Kpad] double4 exact rows.
 //   fast row  = (-2c'x, -2c'y, -2c'z, ||c'||^2) rounded to FP32 ; padding rows = (0,0,0,+inf)
-//   plain row = ( c'x,   c'y,   c'z,  0)        rounded to FP32 ; padding rows = 1e18
 //   exact row = ( c'x,   c'y,   c'z,  ||c'||^2) in FP64, c' = c - origin
 __host__ __device__ inline int pad_k(int k) { return (k + 7) & ~7; }
-__host__ __device__ inline size_t table_bytes(int kpad) { return (size_t)kpad * (16 + 16 + 32); }
+__host__ __device__ inline size_t table_bytes(int kpad) { return (size_t)kpad * (16 + 32); }
+__host__ __device__ inline size_t exact_offset(int kpad) { return (size_t)kpad * 16; }
 
 }  // namespace mdkm

@@ -52,7 +52,7 @@ __device__ __forceinline__ double reloc_dist(const RelocParams& p, const double4
 }
 
 __global__ void __launch_bounds__(kThreads) reloc_maxdist_kernel(const RelocParams p) {
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);  // exact rows
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   unsigned long long best = 0ull;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (long long)gridDim.x * kThreads) {
     if (reloc_taken(p, p.rank_offset + i)) continue;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) reloc_maxdist_kernel(const RelocPara
 }
 
 __global__ void __launch_bounds__(kThreads) reloc_argidx_kernel(const RelocParams p) {
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);  // exact rows
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const unsigned long long target = p.scratch[0];
   unsigned long long best = ~0ull;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (long long)gridDim.x * kThreads) {

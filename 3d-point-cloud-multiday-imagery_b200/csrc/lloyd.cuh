@@ -67,31 +67,32 @@ __device__ __forceinline__ double4 ld_c64(const double4* p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// Bounds of |x - c|^2 over the box [b0, b1] for one centroid row.
-__device__ __forceinline__ void box_bounds(const float4 c, float bx0, float bx1, float by0, float by1, float bz0,
-                                           float bz1, float& lb, float& ub) {
-  const float ax = c.x - bx0, ay = c.y - by0, az = c.z - bz0;  // >= 0 when c is right of the low face
-  const float dx = bx1 - c.x, dy = by1 - c.y, dz = bz1 - c.z;  // >= 0 when c is left of the high face
-  const float hx = fmaxf(ax, dx), hy = fmaxf(ay, dy), hz = fmaxf(az, dz);
-  ub = fmaf(hx, hx, fmaf(hy, hy, hz * hz));
-  const float lx = fmaxf(fmaxf(-ax, -dx), 0.0f), ly = fmaxf(fmaxf(-ay, -dy), 0.0f), lz = fmaxf(fmaxf(-az, -dz), 0.0f);
-  lb = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+// Can centroid `row` beat the reference centroid `ref` anywhere in the box?  Both rows are in
+// the expanded form (-2c', ||c'||^2), so d_row(x) - d_ref(x) = a.w + a.xyz . x is LINEAR in x
+// and its minimum over the box is attained at a corner, coordinate by coordinate.
+__device__ __forceinline__ float min_gap_over_box(const float4 row, const float4 ref, float bx0, float bx1,
+                                                  float by0, float by1, float bz0, float bz1) {
+  const float ax = row.x - ref.x, ay = row.y - ref.y, az = row.z - ref.z, aw = row.w - ref.w;
+  return aw + fminf(ax * bx0, ax * bx1) + fminf(ay * by0, ay * by1) + fminf(az * bz0, az * bz1);
 }
 
 // ---------------------------------------------------------------------------------------
 // Assignment of one warp-group.  xc/yc/zc: centred FP32 coordinates of this lane's 4 points;
 // orig_*: this lane's four ORIGINAL coordinates (shared-memory stage or registers), read only
-// by the FP64 refine.  s_fast: expanded rows (-2c', ||c'||^2); s_plain: (c', 0) rows, both
-// padded to a multiple of 32 rows (padding rows are never candidates).  kChunks = rows/32 when
-// known at compile time (straight-line code), 0 = run-time loop.  Warp-synchronous: all 32
-// lanes must call it.  Returns the number of candidate centroids of the group; the labels of
-// this lane's points are in lab[].
+// by the FP64 refine.  s_fast: expanded rows (-2c', ||c'||^2) padded with (0,0,0,+inf) rows to
+// a multiple of 32.  kChunks = rows/32 when known at compile time (straight-line code),
+// 0 = run-time loop.  Warp-synchronous: all 32 lanes must call it.
+//
+// Pruning: take the centroid i nearest to the centre of the group's bounding box; centroid j
+// stays a candidate only if it can beat i somewhere in the box (min_gap_over_box <= margin).
+// The true nearest centroid of every point, and every centroid within the FP32 error band of
+// it, beats-or-ties i at that point, so it is a candidate: the result equals brute force.
+// Returns the number of candidates; the labels of this lane's points are in lab[].
 // ---------------------------------------------------------------------------------------
 template <int kChunks>
 __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
                                             const float* orig_x, const float* orig_y, const float* orig_z,
                                             const FrameF& f, const float4* __restrict__ s_fast,
-                                            const float4* __restrict__ s_plain,
                                             const double4* __restrict__ c64, int k, int kp32, float thresh,
                                             int lane, int (&lab)[4], unsigned int& n_refined) {
   // bounding box of the group (FMNMX3 + CREDUX.F32)
@@ -101,44 +102,58 @@ __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&
   const float by1 = redux_max_f32(fmaxf(fmaxf(yc[0], yc[1]), fmaxf(yc[2], yc[3])));
   const float bz0 = redux_min_f32(fminf(fminf(zc[0], zc[1]), fminf(zc[2], zc[3])));
   const float bz1 = redux_max_f32(fmaxf(fmaxf(zc[0], zc[1]), fmaxf(zc[2], zc[3])));
+  const float mx = 0.5f * (bx0 + bx1), my = 0.5f * (by0 + by1), mz = 0.5f * (bz0 + bz1);
+  // margin: 4*thresh = 8E covers the FP32 rounding of the gap expression and of the fast
+  // distances themselves (E bounds the error of one fast distance, DESIGN.md "Exactness")
+  const float margin = 4.0f * thresh;
 
   constexpr int kM = kChunks > 0 ? kChunks : 1;
   unsigned int masks[kM];
   int ncand = 0, first = 0;
-  float bound;
+  float4 ref;
   if (kChunks > 0) {
-    // one pass: lower and upper bound of every centroid, then the candidate ballots
-    float lb[kM];
-    float ub = __int_as_float(0x7f800000);
+    float4 row[kM];
+    float dc[kM];
+    float dmin = __int_as_float(0x7f800000);
 #pragma unroll
     for (int c = 0; c < kM; ++c) {
-      float u;
-      box_bounds(s_plain[c * 32 + lane], bx0, bx1, by0, by1, bz0, bz1, lb[c], u);
-      ub = fminf(ub, u);
+      row[c] = s_fast[c * 32 + lane];
+      dc[c] = fmaf(mx, row[c].x, fmaf(my, row[c].y, fmaf(mz, row[c].z, row[c].w)));
+      dmin = fminf(dmin, dc[c]);
     }
-    ub = redux_min_f32(ub);
-    // margin: relative slack for the FP32 box arithmetic + 2*thresh (= 4E) for the rounding of
-    // the centroid rows and of the fast distances themselves
-    bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
+    dmin = redux_min_f32(dmin);
+    int iref = 0;
 #pragma unroll
     for (int c = kM - 1; c >= 0; --c) {
-      masks[c] = __ballot_sync(0xffffffffu, lb[c] <= bound);
+      const unsigned int m = __ballot_sync(0xffffffffu, dc[c] == dmin);
+      if (m) iref = c * 32 + __ffs(m) - 1;
+    }
+    ref = s_fast[iref];
+#pragma unroll
+    for (int c = kM - 1; c >= 0; --c) {
+      const float gap = min_gap_over_box(row[c], ref, bx0, bx1, by0, by1, bz0, bz1);
+      masks[c] = __ballot_sync(0xffffffffu, gap <= margin);
       ncand += __popc(masks[c]);
       if (masks[c]) first = c * 32 + __ffs(masks[c]) - 1;
     }
   } else {
-    float ub = __int_as_float(0x7f800000);
+    float dmin = __int_as_float(0x7f800000);
     for (int j = lane; j < kp32; j += 32) {
-      float l, u;
-      box_bounds(s_plain[j], bx0, bx1, by0, by1, bz0, bz1, l, u);
-      ub = fminf(ub, u);
+      const float4 r = s_fast[j];
+      dmin = fminf(dmin, fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w))));
     }
-    ub = redux_min_f32(ub);
-    bound = fmaf(ub, 1.0e-4f, ub) + 2.0f * thresh;
+    dmin = redux_min_f32(dmin);
+    int iref = -1;
+    for (int base = 0; base < kp32 && iref < 0; base += 32) {
+      const float4 r = s_fast[base + lane];
+      const unsigned int m =
+          __ballot_sync(0xffffffffu, fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w))) == dmin);
+      if (m) iref = base + __ffs(m) - 1;
+    }
+    ref = s_fast[iref < 0 ? 0 : iref];
     for (int base = 0; base < kp32; base += 32) {
-      float l, u;
-      box_bounds(s_plain[base + lane], bx0, bx1, by0, by1, bz0, bz1, l, u);
-      const unsigned int m = __ballot_sync(0xffffffffu, l <= bound);
+      const float gap = min_gap_over_box(s_fast[base + lane], ref, bx0, bx1, by0, by1, bz0, bz1);
+      const unsigned int m = __ballot_sync(0xffffffffu, gap <= margin);
       if (ncand == 0 && m) first = base + __ffs(m) - 1;
       ncand += __popc(m);
     }
@@ -180,9 +195,8 @@ __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&
     }
   } else {
     for (int base = 0; base < kp32; base += 32) {
-      float l, u;
-      box_bounds(s_plain[base + lane], bx0, bx1, by0, by1, bz0, bz1, l, u);
-      unsigned int m = __ballot_sync(0xffffffffu, l <= bound);
+      const float gap = min_gap_over_box(s_fast[base + lane], ref, bx0, bx1, by0, by1, bz0, bz1);
+      unsigned int m = __ballot_sync(0xffffffffu, gap <= margin);
       while (m) {
         eval(base + __ffs(m) - 1);
         m &= m - 1;
@@ -321,8 +335,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kp32 = kChunks > 0 ? kChunks * 32 : ((p.kpad + 31) & ~31);  // rows staged in shared memory
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);
-  float4* s_plain = s_fast + kp32;
-  unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_plain + kp32);
+  unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_fast + kp32);
   unsigned long long* s_acc_all = reinterpret_cast<unsigned long long*>(s_ring + kWarps * kStages * kStageB);
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ __align__(8) uint64_t s_gbar[kWarps * kStages];
@@ -345,16 +358,14 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // rows [kpad, kp32) are not covered by the bulk copies: make them non-candidates
   for (int i = p.kpad + tid; i < kp32; i += kThreads) {
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-    s_plain[i] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
   }
   __syncthreads();
   if (tid == 0) {
-    // centroid rows: global -> shared through the TMA unit (two 1-D bulk copies, one barrier)
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 32u);
+    // centroid rows: global -> shared through the TMA unit (1-D bulk copy)
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
-    tma_load_1d(s_plain, p.table + (size_t)p.kpad * 16, (uint32_t)p.kpad * 16u, &s_bar);
   }
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const float thresh = p.st->thresh;
   const bool first_iter = p.st->first != 0;
   const FrameF f = p.f;
@@ -362,8 +373,12 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
   const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
-  const int stride = (int)gridDim.x * kWarps;
-  const int g0 = (int)blockIdx.x * kWarps + warp;
+  // each warp owns a CONTIGUOUS range of groups: consecutive groups are neighbours in the
+  // raster, so label runs are long and the register accumulators below rarely flush
+  const int per_warp = (n_groups + (int)gridDim.x * kWarps - 1) / ((int)gridDim.x * kWarps);
+  const int g0 = ((int)blockIdx.x * kWarps + warp) * per_warp;
+  const int g_end = min(n_groups, g0 + per_warp);
+  constexpr int stride = 1;
   const uint32_t ring_a = smem_u32(s_ring) + warp * (kStages * kStageB);
   const uint32_t gbar_a = smem_u32(s_gbar) + warp * (kStages * 8);
   const float* pts = p.pts;
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   };
 #pragma unroll
   for (int s = 0; s < kStages; ++s) {
-    if (g_fetch < n_groups) issue(s, g_fetch);
+    if (g_fetch < g_end) issue(s, g_fetch);
     g_fetch += stride;
   }
   mbar_wait(&s_bar, 0);
@@ -394,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   int stage = 0;
   uint32_t parity = 0;
 
-  for (int g = g0; g < n_groups; g += stride) {
+  for (int g = g0; g < g_end; g += stride) {
     const uint32_t st_a = ring_a + stage * kStageB + lane * 16;
     mbar_wait_a(gbar_a + stage * 8, parity);
     const float4 vx = lds_f4(st_a);
@@ -409,11 +424,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const int ncand = assign_group<kChunks>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
                                             reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
                                             reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast,
-                                            s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
+                                            c64, p.k, kp32, thresh, lane, lab, n_ref);
     // every value read from the stage has been consumed: refill it with the group kStages
     // ahead (the reads completed before this point, so the async-proxy write cannot race)
     __syncwarp();
-    if (g_fetch < n_groups) issue(stage, g_fetch);
+    if (g_fetch < g_end) issue(stage, g_fetch);
     g_fetch += stride;
     if (++stage == kStages) {
       stage = 0;
@@ -576,8 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
   const int jmax = kMaxK * 2 - 1 - (int)(s_maxcnt & 0x1fffull);
 
   float4* fast = reinterpret_cast<float4*>(u.table);
-  float4* plain = fast + u.kpad;
-  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 32);
+  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
 
   double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
   for (int j = tid; j < u.kpad; j += kThreads) {
@@ -614,14 +628,12 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
       const double cn = cx * cx + cy * cy + cz * cz;
       exact[j] = make_double4(cx, cy, cz, cn);
       fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
-      plain[j] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
       m_cn = fmax(m_cn, cn);
       m_cx = fmax(m_cx, fabs(cx));
       m_cy = fmax(m_cy, fabs(cy));
       m_cz = fmax(m_cz, fabs(cz));
     } else {
       fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-      plain[j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
@@ -668,8 +680,7 @@ struct InitTableParams {
 __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTableParams u) {
   __shared__ double s_red[kThreads / 32];
   float4* fast = reinterpret_cast<float4*>(u.table);
-  float4* plain = fast + u.kpad;
-  double4* exact = reinterpret_cast<double4*>(u.table + (size_t)u.kpad * 32);
+  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
   double m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
   for (int j = threadIdx.x; j < u.kpad; j += kThreads) {
     if (j < u.k) {
@@ -679,14 +690,12 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
       const double cn = cx * cx + cy * cy + cz * cz;
       exact[j] = make_double4(cx, cy, cz, cn);
       fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
-      plain[j] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
       m_cn = fmax(m_cn, cn);
       m_cx = fmax(m_cx, fabs(cx));
       m_cy = fmax(m_cy, fabs(cy));
       m_cz = fmax(m_cz, fabs(cz));
     } else {
       fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-      plain[j] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
@@ -705,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
 // Reads the table back as K x 3 float64 centroids in original coordinates.
 __global__ void read_table_kernel(const unsigned char* table, int k, int kpad, Frame fr,
                                   double* centers_out) {
-  const double4* exact = reinterpret_cast<const double4*>(table + (size_t)kpad * 32);
+  const double4* exact = reinterpret_cast<const double4*>(table + exact_offset(kpad));
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const double4 c = exact[j];
     centers_out[3 * j + 0] = c.x + fr.origin[0];
@@ -734,7 +743,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kp32 = (p.kpad + 31) & ~31;
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);
-  float4* s_plain = s_fast + kp32;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ double s_red[kThreads / 32];
   __shared__ unsigned int s_refined;
@@ -749,15 +757,13 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   }
   for (int i = p.kpad + tid; i < kp32; i += kThreads) {
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-    s_plain[i] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 32u);
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
-    tma_load_1d(s_plain, p.table + (size_t)p.kpad * 16, (uint32_t)p.kpad * 16u, &s_bar);
   }
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + (size_t)p.kpad * 32);
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const float thresh = p.st->thresh;
   const bool reassign = p.force_assign || !p.st->strict;
   const FrameF f = p.f;
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
       const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
       const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
       const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
-      assign_group<0>(xc, yc, zc, xo, yo, zo, f, s_fast, s_plain, c64, p.k, kp32, thresh, lane, lab, n_ref);
+      assign_group<0>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
     } else {
       const typename LabPack<LabT>::V v = LabPack<LabT>::load(labels + i0);
 #pragma unroll

@@ -24,7 +24,6 @@ using namespace mdkm;
 
 namespace {
 
-constexpr long long kTile = 2048;  // capacity granularity of the point / label arrays
 constexpr int kBatch = 10;                          // Lloyd iterations enqueued between status polls
 
 template <typename T>
@@ -320,8 +319,8 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   const size_t kp32 = (size_t)((kb.kpad + 31) & ~31);
   kb.priv = !kb.wide && kb.kpad <= 128;
   const size_t ring = (size_t)(kThreads / 32) * kStages * (kb.wide ? stage_bytes<unsigned short>() : stage_bytes<unsigned char>());
-  kb.step_smem = kp32 * 32 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1);
-  kb.final_smem = kp32 * 32;
+  kb.step_smem = kp32 * 16 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1);
+  kb.final_smem = kp32 * 16;
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
   OK(ensure(h, h->table, table_bytes(kb.kpad)));
