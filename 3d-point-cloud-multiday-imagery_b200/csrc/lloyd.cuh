@@ -292,24 +292,6 @@ __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long
   }
 }
 
-// Segmented warp reduction for a group that is not label-uniform: one round per distinct label
-// among the active lanes; lane 0 adds the round's totals to the accumulator slice.
-template <bool kPrivate>
-__device__ __forceinline__ void warp_segmented_add(unsigned long long* s_acc, bool active, int l, int qx,
-                                                   int qy, int qz, int cnt, int lane) {
-  unsigned int todo = __ballot_sync(0xffffffffu, active);
-  while (todo) {
-    const int ll = __shfl_sync(0xffffffffu, l, __ffs(todo) - 1);
-    const bool mine = active && (l == ll);
-    const unsigned int peers = __ballot_sync(0xffffffffu, mine);
-    const int sx = __reduce_add_sync(0xffffffffu, mine ? qx : 0);
-    const int sy = __reduce_add_sync(0xffffffffu, mine ? qy : 0);
-    const int sz = __reduce_add_sync(0xffffffffu, mine ? qz : 0);
-    if (lane == 0) acc_add<kPrivate>(s_acc, ll, sx, sy, sz, (unsigned int)(cnt * __popc(peers)));
-    todo &= ~peers;
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // K2 + K3: assignment and per-cluster sums in one pass.
 //
@@ -401,10 +383,24 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   }
   mbar_wait(&s_bar, 0);
 
-  // warp-level run accumulator (identical in every lane)
-  long long wx = 0, wy = 0, wz = 0;
-  unsigned int wn = 0;
+  // run accumulator: while consecutive groups of this warp carry one label, every lane just
+  // adds its own four fixed-point coordinates (int32, no cross-lane traffic); the run is
+  // reduced with three REDUX and added to shared memory only when the label changes, a mixed
+  // group arrives, or after kRunMax groups (int32 headroom: 4 * 2^22 * 64 = 2^30)
+  constexpr int kRunMax = 64;
+  int rx = 0, ry = 0, rz = 0;
+  int run_groups = 0;
   int wlab = -1;
+  auto flush_run = [&]() {
+    if (run_groups > 0) {
+      const int sx = __reduce_add_sync(0xffffffffu, rx);
+      const int sy = __reduce_add_sync(0xffffffffu, ry);
+      const int sz = __reduce_add_sync(0xffffffffu, rz);
+      if (lane == 0) acc_add<kPrivate>(s_acc, wlab, sx, sy, sz, (unsigned int)run_groups * kGroup);
+      rx = ry = rz = 0;
+      run_groups = 0;
+    }
+  };
   unsigned int n_chg = 0, n_ref = 0;
   int stage = 0;
   uint32_t parity = 0;
@@ -459,47 +455,60 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const int tx = (int)(ux[0] + ux[1] + ux[2] + ux[3] - 4u * kMagicBits);
     const int ty = (int)(uy[0] + uy[1] + uy[2] + uy[3] - 4u * kMagicBits);
     const int tz = (int)(uz[0] + uz[1] + uz[2] + uz[3] - 4u * kMagicBits);
-    // 0: one label for the whole group, 1: one label per lane, 2: mixed inside lanes / tail
-    int mode = 2;
+    // is the whole group one label?  (a lone candidate labels it without looking)
+    bool uniform = full && (ncand <= 1);
     int l0 = lab[0];
-    if (full) {
-      if (ncand <= 1) {
-        mode = 0;  // a lone candidate labels the whole group
-      } else {
-        const bool t_uni = (lab[0] == lab[1]) && (lab[1] == lab[2]) && (lab[2] == lab[3]);
-        if (__all_sync(0xffffffffu, t_uni)) {
-          l0 = __shfl_sync(0xffffffffu, lab[0], 0);
-          mode = __all_sync(0xffffffffu, lab[0] == l0) ? 0 : 1;
-        }
-      }
+    if (full && !uniform) {
+      l0 = __shfl_sync(0xffffffffu, lab[0], 0);
+      uniform = __all_sync(0xffffffffu, (lab[0] == l0) && (lab[1] == l0) && (lab[2] == l0) && (lab[3] == l0));
     }
-    if (mode == 0) {
-      // three REDUX + register accumulation; shared memory is touched only when the label of
-      // this warp's run of groups changes
-      const int sx = __reduce_add_sync(0xffffffffu, tx);
-      const int sy = __reduce_add_sync(0xffffffffu, ty);
-      const int sz = __reduce_add_sync(0xffffffffu, tz);
-      if (l0 != wlab) {
-        if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
-        wx = wy = wz = 0;
-        wn = 0;
+    if (uniform) {
+      if (l0 != wlab || run_groups == kRunMax) {  // warp-uniform
+        flush_run();
         wlab = l0;
       }
-      wx += sx;
-      wy += sy;
-      wz += sz;
-      wn += kGroup;
-    } else if (mode == 1) {
-      warp_segmented_add<kPrivate>(s_acc, true, lab[0], tx, ty, tz, 4, lane);
+      rx += tx;
+      ry += ty;
+      rz += tz;
+      ++run_groups;
     } else {
+      // mixed group (a cluster boundary crosses it) or the partial tail group: one round per
+      // distinct label, each lane contributing the points it has with that label
+      flush_run();
       const long long i0 = (long long)g * kGroup + lane * 4;
+      bool act[4];
+      unsigned int rem = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        warp_segmented_add<kPrivate>(s_acc, full || (i0 + e < p.n), lab[e], (int)(ux[e] - kMagicBits),
-                                     (int)(uy[e] - kMagicBits), (int)(uz[e] - kMagicBits), 1, lane);
+      for (int e = 0; e < 4; ++e) {
+        act[e] = full || (i0 + e < p.n);
+        rem |= act[e] ? (1u << e) : 0u;
+      }
+      unsigned int todo = __ballot_sync(0xffffffffu, rem != 0);
+      while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        // this lane's first unprocessed label (selects, not a dynamically indexed array)
+        const int mine_first = (rem & 1u) ? lab[0] : ((rem & 2u) ? lab[1] : ((rem & 4u) ? lab[2] : lab[3]));
+        const int L = __shfl_sync(0xffffffffu, mine_first, src_lane);
+        int sx = 0, sy = 0, sz = 0, sc = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool hit = ((rem >> e) & 1u) && (lab[e] == L);
+          sx += hit ? (int)(ux[e] - kMagicBits) : 0;
+          sy += hit ? (int)(uy[e] - kMagicBits) : 0;
+          sz += hit ? (int)(uz[e] - kMagicBits) : 0;
+          sc += hit ? 1 : 0;
+          rem &= hit ? ~(1u << e) : ~0u;
+        }
+        sx = __reduce_add_sync(0xffffffffu, sx);
+        sy = __reduce_add_sync(0xffffffffu, sy);
+        sz = __reduce_add_sync(0xffffffffu, sz);
+        sc = __reduce_add_sync(0xffffffffu, sc);
+        if (lane == 0) acc_add<kPrivate>(s_acc, L, sx, sy, sz, (unsigned int)sc);
+        todo = __ballot_sync(0xffffffffu, rem != 0);
+      }
     }
   }
-  if (lane == 0 && wn > 0) acc_add<kPrivate>(s_acc, wlab, wx, wy, wz, wn);
+  flush_run();
   n_chg = __reduce_add_sync(0xffffffffu, n_chg);
   n_ref = __reduce_add_sync(0xffffffffu, n_ref);
   if (lane == 0) {
