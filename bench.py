@@ -35,8 +35,10 @@ CONFIGS = {
     # name: (days per GPU, H, W, k, iters)
     "c1": (3, 512, 512, 8, 20),
     "c2": (10, 2048, 2048, 16, 20),
-    "c3": (20, 8192, 8192, 64, 20),      # days are for the WHOLE job (sharded), see below
+    # c3 = 20-day 8192x8192 stack (1.34 G pts) over 8 GPUs: 2.5 days = 20 x 1024 rows bands per GPU
+    "c3": (20, 1024, 8192, 64, 20),
     "c4": (12, 4096, 4096, 1024, 10),
+    "c5": (30, 4096, 4096, 32, 300),
 }
 
 
