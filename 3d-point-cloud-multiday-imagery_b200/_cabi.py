@@ -28,6 +28,8 @@ STATUS_NAMES = {
     -6: "MDKM_ERR_OOM",
 }
 
+STATUS_BY_NAME = {v: k for k, v in STATUS_NAMES.items()}
+
 # name -> (restype, argtypes); mirrors include/mdkm.h one to one
 SIGNATURES = {
     "mdkm_version": (c_char_p, []),
@@ -42,6 +44,8 @@ SIGNATURES = {
     "mdkm_num_points": (c_int64, [c_void_p]),
     "mdkm_gather_points": (c_int, [c_void_p, POINTER(c_int64), c_int, POINTER(c_float)]),
     "mdkm_get_cloud": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdkm_num_segments": (c_int, [c_void_p]),
+    "mdkm_segment_offsets": (c_int, [c_void_p, POINTER(c_int64)]),
     "mdkm_ground_level": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_double), POINTER(c_double)]),
     "mdkm_fit": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, c_double, c_void_p, c_int,
                          POINTER(c_double), POINTER(c_int), POINTER(c_double)]),

@@ -82,6 +82,24 @@ def _is_same_clustering(l1, l2, k) -> bool:
     return bool(np.array_equal(mapping[l1], l2))
 
 
+def _random_seeds(rs, n: int, k: int) -> np.ndarray:
+    """``random_state.choice(n, size=k, replace=False, p=w / w.sum())`` with unit weights
+    (sklearn/_kmeans.py:1014-1021).  numpy draws differently when ``p`` is given, so the very
+    call is made while the probability vector fits comfortably in host memory; beyond that
+    the same rejection scheme is run on ``floor(u * n)`` (identical up to FP rounding of the
+    cdf)."""
+    if n <= (1 << 27):
+        return rs.choice(n, size=k, replace=False, p=np.full(n, 1.0 / n))
+    found = np.empty(0, dtype=np.int64)
+    while found.size < k:
+        x = rs.random_sample(k - found.size)
+        new = np.minimum((x * n).astype(np.int64), n - 1)
+        new = new[np.sort(np.unique(new, return_index=True)[1])]
+        new = new[~np.isin(new, found)]
+        found = np.concatenate([found, new])
+    return found[:k]
+
+
 def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True):
     """KMeans.fit driver (sklearn/_kmeans.py:1436-1563): init, n_init restarts, best inertia."""
     n = eng.n_points
@@ -106,8 +124,7 @@ def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_
         if init_is_array:
             centers0 = init_arr
         elif init == "random":
-            seeds = rs.choice(n, size=k, replace=False)  # sklearn/_kmeans.py:1014-1021
-            centers0 = eng.gather_points(seeds).astype(np.float64)
+            centers0 = eng.gather_points(_random_seeds(rs, n, k)).astype(np.float64)
         else:
             centers0, _ = eng.kmeans_plusplus(k, rs)
         r = eng.fit(centers0, max_iter=max_iter, tol=tol, want_labels=want_labels)
@@ -131,8 +148,9 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     valid_masks : optional bool/uint8 ``[D,H,W]`` (``final_defined`` of disparity.py:203-204).
     n_clusters, init, n_init, max_iter, tol, random_state : as sklearn.cluster.KMeans.
     detrend : apply the per-day plane fit of plugin.py:161-171 to z before clustering.
-    ground_level : additionally shift z by the 2nd percentile and return the 'height'
-        colour property of plugin.py:181-192 (after clustering; does not change labels).
+    ground_level : per day, shift z so that its 2nd percentile is 0 and return the 'height'
+        colour property (plugin.py:181-192), before clustering -- with ``detrend=True`` this
+        is the reference's whole per-pair tail, applied to every day of the stack.
     engine : reuse an existing ``Engine`` (keeps device buffers, and with
         ``Engine(pinned_results=True)`` page-locked result buffers, across calls); with a
         multi-rank engine pass this rank's flat slice plus ``stack_shape`` / ``pix_begin``.
@@ -143,19 +161,15 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     try:
         n = eng.unproject(height_maps, valid_masks, max_abs_height=max_abs_height, detrend=detrend,
                           disparity_scale=disparity_scale, stack_shape=stack_shape, pix_begin=pix_begin)
-        # the cloud is final once unprojected: start its device->host copy before the Lloyd loop
-        cloud = eng.get_cloud(napari_order=True) if (return_cloud and not ground_level) else None
-        r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
-                        tol=tol, random_state=random_state)
         hn = None
-        extra = {}
+        extra = {"segment_offsets": eng.segment_offsets}
         if ground_level:
             lo, hi, hn = eng.ground_level(True)
             extra["h_min"], extra["h_max"] = lo, hi
-            r["centers"] = r["centers"].copy()
-            r["centers"][:, 2] -= lo
-        if return_cloud and cloud is None:
-            cloud = eng.get_cloud(napari_order=True)
+        # the cloud is final now: its device->host copy is issued before the Lloyd loop
+        cloud = eng.get_cloud(napari_order=True) if return_cloud else None
+        r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
+                        tol=tol, random_state=random_state)
         return FusionResult(labels=r["labels"], centroids=r["centers"], fused_cloud=cloud,
                             n_iter=r["n_iter"], inertia=r["inertia"], n_points=n,
                             n_refined=r["n_refined"], n_relocations=r["n_relocations"],
@@ -195,7 +209,7 @@ def to_layers(result: FusionResult, prefix: str = "Multi-day") -> List[Layer]:
     props: Dict[str, Any] = {"cluster": result.labels}
     face = "cluster"
     if result.height_norm is not None:
-        props["height"] = result.height_norm
+        props["height"] = result.height_norm  # plugin.py:186-188
     layers: List[Layer] = [(
         result.fused_cloud,
         {

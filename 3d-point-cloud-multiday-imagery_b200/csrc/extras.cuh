@@ -1,7 +1,4 @@
-// Rare-path and "next row" kernels:
-//   * empty-cluster relocation  (sklearn/cluster/_k_means_common.pyx:167-211)
-//   * percentile ground-levelling (members/rafael/disparity/plugin.py:181-192)
-//   * k-means++ seeding           (sklearn/cluster/_kmeans.py:180-278)
+// Rare-path kernels: empty-cluster relocation (sklearn/cluster/_k_means_common.pyx:167-211).
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -120,14 +117,5 @@ __global__ void reloc_apply_kernel(const RelocParams p, DevStatus* st) {
   p.acc[old_id * 4 + 3] -= 1ull;  // pyx:209
   st->n_relocated += 1ull;
 }
-
-// ---------------------------------------------------------------------------------------
-// Placeholders wired to the C ABI; implemented in extras_impl (ground level, k-means++).
-// ---------------------------------------------------------------------------------------
-int ground_level_impl(cudaStream_t stream, float* pts, long long n, float* height_norm_out,
-                      int mem, double* h_min_out, double* h_max_out, int* launches);
-int kmeanspp_impl(cudaStream_t stream, int sm_count, const float* pts, long long n,
-                  FrameF f, int k, long long first_index, const double* rand_vals, int n_local_trials, double* centers_out,
-                  long long* indices_out, int* launches);
 
 }  // namespace mdkm

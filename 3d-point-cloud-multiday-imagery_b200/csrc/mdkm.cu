@@ -15,9 +15,10 @@
 #include "../../include/mdkm.h"
 #include "common.cuh"
 #include "extras.cuh"
-#include "extras_impl.cuh"
+#include "levelling.cuh"
 #include "lloyd.cuh"
 #include "nccl_shim.h"
+#include "seeding.cuh"
 #include "unproject.cuh"
 
 using namespace mdkm;
@@ -74,6 +75,17 @@ struct mdkm_handle {
   DevBuf<unsigned char> staging;  // host inputs staged here
   DevBuf<double> planes;
   long long* h_total = nullptr;  // pinned
+
+  // segments of the resident cloud (one per day of the unprojected range; one for set_points)
+  std::vector<long long> seg_off;  // [n_seg + 1] point offsets
+  bool seg_whole = false;          // every segment is a whole day / the whole cloud
+  DevBuf<long long> d_seg_off;
+  DevBuf<unsigned int> sel_hist;
+  DevBuf<unsigned char> sel_targets;
+
+  // k-means++ state
+  DevBuf<double> kpp_closest, kpp_cell, kpp_blk, kpp_prefix, kpp_partials, kpp_rand;
+  DevBuf<unsigned char> kpp_state;
 
   // communicator
   ncclComm_t comm = nullptr;
@@ -533,6 +545,9 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
   release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
+  release(h->d_seg_off); release(h->sel_hist); release(h->sel_targets);
+  release(h->kpp_closest); release(h->kpp_cell); release(h->kpp_blk); release(h->kpp_prefix);
+  release(h->kpp_partials); release(h->kpp_rand); release(h->kpp_state);
   if (h->d_status) cudaFree(h->d_status);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->h_total) cudaFreeHost(h->h_total);
@@ -595,6 +610,8 @@ int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int
     CU(cudaGetLastError());
   }
   OK(zero_tail(h));
+  h->seg_off.assign({0, (long long)n});
+  h->seg_whole = true;
   h->have_points = true;
   h->frame_ok = false;
   OK(compute_frame(h));
@@ -679,9 +696,27 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
     unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
     h->launches += 3;
     CU(cudaGetLastError());
+    // segments: where each day of the range starts in the output
+    const long long d_first = pix_begin / HW, d_last = (pix_begin + pix_count - 1) / HW;
+    const int n_seg = (int)(d_last - d_first + 1);
+    OK(ensure(h, h->d_seg_off, (size_t)n_seg + 1));
+    if (n_seg > 1) {
+      day_offsets_kernel<<<n_seg - 1, 32, 0, h->stream>>>(up, n_seg, h->d_seg_off.p);
+      ++h->launches;
+      CU(cudaGetLastError());
+    }
+    h->seg_off.assign((size_t)n_seg + 1, 0);
     CU(cudaMemcpyAsync(h->h_total, h->chunk_offsets.p + n_chunks + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    if (n_seg > 1)
+      CU(cudaMemcpyAsync(h->seg_off.data() + 1, h->d_seg_off.p + 1, (size_t)(n_seg - 1) * 8, cudaMemcpyDeviceToHost,
+                         h->stream));
     CU(cudaStreamSynchronize(h->stream));
     n_out = *h->h_total;
+    h->seg_off[n_seg] = n_out;
+    h->seg_whole = (pix_begin % HW) == 0 && (pix_count % HW) == 0;
+  } else {
+    h->seg_off.assign({0, 0});
+    h->seg_whole = true;
   }
   h->n = n_out;
   OK(zero_tail(h));
@@ -869,15 +904,107 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   return MDKM_OK;
 }
 
+int mdkm_num_segments(const mdkm_handle* h) { return h && h->have_points ? (int)h->seg_off.size() - 1 : -1; }
+
+int mdkm_segment_offsets(const mdkm_handle* h, int64_t* out) {
+  if (!h || !out || !h->have_points) return MDKM_ERR_INVALID;
+  for (size_t i = 0; i < h->seg_off.size(); ++i) out[i] = h->seg_off[i];
+  return MDKM_OK;
+}
+
 int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h_min_out, double* h_max_out) {
   if (!h) return MDKM_ERR_INVALID;
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
-  if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_ground_level is single-rank");
+  if (!h->seg_whole)
+    return fail(h, MDKM_ERR_STATE, "mdkm_ground_level needs whole days on this rank (shard the stack by days)");
   CU(cudaSetDevice(h->device));
-  return ground_level_impl(h->stream, h->pts.p, h->n, height_norm_out, mem, h_min_out, h_max_out,
-                           &h->launches) == 0
-             ? (h->frame_ok = false, compute_frame(h))
-             : fail(h, MDKM_ERR_CUDA, "ground_level failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const int n_seg = (int)h->seg_off.size() - 1;
+  OK(ensure(h, h->d_seg_off, (size_t)n_seg + 1));
+  OK(ensure(h, h->sel_hist, (size_t)n_seg * kSelTargets * kSelBins));
+  OK(ensure(h, h->sel_targets, (size_t)n_seg * kSelTargets * sizeof(SelTarget)));
+  OK(ensure(h, h->planes, (size_t)n_seg * 2 + 8));
+  CU(cudaMemcpyAsync(h->d_seg_off.p, h->seg_off.data(), (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->sel_hist.p, 0, (size_t)n_seg * kSelTargets * kSelBins * 4, h->stream));
+  // numpy "linear" percentile: virtual index (n-1)*q, neighbours floor / floor+1
+  // (numpy/lib/_function_base_impl.py: _QuantileMethods['linear'], _get_indexes, _lerp)
+  const double qs[2] = {2.0 / 100.0, 98.0 / 100.0};
+  std::vector<SelTarget> tg((size_t)n_seg * kSelTargets);
+  std::vector<double> gam((size_t)n_seg * 2, 0.0);
+  for (int s = 0; s < n_seg; ++s) {
+    const long long ns = h->seg_off[s + 1] - h->seg_off[s];
+    for (int q = 0; q < 2; ++q) {
+      long long prev = 0, next = 0;
+      double g = 0.0;
+      if (ns > 0) {
+        const double v = (double)(ns - 1) * qs[q];
+        prev = (long long)floor(v);
+        next = prev + 1;
+        g = v - (double)prev;
+        if (v >= (double)(ns - 1)) { prev = next = ns - 1; g = v - (-1.0); }
+        if (v < 0) { prev = next = 0; }
+      }
+      tg[(size_t)s * kSelTargets + 2 * q + 0] = SelTarget{0u, 0u, prev};
+      tg[(size_t)s * kSelTargets + 2 * q + 1] = SelTarget{0u, 0u, next};
+      gam[(size_t)s * 2 + q] = g;
+    }
+  }
+  CU(cudaMemcpyAsync(h->sel_targets.p, tg.data(), tg.size() * sizeof(SelTarget), cudaMemcpyHostToDevice, h->stream));
+  SelParams sp{};
+  sp.pts = h->pts.p;
+  sp.seg_off = h->d_seg_off.p;
+  sp.hist = h->sel_hist.p;
+  sp.targets = reinterpret_cast<SelTarget*>(h->sel_targets.p);
+  sp.n_seg = n_seg;
+  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10}, pshift[3] = {32, 21, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    sp.shift = shifts[pass]; sp.bits = bits[pass]; sp.prefix_shift = pshift[pass];
+    select_hist_kernel<<<dim3(kSelCtasPerSeg, n_seg), kThreads, 0, h->stream>>>(sp);
+    select_pick_kernel<<<n_seg, kSelTargets * 32, 0, h->stream>>>(sp);
+    h->launches += 2;
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(tg.data(), h->sel_targets.p, tg.size() * sizeof(SelTarget), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<double> levels((size_t)n_seg * 2, 0.0);
+  for (int s = 0; s < n_seg; ++s) {
+    const long long ns = h->seg_off[s + 1] - h->seg_off[s];
+    double pc[2] = {NAN, NAN};
+    if (ns > 0) {
+      for (int q = 0; q < 2; ++q) {
+        const double a = (double)ord2f(tg[(size_t)s * kSelTargets + 2 * q + 0].prefix);
+        const double b = (double)ord2f(tg[(size_t)s * kSelTargets + 2 * q + 1].prefix);
+        const double t = gam[(size_t)s * 2 + q];
+        const double diff = b - a;
+        double r = a + diff * t;              // numpy _lerp
+        if (t >= 0.5) r = b - diff * (1.0 - t);
+        pc[q] = r;
+      }
+    }
+    if (h_min_out) h_min_out[s] = pc[0];
+    if (h_max_out) h_max_out[s] = pc[1];
+    levels[(size_t)s * 2 + 0] = ns > 0 ? pc[0] : 0.0;
+    levels[(size_t)s * 2 + 1] = ns > 0 ? (pc[1] - pc[0] + 1e-6) : 1.0;  // plugin.py:183
+  }
+  if (h->n > 0) {
+    CU(cudaMemcpyAsync(h->planes.p, levels.data(), levels.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    float* hn_dev = height_norm_out;
+    if (height_norm_out && mem != MDKM_MEM_DEVICE) {
+      OK(ensure(h, h->staging, (size_t)h->n * 4));
+      hn_dev = reinterpret_cast<float*>(h->staging.p);
+    }
+    LevelParams lp{};
+    lp.pts = h->pts.p; lp.seg_off = h->d_seg_off.p; lp.levels = h->planes.p;
+    lp.height_norm = hn_dev; lp.n = h->n; lp.n_seg = n_seg;
+    level_apply_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, (size_t)(n_seg + 1) * 8, h->stream>>>(lp);
+    ++h->launches;
+    CU(cudaGetLastError());
+    OK(zero_tail(h));
+    if (height_norm_out && mem != MDKM_MEM_DEVICE)
+      CU(cudaMemcpyAsync(height_norm_out, hn_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->frame_ok = false;
+  return compute_frame(h);
 }
 
 int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals, int n_local_trials,
@@ -887,12 +1014,54 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
   if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_kmeans_plusplus is single-rank");
   if (k < 1 || k > kMaxK || (long long)k > h->n) return fail(h, MDKM_ERR_INVALID, "bad k");
   if (first_index < 0 || first_index >= h->n) return fail(h, MDKM_ERR_INVALID, "first_index out of range");
-  if (k > 1 && (!rand_vals || n_local_trials < 1)) return fail(h, MDKM_ERR_INVALID, "rand_vals required");
+  if (k > 1 && (!rand_vals || n_local_trials < 1 || n_local_trials > kKppMaxTrials))
+    return fail(h, MDKM_ERR_INVALID, "rand_vals required and 1 <= n_local_trials <= %d", kKppMaxTrials);
+  if (!centers_out) return fail(h, MDKM_ERR_INVALID, "centers_out required");
   CU(cudaSetDevice(h->device));
-  if (!h->frame_ok) OK(compute_frame(h));
-  const int rc = kmeanspp_impl(h->stream, h->sm_count, h->pts.p, h->n, h->ff, k, (long long)first_index, rand_vals,
-                               n_local_trials, centers_out, reinterpret_cast<long long*>(indices_out), &h->launches);
-  if (rc != 0) return fail(h, MDKM_ERR_CUDA, "kmeans++ failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const long long cap = round_up(h->n, kGroup);
+  const long long n_cells = cap / kGroup;
+  const long long n_blk = (n_cells + kKppCellsPerBlock - 1) / kKppCellsPerBlock;
+  const int T = k > 1 ? n_local_trials : 1;
+  const int grid = grid_for(h, (n_cells + 7) / 8, 8);
+  OK(ensure(h, h->kpp_closest, (size_t)cap));
+  OK(ensure(h, h->kpp_cell, (size_t)n_cells));
+  OK(ensure(h, h->kpp_blk, (size_t)n_blk));
+  OK(ensure(h, h->kpp_prefix, (size_t)n_blk));
+  OK(ensure(h, h->kpp_partials, (size_t)grid * kKppMaxTrials));
+  OK(ensure(h, h->kpp_rand, (size_t)std::max(1, (k - 1) * T)));
+  OK(ensure(h, h->kpp_state, sizeof(KppState)));
+  OK(ensure(h, h->dscratch, (size_t)k * 4 + 16));
+  CU(cudaMemsetAsync(h->kpp_state.p, 0, sizeof(KppState), h->stream));
+  if (k > 1)
+    CU(cudaMemcpyAsync(h->kpp_rand.p, rand_vals, (size_t)(k - 1) * T * 8, cudaMemcpyHostToDevice, h->stream));
+  KppParams kp{};
+  kp.pts = h->pts.p; kp.n = h->n;
+  kp.closest = h->kpp_closest.p; kp.cell_sum = h->kpp_cell.p; kp.blk_sum = h->kpp_blk.p;
+  kp.blk_prefix = h->kpp_prefix.p; kp.partials = h->kpp_partials.p; kp.rand_vals = h->kpp_rand.p;
+  kp.st = reinterpret_cast<KppState*>(h->kpp_state.p);
+  kp.centers_out = h->dscratch.p;
+  kp.indices_out = reinterpret_cast<long long*>(h->dscratch.p + (size_t)k * 3);
+  kp.n_trials = T;
+  kp.first_index = first_index;
+  KppPotKernel pot_fn = kpp_pot_variant(T);
+  // all k rounds are enqueued back to back; nothing returns to the host until the end
+  for (int c = 0; c < k; ++c) {
+    kp.round = c;
+    if (c > 0) {
+      kpp_search_kernel<<<1, 1024, 0, h->stream>>>(kp, n_blk);
+      pot_fn<<<grid, kThreads, 0, h->stream>>>(kp);
+      h->launches += 2;
+    }
+    if (c == 0 || c < k - 1) {  // the last centre has no later draw to prepare
+      kpp_commit_kernel<<<(unsigned int)n_blk, kThreads, 0, h->stream>>>(kp);
+      ++h->launches;
+    }
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(centers_out, kp.centers_out, (size_t)k * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (indices_out)
+    CU(cudaMemcpyAsync(indices_out, kp.indices_out, (size_t)k * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return MDKM_OK;
 }
 

@@ -195,14 +195,27 @@ class Engine:
         self._check(self._lib.mdkm_get_cloud(self._h, c_void_p(ptr), 1 if napari_order else 0, mem))
         return out
 
+    @property
+    def segment_offsets(self) -> np.ndarray:
+        """Point offsets of the cloud's segments (one per day), int64 ``[n_segments + 1]``."""
+        ns = int(self._lib.mdkm_num_segments(self._h))
+        if ns < 0:
+            raise C.MdkmError(C.STATUS_BY_NAME["MDKM_ERR_STATE"], "no points resident")
+        out = np.zeros(ns + 1, dtype=np.int64)
+        self._check(self._lib.mdkm_segment_offsets(self._h, out.ctypes.data_as(POINTER(c_int64))))
+        return out
+
     def ground_level(self, want_height_norm=True):
-        """plugin.py:181-192.  Returns (h_min, h_max, height_norm or None)."""
+        """plugin.py:181-192 per day.  Returns (h_min[S], h_max[S], height_norm[N] or None)."""
         n = self.n_points
-        hn = np.empty(n, dtype=np.float32) if want_height_norm else None
-        lo, hi = c_double(0), c_double(0)
+        ns = int(self._lib.mdkm_num_segments(self._h))
+        hn = self._result_buffer("height_norm", (n,), np.float32) if want_height_norm else None
+        lo = np.zeros(max(ns, 1), dtype=np.float64)
+        hi = np.zeros(max(ns, 1), dtype=np.float64)
         self._check(self._lib.mdkm_ground_level(
-            self._h, c_void_p(hn.ctypes.data) if hn is not None else None, C.MEM_HOST, byref(lo), byref(hi)))
-        return float(lo.value), float(hi.value), hn
+            self._h, c_void_p(hn.ctypes.data) if hn is not None else None, C.MEM_HOST,
+            lo.ctypes.data_as(POINTER(c_double)), hi.ctypes.data_as(POINTER(c_double))))
+        return lo[:ns], hi[:ns], hn
 
     # -- k-means -------------------------------------------------------------------------
     def fit(self, init, max_iter=300, tol=1e-4, want_labels=True, labels_out=None):

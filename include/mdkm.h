@@ -94,9 +94,19 @@ int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz
  * plugin.py:192 builds `points_coords`; 0 gives (x,y,z). */
 int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem);
 
-/* Ground-levelling of plugin.py:181-192: h_min/h_max = percentile(z,[2,98]) with numpy's
- * linear interpolation; z -= h_min in the resident cloud; height_norm_out (optional, n
- * floats) = clip((z-h_min)/(h_max-h_min+1e-6),0,1).  Single rank only. */
+/* Segments of the resident cloud: one per day of the unprojected pixel range (the reference
+ * treats every stereo pair / day separately, plugin.py:106), one for mdkm_set_points.
+ * mdkm_segment_offsets writes n_segments + 1 point offsets (the last one is n). */
+int mdkm_num_segments(const mdkm_handle* h);
+int mdkm_segment_offsets(const mdkm_handle* h, int64_t* out);
+
+/* Ground-levelling of plugin.py:181-192, per segment (day): h_min / h_max =
+ * np.percentile(z, 2) / np.percentile(z, 98) with numpy's linear interpolation (exact order
+ * statistics by radix select on the device); z -= h_min in the resident cloud;
+ * height_norm_out (optional, n floats, host or device per `mem`) =
+ * clip((z - h_min) / (h_max - h_min + 1e-6), 0, 1), the 'height' colour property.
+ * h_min_out / h_max_out: optional arrays of n_segments doubles.  Rank-local: needs whole days
+ * on this rank (shard the stack by days).  Call it before mdkm_fit. */
 int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h_min_out,
                       double* h_max_out);
 
@@ -130,8 +140,10 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
  * of numpy.random.RandomState stay on the host and are supplied by the caller in
  * scikit-learn's order: `first_index` is the result of RandomState.choice(n) for the first
  * centre, then for each further centre `n_local_trials` uniforms in [0,1) from rand_vals
- * (row-major [(k-1), n_local_trials]); the device does the distance, min, potential and
- * cumulative-sum search passes.  centers_out: float64[k*3]; indices_out: int64[k].
+ * (row-major [(k-1), n_local_trials], n_local_trials <= 16; scikit-learn uses
+ * 2 + int(ln k)); the device does the distances (float64), the potentials, the
+ * cumulative-sum search and the greedy choice among the trials, all k centres without a
+ * host round trip.  centers_out: float64[k*3]; indices_out: int64[k] (may be NULL).
  * Single rank only. */
 int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals,
                          int n_local_trials, double* centers_out, int64_t* indices_out);

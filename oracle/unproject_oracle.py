@@ -84,6 +84,39 @@ def unproject_stack(height_maps, validity_masks=None, limit=MAX_DISP / 2, detren
     return np.concatenate(out, axis=0)
 
 
+def reference_tail_stack(height_maps, validity_masks=None, limit=MAX_DISP / 2, detrend=True):
+    """The reference's whole per-pair tail (plugin.py:148-192) applied to every day, merged.
+
+    Per day: unprojection, plane detrend (the reference always applies it), percentile
+    ground-levelling.  Returns (P[N,3] = x,y,z with z levelled, h_norm[N], h_min[D], h_max[D],
+    offsets[D+1]).
+    """
+    hm = np.asarray(height_maps)
+    if hm.ndim == 2:
+        hm = hm[None]
+    pts, hns, los, his, off = [], [], [], [], [0]
+    for d in range(hm.shape[0]):
+        vm = None if validity_masks is None else np.asarray(validity_masks)[d]
+        P, _ = unproject_day(hm[d], vm, limit, detrend)
+        if P.shape[0]:
+            z = P[:, 2]
+            h_min = np.percentile(z, 2)   # plugin.py:181
+            h_max = np.percentile(z, 98)  # plugin.py:182
+            z0, hn = ground_level(z)
+            P = P.copy()
+            P[:, 2] = z0
+        else:
+            h_min = h_max = np.nan
+            hn = np.zeros(0)
+        pts.append(P)
+        hns.append(hn)
+        los.append(h_min)
+        his.append(h_max)
+        off.append(off[-1] + P.shape[0])
+    return (np.concatenate(pts, axis=0), np.concatenate(hns), np.array(los), np.array(his),
+            np.array(off, dtype=np.int64))
+
+
 def to_napari_points(P):
     """plugin.py:192: ``np.stack([z, y, x], axis=1)`` -- napari axis order."""
     return np.stack([P[:, 2], P[:, 1], P[:, 0]], axis=1)

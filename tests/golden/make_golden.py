@@ -9,7 +9,7 @@ scikit-learn 1.9.0 / numpy 2.3.5:
     python tests/golden/make_golden.py
 
 Outputs (committed): kmeans_stack_small.npz, kmeans_c1_like.npz, kmeans_tol.npz,
-kmeans_relocate.npz, kmeanspp.npz, unproject_small.npz
+kmeans_relocate.npz, kmeanspp.npz, unproject_small.npz, kmeans_default_call.npz
 """
 from __future__ import annotations
 
@@ -81,15 +81,47 @@ def unproject_case():
     P = unproject_oracle.unproject_stack(hm, mask, detrend=False)
     Pd = unproject_oracle.unproject_stack(hm, mask, detrend=True)
     z0, hn = unproject_oracle.ground_level(Pd[:, 2])
+    Pt, hnt, lo, hi, off = unproject_oracle.reference_tail_stack(hm, mask, detrend=True)
     np.savez_compressed(os.path.join(HERE, "unproject_small.npz"), disparity=disp, mask=mask,
-                        points=P, points_detrended=Pd, z_ground=z0, height_norm=hn)
+                        points=P, points_detrended=Pd, z_ground=z0, height_norm=hn,
+                        tail_points=Pt, tail_height_norm=hnt, tail_h_min=lo, tail_h_max=hi, tail_offsets=off)
     print("unproject N", P.shape[0])
 
 
+def default_call_case():
+    """The reference's very call, ``KMeans(n_clusters, random_state=42, n_init=10)``
+    (core.py:227-228; default init="k-means++", max_iter=300, tol=1e-4), on a small cloud."""
+    from sklearn.cluster import KMeans
+
+    hm = synth.make_stack(2, 40, 56, seed=7, n_buildings=6).numpy()
+    P = unproject_oracle.unproject_stack(hm)
+    out = {"height_maps": hm}
+    for k, n_init in ((5, 10), (3, 1)):
+        km = KMeans(n_clusters=k, random_state=42, n_init=n_init).fit(P)
+        out[f"labels_{k}"] = km.labels_.astype(np.int32)
+        out[f"centers_{k}"] = km.cluster_centers_
+        out[f"inertia_{k}"] = km.inertia_
+        out[f"n_iter_{k}"] = km.n_iter_
+        km = KMeans(n_clusters=k, random_state=42, n_init=n_init, init="random").fit(P)
+        out[f"rlabels_{k}"] = km.labels_.astype(np.int32)
+        out[f"rcenters_{k}"] = km.cluster_centers_
+        out[f"rinertia_{k}"] = km.inertia_
+        out[f"rn_iter_{k}"] = km.n_iter_
+    np.savez_compressed(os.path.join(HERE, "kmeans_default_call.npz"), **out)
+    print("default call", {k: v for k, v in out.items() if k.startswith(("n_iter", "inertia", "rn_iter"))})
+
+
 if __name__ == "__main__":
-    stack_case("kmeans_stack_small.npz", 2, 48, 64, 5, 50, 1e-4, 0)
-    stack_case("kmeans_c1_like.npz", 3, 96, 128, 8, 20, 0.0, 1)
-    stack_case("kmeans_tol.npz", 2, 64, 64, 6, 300, 1e-4, 2)
-    relocate_case()
-    kpp_case()
-    unproject_case()
+    only = set(sys.argv[1:])
+    if not only or "stack" in only:
+        stack_case("kmeans_stack_small.npz", 2, 48, 64, 5, 50, 1e-4, 0)
+        stack_case("kmeans_c1_like.npz", 3, 96, 128, 8, 20, 0.0, 1)
+        stack_case("kmeans_tol.npz", 2, 64, 64, 6, 300, 1e-4, 2)
+    if not only or "relocate" in only:
+        relocate_case()
+    if not only or "kpp" in only:
+        kpp_case()
+    if not only or "unproject" in only:
+        unproject_case()
+    if not only or "default" in only:
+        default_call_case()

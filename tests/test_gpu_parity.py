@@ -261,6 +261,137 @@ def test_fit_errors(engine):
 
 
 # ---------------------------------------------------------------------------------------
+# a5: percentile ground-levelling (plugin.py:181-192), per day
+# ---------------------------------------------------------------------------------------
+def _check_ground_level(engine, hm, mask=None):
+    P, hn_ref, lo_ref, hi_ref, off_ref = UO.reference_tail_stack(hm, mask, detrend=False)
+    n = engine.unproject(hm, mask)
+    assert n == P.shape[0]
+    np.testing.assert_array_equal(engine.segment_offsets, off_ref)
+    lo, hi, hn = engine.ground_level(True)
+    # z is exact in FP32 here, so the order statistics and numpy's lerp are reproduced exactly
+    np.testing.assert_array_equal(lo, lo_ref)
+    np.testing.assert_array_equal(hi, hi_ref)
+    cloud = engine.get_cloud(False)
+    np.testing.assert_array_equal(cloud[:, :2].astype(np.float64), P[:, :2])
+    np.testing.assert_array_equal(cloud[:, 2], P[:, 2].astype(np.float32))       # one rounding of z - h_min
+    np.testing.assert_array_equal(hn, hn_ref.astype(np.float32))                  # idem for h_norm
+    return n
+
+
+def test_ground_level_per_day_exact(engine):
+    hm = synth.make_stack(3, 120, 200, seed=21, n_buildings=9).numpy()
+    _check_ground_level(engine, hm)
+    rs = np.random.RandomState(2)
+    _check_ground_level(engine, hm, rs.rand(*hm.shape) > 0.3)
+
+
+def test_ground_level_tiny_and_empty_days(engine):
+    hm = np.full((5, 3, 7), np.nan, dtype=np.float32)
+    hm[0, 1, 2] = 3.5                       # one point
+    hm[1, 0, :2] = [1.0, -2.0]              # two points
+    hm[3].flat[:9] = np.arange(9) * 0.25    # day 2 and day 4 stay empty
+    P, hn_ref, lo_ref, hi_ref, off_ref = UO.reference_tail_stack(hm, detrend=False)
+    assert engine.unproject(hm) == 12
+    np.testing.assert_array_equal(engine.segment_offsets, off_ref)
+    lo, hi, hn = engine.ground_level(True)
+    np.testing.assert_array_equal(lo, lo_ref)  # NaN for the empty days on both sides
+    np.testing.assert_array_equal(hi, hi_ref)
+    np.testing.assert_array_equal(hn, hn_ref.astype(np.float32))
+    np.testing.assert_array_equal(engine.get_cloud(False)[:, 2], P[:, 2].astype(np.float32))
+
+
+def test_reference_tail_golden(engine, golden):
+    """Unprojection + detrend + ground level, the reference's whole per-pair tail."""
+    g = golden("unproject_small.npz")
+    n = engine.unproject(g["disparity"], g["mask"], disparity_scale=-1.0 / 16.0, detrend=True)
+    assert n == g["tail_points"].shape[0]
+    lo, hi, hn = engine.ground_level(True)
+    # the detrended z is the FP64 plane distance rounded to FP32 (1e-4 absolute, see above)
+    np.testing.assert_allclose(lo, g["tail_h_min"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(hi, g["tail_h_max"], rtol=0, atol=1e-4)
+    cloud = engine.get_cloud(False).astype(np.float64)
+    np.testing.assert_array_equal(cloud[:, :2], g["tail_points"][:, :2])
+    np.testing.assert_allclose(cloud[:, 2], g["tail_points"][:, 2], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(hn, g["tail_height_norm"], rtol=0, atol=1e-5)
+
+
+def test_ground_level_needs_whole_days(engine):
+    hm = synth.make_stack(2, 16, 16, seed=1, n_buildings=1).numpy().reshape(-1)
+    engine.unproject(hm[5:300], stack_shape=(2, 16, 16), pix_begin=5)
+    assert len(engine.segment_offsets) == 3
+    with pytest.raises(Exception, match="whole days"):
+        engine.ground_level()
+
+
+# ---------------------------------------------------------------------------------------
+# a14: k-means++ seeding and the reference's default call
+# ---------------------------------------------------------------------------------------
+def test_kmeanspp_golden(engine, golden):
+    g = golden("kmeanspp.npz")
+    engine.set_points(g["X"])
+    for seed, k in ((0, 4), (5, 8), (42, 16)):
+        centers, idx = engine.kmeans_plusplus(k, np.random.RandomState(seed))
+        np.testing.assert_array_equal(idx, g[f"indices_{seed}_{k}"])
+        np.testing.assert_array_equal(centers, g[f"centers_{seed}_{k}"])
+
+
+@pytest.mark.parametrize("k,seed", [(1, 0), (2, 1), (32, 2), (200, 3)])
+def test_kmeanspp_vs_oracle_stack(engine, k, seed):
+    hm = synth.make_stack(2, 160, 200, seed=seed, n_buildings=8).numpy()
+    P = UO.unproject_stack(hm)
+    engine.unproject(hm)
+    c_ref, i_ref = KO.kmeans_plusplus(P - P.mean(axis=0), k, np.random.RandomState(seed))
+    centers, idx = engine.kmeans_plusplus(k, np.random.RandomState(seed))
+    np.testing.assert_array_equal(idx, i_ref)
+    np.testing.assert_array_equal(centers, P[i_ref])
+
+
+def test_kmeanspp_is_deterministic(engine):
+    hm = synth.make_stack(4, 300, 500, seed=8).numpy()
+    engine.unproject(hm)
+    a = engine.kmeans_plusplus(64, np.random.RandomState(9))
+    b = engine.kmeans_plusplus(64, np.random.RandomState(9))
+    np.testing.assert_array_equal(a[1], b[1])
+    assert len(set(a[1].tolist())) == 64
+
+
+@pytest.mark.parametrize("k,n_init", [(5, 10), (3, 1)])
+def test_default_call_golden(pkg, engine, golden, k, n_init):
+    """KMeans(n_clusters, random_state=42, n_init=10) -- the reference's call, core.py:227-228."""
+    g = golden("kmeans_default_call.npz")
+    P = UO.unproject_stack(g["height_maps"])
+    for init, pre in (("k-means++", ""), ("random", "r")):
+        res = pkg.fuse_multiday_kmeans(g["height_maps"], n_clusters=k, random_state=42, n_init=n_init,
+                                       init=init, engine=engine)
+        assert res.n_iter == int(g[f"{pre}n_iter_{k}"])
+        check_labels(P, g[f"{pre}centers_{k}"], g[f"{pre}labels_{k}"], res.labels, allow_near=0)
+        check_centroids(g[f"{pre}centers_{k}"], res.centroids, P)
+        np.testing.assert_allclose(res.inertia, float(g[f"{pre}inertia_{k}"]), rtol=1e-6)
+
+
+def test_fuse_with_reference_tail(pkg, engine):
+    hm = synth.make_stack(3, 128, 160, seed=4, n_buildings=6).numpy()
+    res = pkg.fuse_multiday_kmeans(hm, n_clusters=6, init="k-means++", random_state=1, max_iter=30, tol=0.0,
+                                   detrend=True, ground_level=True, engine=engine)
+    assert res.height_norm is not None and res.height_norm.shape == (res.n_points,)
+    assert res.height_norm.min() == 0.0 and res.height_norm.max() == 1.0
+    Pt, hn_ref, lo, hi, off = UO.reference_tail_stack(hm)
+    np.testing.assert_array_equal(res.extra["segment_offsets"], off)
+    np.testing.assert_allclose(res.extra["h_min"], lo, atol=1e-4)
+    np.testing.assert_allclose(res.fused_cloud[:, 0], Pt[:, 2], rtol=0, atol=2e-4)   # napari (z,y,x)
+    np.testing.assert_allclose(res.height_norm, hn_ref, rtol=0, atol=1e-5)
+    # k-means parity on the cloud the device actually clustered
+    X = res.fused_cloud[:, ::-1].astype(np.float64)
+    ref = KO.kmeans_default_call(X, 6, 1, n_init=1, max_iter=30, tol=0.0)
+    assert res.n_iter == ref["n_iter"]
+    check_labels(X, ref["centers"], ref["labels"], res.labels)
+    check_centroids(ref["centers"], res.centroids, X)
+    layers = pkg.to_layers(res)
+    assert layers[0][1]["properties"]["height"] is res.height_norm
+
+
+# ---------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs[1]: 10 x 2048 x 2048, k = 16)
 # ---------------------------------------------------------------------------------------
 def test_config2_full_size_single_step(engine):
