@@ -40,10 +40,13 @@ SIGNATURES = {
     "mdkm_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_ubyte)]),
     "mdkm_unproject": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int,
                                c_int64, c_int64, c_float, c_int, c_int, POINTER(c_int64)]),
+    "mdkm_bind_cloud_output": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
     "mdkm_set_points": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int]),
     "mdkm_num_points": (c_int64, [c_void_p]),
     "mdkm_gather_points": (c_int, [c_void_p, POINTER(c_int64), c_int, POINTER(c_float)]),
     "mdkm_get_cloud": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdkm_get_cloud_async": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "mdkm_wait": (c_int, [c_void_p]),
     "mdkm_num_segments": (c_int, [c_void_p]),
     "mdkm_segment_offsets": (c_int, [c_void_p, POINTER(c_int64)]),
     "mdkm_ground_level": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_double), POINTER(c_double)]),

@@ -159,17 +159,26 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     own = engine is None
     eng = engine or Engine(device)
     try:
+        # without ground levelling the cloud is final as soon as a slab is unprojected: it is
+        # streamed back while the rest of the stack is still being uploaded
+        stream = "napari" if (return_cloud and not ground_level) else None
         n = eng.unproject(height_maps, valid_masks, max_abs_height=max_abs_height, detrend=detrend,
-                          disparity_scale=disparity_scale, stack_shape=stack_shape, pix_begin=pix_begin)
+                          disparity_scale=disparity_scale, stack_shape=stack_shape, pix_begin=pix_begin,
+                          stream_cloud=stream)
+        cloud = None
+        if stream is not None:
+            n, cloud = n
         hn = None
         extra = {"segment_offsets": eng.segment_offsets}
         if ground_level:
             lo, hi, hn = eng.ground_level(True)
             extra["h_min"], extra["h_max"] = lo, hi
-        # the cloud is final now: its device->host copy is issued before the Lloyd loop
-        cloud = eng.get_cloud(napari_order=True) if return_cloud else None
+        # otherwise its device->host copy is issued now and overlaps the Lloyd loop
+        if return_cloud and cloud is None:
+            cloud = eng.get_cloud(napari_order=True, wait=False)
         r = _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
                         tol=tol, random_state=random_state)
+        eng.wait()
         return FusionResult(labels=r["labels"], centroids=r["centers"], fused_cloud=cloud,
                             n_iter=r["n_iter"], inertia=r["inertia"], n_points=n,
                             n_refined=r["n_refined"], n_relocations=r["n_relocations"],

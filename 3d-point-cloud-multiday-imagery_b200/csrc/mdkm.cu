@@ -26,6 +26,15 @@ using namespace mdkm;
 namespace {
 
 constexpr int kBatch = 10;                          // Lloyd iterations enqueued between status polls
+constexpr size_t kMappedBytes = 256 << 10;          // device-visible host buffer for small results
+
+// copies `bytes` (a multiple of 4) from device memory into device-visible host memory
+__global__ void publish_kernel(void* dst_host, const void* src, int bytes) {
+  const int n4 = bytes >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x)
+    reinterpret_cast<unsigned int*>(dst_host)[i] = reinterpret_cast<const unsigned int*>(src)[i];
+  __threadfence_system();
+}
 
 template <typename T>
 struct DevBuf {
@@ -87,6 +96,29 @@ struct mdkm_handle {
   DevBuf<double> kpp_closest, kpp_cell, kpp_blk, kpp_prefix, kpp_partials, kpp_rand;
   DevBuf<unsigned char> kpp_state;
 
+  // small device->host results (status words, totals, centroids) never use the copy engine --
+  // it may be busy for milliseconds with a bulk result copy -- but are written by a tiny
+  // kernel straight into this page-locked, device-visible (UVA) host buffer
+  unsigned char* mapped = nullptr;
+  size_t mapped_used = 0;
+  struct SmallCopy { void* dst; size_t off, bytes; };
+  std::vector<SmallCopy> small_pending;
+
+  // asynchronous result copies (cloud): side stream + staging that outlives the call
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr;   // compute stream -> d2h stream
+  bool d2h_pending = false;
+  DevBuf<float> cloud_aos;
+  // slab pipeline of mdkm_unproject: H2D copies on their own stream, per-slab events
+  cudaStream_t h2d_stream = nullptr;
+  std::vector<cudaEvent_t> slab_ev;
+  DevBuf<long long> slab_totals;     // [n_slabs + 1] running point totals (device)
+  long long* h_slab_totals = nullptr;  // pinned mirror
+  size_t h_slab_cap = 0;
+  float* bound_cloud_out = nullptr;  // mdkm_bind_cloud_output
+  long long bound_cloud_cap = 0;
+  int bound_cloud_napari = 1;
+
   // communicator
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -134,6 +166,34 @@ int fail(mdkm_handle* h, int code, const char* fmt, ...) {
     if (rc__ != MDKM_OK) return rc__; \
   } while (0)
 
+// Enqueue a small device->host result on the compute stream without the copy engine.
+// `pinned_dst` (optional) is a page-locked destination written directly; otherwise the bytes
+// land in the handle's mapped buffer and sync_small() hands them to `dst`.
+int small_d2h(mdkm_handle* h, void* dst, const void* dev_src, size_t bytes, bool dst_is_pinned = false) {
+  if (bytes == 0) return MDKM_OK;
+  if (bytes % 4 != 0) return fail(h, MDKM_ERR_INVALID, "small_d2h: size must be a multiple of 4");
+  void* target = dst;
+  if (!dst_is_pinned) {
+    const size_t off = (h->mapped_used + 15) & ~(size_t)15;
+    if (off + bytes > kMappedBytes) return fail(h, MDKM_ERR_INVALID, "small result buffer exhausted");
+    target = h->mapped + off;
+    h->mapped_used = off + bytes;
+    h->small_pending.push_back({dst, off, bytes});
+  }
+  publish_kernel<<<1, 256, 0, h->stream>>>(target, dev_src, (int)bytes);
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+// Synchronise the compute stream and deliver the pending small results.
+int sync_small(mdkm_handle* h) {
+  CU(cudaStreamSynchronize(h->stream));
+  for (const auto& c : h->small_pending) memcpy(c.dst, h->mapped + c.off, c.bytes);
+  h->small_pending.clear();
+  h->mapped_used = 0;
+  return MDKM_OK;
+}
+
 template <typename T>
 int ensure(mdkm_handle* h, DevBuf<T>& b, size_t elems) {
   if (b.cap >= elems && b.p) return MDKM_OK;
@@ -161,6 +221,15 @@ inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m
 int grid_for(const mdkm_handle* h, long long work_items, int per_sm) {
   long long g = std::min<long long>(work_items, (long long)h->sm_count * per_sm);
   return (int)std::max<long long>(1, g);
+}
+
+// Blocks until the asynchronous result copies issued so far have landed in host memory.
+int wait_pending(mdkm_handle* h) {
+  if (h->d2h_pending) {
+    CU(cudaStreamSynchronize(h->d2h_stream));
+    h->d2h_pending = false;
+  }
+  return MDKM_OK;
 }
 
 int alloc_points(mdkm_handle* h, long long n) {
@@ -203,8 +272,8 @@ int compute_frame(mdkm_handle* h) {
     CU(cudaGetLastError());
   }
   unsigned int ord[6];
-  CU(cudaMemcpyAsync(ord, h->uscratch.p + 4, sizeof(ord), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(small_d2h(h, ord, h->uscratch.p + 4, sizeof(ord)));
+  OK(sync_small(h));
   float mm[6];
   for (int i = 0; i < 6; ++i) mm[i] = ord2f(ord[i]);
   long long ntot = h->n;
@@ -217,9 +286,9 @@ int compute_frame(mdkm_handle* h) {
     OK(allreduce(h, dmm, 3, kNcclFloat32, kNcclMin));
     OK(allreduce(h, dmm + 3, 3, kNcclFloat32, kNcclMax));
     OK(allreduce(h, dn, 1, kNcclInt64, kNcclSum));
-    CU(cudaMemcpyAsync(mm, dmm, sizeof(mm), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(&ntot, dn, 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    OK(small_d2h(h, mm, dmm, sizeof(mm)));
+    OK(small_d2h(h, &ntot, dn, 8));
+    OK(sync_small(h));
   }
   h->n_total = ntot;
   for (int d = 0; d < 3; ++d) {
@@ -263,8 +332,8 @@ int compute_moments(mdkm_handle* h, double* mean_var_out) {
   }
   OK(allreduce(h, h->dscratch.p, 6, kNcclFloat64, kNcclSum));
   double m[6];
-  CU(cudaMemcpyAsync(m, h->dscratch.p, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(small_d2h(h, m, h->dscratch.p, sizeof(m)));
+  OK(sync_small(h));
   const double N = (double)std::max<long long>(h->n_total, 1);
   double mv = 0.0;
   for (int d = 0; d < 3; ++d) {
@@ -446,8 +515,8 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
     long long* d = reinterpret_cast<long long*>(h->dscratch.p);
     CU(cudaMemcpyAsync(d, sizes.data(), sizeof(long long) * h->n_ranks, cudaMemcpyHostToDevice, h->stream));
     OK(allreduce(h, d, h->n_ranks, kNcclInt64, kNcclSum));
-    CU(cudaMemcpyAsync(sizes.data(), d, sizeof(long long) * h->n_ranks, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    OK(small_d2h(h, sizes.data(), d, sizeof(long long) * h->n_ranks));
+    OK(sync_small(h));
     for (int r = 0; r < h->rank; ++r) rank_offset += sizes[r];
   }
   RelocParams rp{};
@@ -528,7 +597,11 @@ int mdkm_create(mdkm_handle** out, int device, void* cuda_stream) {
     }
     h->own_stream = true;
   }
-  if (cudaMallocHost(&h->h_total, 64) != cudaSuccess) {
+  if (cudaMallocHost(&h->h_total, 64) != cudaSuccess ||
+      cudaHostAlloc(&h->mapped, kMappedBytes, cudaHostAllocMapped) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return MDKM_ERR_CUDA;
   }
@@ -540,7 +613,18 @@ void mdkm_destroy(mdkm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
   if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->h2d_stream) {
+    cudaStreamSynchronize(h->h2d_stream);
+    cudaStreamDestroy(h->h2d_stream);
+  }
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  for (auto e : h->slab_ev) cudaEventDestroy(e);
+  if (h->h_slab_totals) cudaFreeHost(h->h_slab_totals);
+  release(h->slab_totals);
+  release(h->cloud_aos);
   release(h->pts);
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
@@ -551,6 +635,7 @@ void mdkm_destroy(mdkm_handle* h) {
   if (h->d_status) cudaFree(h->d_status);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->h_total) cudaFreeHost(h->h_total);
+  if (h->mapped) cudaFreeHost(h->mapped);
   for (auto e : h->batch_ev)
     if (e) cudaEventDestroy(e);
   for (auto e : h->prof_ev) cudaEventDestroy(e);
@@ -624,21 +709,44 @@ int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz
   if (!h || !idx || !out_xyz || m < 0) return fail(h, MDKM_ERR_INVALID, "bad gather argument");
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
   CU(cudaSetDevice(h->device));
-  for (int i = 0; i < m; ++i) {
+  for (int i = 0; i < m; ++i)
     if (idx[i] < 0 || idx[i] >= h->n) return fail(h, MDKM_ERR_INVALID, "gather index %lld out of range", (long long)idx[i]);
-    const float* q = h->pts.p + pt_off(idx[i]);
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 0, q, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 1, q + kGroup, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(out_xyz + 3 * i + 2, q + 2 * kGroup, 4, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CU(cudaStreamSynchronize(h->stream));
+  if (m == 0) return MDKM_OK;
+  if ((size_t)m * 12 > kMappedBytes / 2) return fail(h, MDKM_ERR_INVALID, "gather of %d points is too large", m);
+  OK(ensure(h, h->dscratch, (size_t)m * 3 + 16));
+  long long* d_idx = reinterpret_cast<long long*>(h->dscratch.p);
+  float* d_out = reinterpret_cast<float*>(h->dscratch.p + m);
+  CU(cudaMemcpyAsync(d_idx, idx, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+  gather_points_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(h->pts.p, d_idx, m, d_out);
+  ++h->launches;
+  CU(cudaGetLastError());
+  OK(small_d2h(h, out_xyz, d_out, (size_t)m * 12));
+  OK(sync_small(h));
   return MDKM_OK;
 }
 
+int mdkm_bind_cloud_output(mdkm_handle* h, float* out_host, int64_t capacity_points, int napari_order) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (out_host && capacity_points < 0) return fail(h, MDKM_ERR_INVALID, "bad capacity");
+  h->bound_cloud_out = out_host;
+  h->bound_cloud_cap = out_host ? capacity_points : 0;
+  h->bound_cloud_napari = napari_order;
+  return MDKM_OK;
+}
+
+// Unprojection as a pipeline of slabs: the host->device copy of slab s+1 (copy stream) overlaps
+// the kernels of slab s (compute stream) and, when a cloud output is bound, the device->host
+// copy of the points slab s-1 produced (result stream).  PCIe is full duplex, so the two copy
+// directions proceed together; the kernels are negligible next to either.
 int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale, const uint8_t* mask, int D, int H,
                    int W, int64_t pix_begin, int64_t pix_count, float max_abs, int detrend, int mem,
                    int64_t* n_points_out) {
   if (!h) return MDKM_ERR_INVALID;
+  float* cloud_out = h->bound_cloud_out;  // a binding is consumed by this call, whatever happens
+  const long long cloud_cap = h->bound_cloud_cap;
+  const int cloud_napari = h->bound_cloud_napari;
+  h->bound_cloud_out = nullptr;
+  h->bound_cloud_cap = 0;
   if (D < 0 || H <= 0 || W <= 0 || pix_begin < 0 || pix_count < 0 ||
       pix_begin + pix_count > (int64_t)D * H * W || (pix_count > 0 && !hm))
     return fail(h, MDKM_ERR_INVALID, "bad stack geometry");
@@ -646,21 +754,21 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   const long long HW = (long long)H * W;
   if (detrend && ((pix_begin % HW) != 0 || (pix_count % HW) != 0))
     return fail(h, MDKM_ERR_INVALID, "detrend needs whole days in [pix_begin, pix_begin+pix_count)");
+  if (cloud_out && cloud_cap < pix_count)
+    return fail(h, MDKM_ERR_INVALID, "bound cloud output holds %lld points, the range has %lld pixels", cloud_cap,
+                (long long)pix_count);
   CU(cudaSetDevice(h->device));
+  OK(wait_pending(h));
   const size_t esz = hm_dtype == MDKM_HM_F32 ? 4 : 2;
+  const bool from_host = mem != MDKM_MEM_DEVICE;
   const void* d_hm = hm;
   const uint8_t* d_mask = mask;
-  if (mem != MDKM_MEM_DEVICE && pix_count > 0) {
-    // stage host rasters (pinned or pageable) in device memory
-    const size_t hm_bytes = (size_t)pix_count * esz;
-    const size_t hm_pad = (hm_bytes + 255) / 256 * 256;
+  const size_t hm_bytes = (size_t)pix_count * esz;
+  const size_t hm_pad = (hm_bytes + 255) / 256 * 256;
+  if (from_host && pix_count > 0) {
     OK(ensure(h, h->staging, hm_pad + (mask ? (size_t)pix_count : 0) + 256));
-    CU(cudaMemcpyAsync(h->staging.p, hm, hm_bytes, cudaMemcpyHostToDevice, h->stream));
     d_hm = h->staging.p;
-    if (mask) {
-      CU(cudaMemcpyAsync(h->staging.p + hm_pad, mask, (size_t)pix_count, cudaMemcpyHostToDevice, h->stream));
-      d_mask = h->staging.p + hm_pad;
-    }
+    if (mask) d_mask = h->staging.p + hm_pad;
   }
   OK(alloc_points(h, pix_count));
   const long long n_chunks = (pix_count + kChunk - 1) / kChunk;
@@ -679,23 +787,105 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   up.day0 = (int)(pix_begin / HW);
   long long n_out = 0;
   if (pix_count > 0) {
+    const int n_days = detrend ? (int)(pix_count / HW) : 0;
     if (detrend) {
-      const int n_days = (int)(pix_count / HW);
       OK(ensure(h, h->planes, (size_t)n_days * 8));
       OK(ensure(h, h->partials, (size_t)n_days * kPlaneBlocks * 10 + 16));
-      plane_moments_kernel<<<dim3(kPlaneBlocks, n_days), kThreads, 0, h->stream>>>(up, n_days, h->partials.p);
-      plane_solve_kernel<<<n_days, 32, 0, h->stream>>>(h->partials.p, kPlaneBlocks, W, H, h->planes.p);
-      h->launches += 2;
-      CU(cudaGetLastError());
-      up.planes = h->planes.p;
     }
-    const int g = grid_for(h, (n_chunks + 7) / 8, 8);
-    unproject_count_kernel<<<g, kThreads, 0, h->stream>>>(up);
-    scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->chunk_counts.p, n_chunks, h->chunk_offsets.p,
-                                                  h->chunk_offsets.p + n_chunks + 1);
-    unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
-    h->launches += 3;
-    CU(cudaGetLastError());
+    // slab boundaries (pixels of the range): every kSlabPix, plus the day ends when detrending
+    // (a day's plane needs the whole day).  Device input without a bound output: one slab.
+    constexpr long long kSlabPix = 4ll << 20;
+    std::vector<long long> cut;  // exclusive ends
+    if (!from_host && !cloud_out) {
+      cut.push_back(pix_count);
+    } else {
+      long long next_day = detrend ? HW : pix_count;
+      for (long long p = 0; p < pix_count;) {
+        long long e = std::min<long long>(pix_count, p + kSlabPix);
+        if (detrend && e > next_day) e = next_day;
+        if (e == next_day) next_day += HW;
+        cut.push_back(e);
+        p = e;
+      }
+    }
+    const int n_slabs = (int)cut.size();
+    OK(ensure(h, h->slab_totals, (size_t)n_slabs + 1));
+    if (h->h_slab_cap < (size_t)n_slabs + 1) {
+      if (h->h_slab_totals) cudaFreeHost(h->h_slab_totals);
+      h->h_slab_totals = nullptr;
+      h->h_slab_cap = 0;
+      CU(cudaMallocHost(&h->h_slab_totals, ((size_t)n_slabs + 1) * 8));
+      h->h_slab_cap = (size_t)n_slabs + 1;
+    }
+    while (h->slab_ev.size() < (size_t)n_slabs * 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->slab_ev.push_back(e);
+    }
+    if (cloud_out) OK(ensure(h, h->cloud_aos, (size_t)pix_count * 3));
+    CU(cudaMemsetAsync(h->slab_totals.p, 0, 8, h->stream));
+    // copies of this call must not start before earlier work on the compute stream that still
+    // reads the staging buffer has finished
+    if (from_host) {
+      CU(cudaEventRecord(h->ev_ready, h->stream));
+      CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_ready, 0));
+    }
+    long long done_chunks = 0, days_solved = 0, begin = 0;
+    for (int s = 0; s < n_slabs; ++s) {
+      const long long end = cut[s];
+      if (from_host) {
+        CU(cudaMemcpyAsync(h->staging.p + (size_t)begin * esz, static_cast<const char*>(hm) + (size_t)begin * esz,
+                           (size_t)(end - begin) * esz, cudaMemcpyHostToDevice, h->h2d_stream));
+        if (mask)
+          CU(cudaMemcpyAsync(h->staging.p + hm_pad + begin, mask + begin, (size_t)(end - begin),
+                             cudaMemcpyHostToDevice, h->h2d_stream));
+        CU(cudaEventRecord(h->slab_ev[2 * s], h->h2d_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->slab_ev[2 * s], 0));
+      }
+      long long ready = end;  // pixels whose chunks may be processed now
+      if (detrend) {
+        const long long days_in = end / HW;
+        if (days_in > days_solved) {
+          UnprojParams upd = up;
+          upd.day0 = up.day0 + (int)days_solved;
+          const int nd = (int)(days_in - days_solved);
+          plane_moments_kernel<<<dim3(kPlaneBlocks, nd), kThreads, 0, h->stream>>>(
+              upd, nd, h->partials.p + (size_t)days_solved * kPlaneBlocks * 10);
+          plane_solve_kernel<<<nd, 32, 0, h->stream>>>(h->partials.p + (size_t)days_solved * kPlaneBlocks * 10,
+                                                       kPlaneBlocks, W, H, h->planes.p + (size_t)days_solved * 8);
+          h->launches += 2;
+          days_solved = days_in;
+        }
+        ready = days_solved * HW;
+        up.planes = h->planes.p;
+      }
+      const long long c_end = (s == n_slabs - 1) ? n_chunks : ready / kChunk;
+      if (c_end > done_chunks) {
+        up.chunk_begin = done_chunks;
+        up.chunk_end = c_end;
+        const long long nc = c_end - done_chunks;
+        const int g = grid_for(h, (nc + 7) / 8, 8);
+        unproject_count_kernel<<<g, kThreads, 0, h->stream>>>(up);
+        scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->chunk_counts.p + done_chunks, nc,
+                                                      h->chunk_offsets.p + done_chunks, h->slab_totals.p + s,
+                                                      h->slab_totals.p + s + 1);
+        unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
+        h->launches += 3;
+        if (cloud_out) {
+          blocked_to_aos_range_kernel<<<g, kThreads, 0, h->stream>>>(h->pts.p, h->slab_totals.p + s, cloud_napari,
+                                                                     h->cloud_aos.p);
+          ++h->launches;
+        }
+        done_chunks = c_end;
+      } else {
+        CU(cudaMemcpyAsync(h->slab_totals.p + s + 1, h->slab_totals.p + s, 8, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      CU(cudaGetLastError());
+      OK(small_d2h(h, h->h_slab_totals + s + 1, h->slab_totals.p + s + 1, 8, /*dst_is_pinned=*/true));
+      CU(cudaEventRecord(h->slab_ev[2 * s + 1], h->stream));
+      begin = end;
+    }
+    h->h_slab_totals[0] = 0;
     // segments: where each day of the range starts in the output
     const long long d_first = pix_begin / HW, d_last = (pix_begin + pix_count - 1) / HW;
     const int n_seg = (int)(d_last - d_first + 1);
@@ -706,12 +896,20 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
       CU(cudaGetLastError());
     }
     h->seg_off.assign((size_t)n_seg + 1, 0);
-    CU(cudaMemcpyAsync(h->h_total, h->chunk_offsets.p + n_chunks + 1, 8, cudaMemcpyDeviceToHost, h->stream));
-    if (n_seg > 1)
-      CU(cudaMemcpyAsync(h->seg_off.data() + 1, h->d_seg_off.p + 1, (size_t)(n_seg - 1) * 8, cudaMemcpyDeviceToHost,
-                         h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    n_out = *h->h_total;
+    if (n_seg > 1) OK(small_d2h(h, h->seg_off.data() + 1, h->d_seg_off.p + 1, (size_t)(n_seg - 1) * 8));
+    // result copies: as soon as the host knows how many points a slab produced
+    for (int s = 0; s < n_slabs; ++s) {
+      CU(cudaEventSynchronize(h->slab_ev[2 * s + 1]));
+      const long long a = h->h_slab_totals[s], b = h->h_slab_totals[s + 1];
+      if (cloud_out && b > a) {
+        CU(cudaStreamWaitEvent(h->d2h_stream, h->slab_ev[2 * s + 1], 0));
+        CU(cudaMemcpyAsync(cloud_out + a * 3, h->cloud_aos.p + a * 3, (size_t)(b - a) * 12, cudaMemcpyDeviceToHost,
+                           h->d2h_stream));
+        h->d2h_pending = true;
+      }
+    }
+    OK(sync_small(h));
+    n_out = h->h_slab_totals[n_slabs];
     h->seg_off[n_seg] = n_out;
     h->seg_whole = (pix_begin % HW) == 0 && (pix_count % HW) == 0;
   } else {
@@ -727,21 +925,46 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   return MDKM_OK;
 }
 
-int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem) {
+static int get_cloud_impl(mdkm_handle* h, float* out, int napari_order, int mem, bool async) {
   if (!h || !out) return fail(h, MDKM_ERR_INVALID, "null argument");
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
   CU(cudaSetDevice(h->device));
+  OK(wait_pending(h));  // the staging buffer below may still be in flight
   if (h->n == 0) return MDKM_OK;
   float* dst = out;
   if (mem != MDKM_MEM_DEVICE) {
-    OK(ensure(h, h->staging, (size_t)h->n * 12));
-    dst = reinterpret_cast<float*>(h->staging.p);
+    OK(ensure(h, h->cloud_aos, (size_t)h->n * 3));
+    dst = h->cloud_aos.p;
   }
   blocked_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
       h->pts.p, h->n, napari_order, dst);
   ++h->launches;
   CU(cudaGetLastError());
-  if (mem != MDKM_MEM_DEVICE) CU(cudaMemcpyAsync(out, dst, (size_t)h->n * 12, cudaMemcpyDeviceToHost, h->stream));
+  if (mem != MDKM_MEM_DEVICE) {
+    // the copy runs on the side stream so that later kernels of this handle overlap it
+    CU(cudaEventRecord(h->ev_ready, h->stream));
+    CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_ready, 0));
+    CU(cudaMemcpyAsync(out, dst, (size_t)h->n * 12, cudaMemcpyDeviceToHost, h->d2h_stream));
+    h->d2h_pending = true;
+    if (!async) OK(wait_pending(h));
+  } else if (!async) {
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return MDKM_OK;
+}
+
+int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem) {
+  return get_cloud_impl(h, out, napari_order, mem, false);
+}
+
+int mdkm_get_cloud_async(mdkm_handle* h, float* out, int napari_order, int mem) {
+  return get_cloud_impl(h, out, napari_order, mem, true);
+}
+
+int mdkm_wait(mdkm_handle* h) {
+  if (!h) return MDKM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  OK(wait_pending(h));
   CU(cudaStreamSynchronize(h->stream));
   return MDKM_OK;
 }
@@ -789,7 +1012,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
         OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
         OK(launch_update(h, kb, /*allow_pause=*/1, 0));
       }
-      CU(cudaMemcpyAsync(&h->h_status[tail], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+      OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
       CU(cudaEventRecord(h->batch_ev[tail], h->stream));
       tail ^= 1;
       ++inflight;
@@ -834,12 +1057,11 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   ++h->launches;
   CU(cudaGetLastError());
   if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
-  if (centroids_out)
-    CU(cudaMemcpyAsync(centroids_out, h->dscratch.p, (size_t)k * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(&h->h_status[0], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+  if (centroids_out) OK(small_d2h(h, centroids_out, h->dscratch.p, (size_t)k * 3 * sizeof(double)));
+  OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
   if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
     CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(sync_small(h));
   const DevStatus& fin = h->h_status[0];
   if (n_iter_out) *n_iter_out = fin.iter;
   if (inertia_out) *inertia_out = fin.inertia;
@@ -879,9 +1101,8 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   read_sums_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->acc.p, k, h->fr, h->dscratch.p, d_counts);
   ++h->launches;
   CU(cudaGetLastError());
-  if (sums_out)
-    CU(cudaMemcpyAsync(sums_out, h->dscratch.p, (size_t)k * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (counts_out) CU(cudaMemcpyAsync(counts_out, d_counts, (size_t)k * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sums_out) OK(small_d2h(h, sums_out, h->dscratch.p, (size_t)k * 3 * sizeof(double)));
+  if (counts_out) OK(small_d2h(h, counts_out, d_counts, (size_t)k * 8));
   if (labels_out) {
     // widen the stored labels: the final kernel in "use stored labels" mode
     int* labels_dev = labels_out;
@@ -896,8 +1117,8 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
     if (labels_mem != MDKM_MEM_DEVICE && h->n > 0)
       CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
-  CU(cudaMemcpyAsync(&h->h_status[0], h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
+  OK(sync_small(h));
   h->stat_refined = (long long)h->h_status[0].n_refined;
   h->stat_reloc = 0;
   OK(collect_profile(h));
@@ -963,8 +1184,8 @@ int mdkm_ground_level(mdkm_handle* h, float* height_norm_out, int mem, double* h
     h->launches += 2;
     CU(cudaGetLastError());
   }
-  CU(cudaMemcpyAsync(tg.data(), h->sel_targets.p, tg.size() * sizeof(SelTarget), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(small_d2h(h, tg.data(), h->sel_targets.p, tg.size() * sizeof(SelTarget)));
+  OK(sync_small(h));
   std::vector<double> levels((size_t)n_seg * 2, 0.0);
   for (int s = 0; s < n_seg; ++s) {
     const long long ns = h->seg_off[s + 1] - h->seg_off[s];
@@ -1058,10 +1279,9 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
     }
     CU(cudaGetLastError());
   }
-  CU(cudaMemcpyAsync(centers_out, kp.centers_out, (size_t)k * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
-  if (indices_out)
-    CU(cudaMemcpyAsync(indices_out, kp.indices_out, (size_t)k * 8, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  OK(small_d2h(h, centers_out, kp.centers_out, (size_t)k * 3 * 8));
+  if (indices_out) OK(small_d2h(h, indices_out, kp.indices_out, (size_t)k * 8));
+  OK(sync_small(h));
   return MDKM_OK;
 }
 

@@ -34,6 +34,8 @@ struct UnprojParams {
   float* pts;             // blocked cloud (common.cuh)
   const double* planes;   // [n_days][8]: centre xyz, normal xyz, pad -- or nullptr
   int day0;               // day index of planes[0]
+  long long chunk_begin;  // this launch handles chunks [chunk_begin, chunk_end) of the range
+  long long chunk_end;
 };
 
 // Loads 4 consecutive pixel heights starting at local index i (i % 4 == 0); invalid -> NaN.
@@ -87,8 +89,7 @@ __global__ void __launch_bounds__(kThreads) unproject_count_kernel(const UnprojP
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (kThreads / 32);
-  const long long n_chunks = (p.pix_count + kChunk - 1) / kChunk;
-  for (long long c = warp; c < n_chunks; c += n_warps) {
+  for (long long c = p.chunk_begin + warp; c < p.chunk_end; c += n_warps) {
     unsigned int cnt = 0;
 #pragma unroll 4
     for (int r = 0; r < kChunk / 128; ++r) {
@@ -103,13 +104,15 @@ __global__ void __launch_bounds__(kThreads) unproject_count_kernel(const UnprojP
   }
 }
 
-// Exclusive scan of the chunk counts (single CTA of 1024 threads); writes the total.
+// Exclusive scan of n chunk counts (single CTA of 1024 threads), continuing from *carry_in
+// (points produced by the earlier slabs); writes the running total to *carry_out.
 __global__ void __launch_bounds__(1024) scan_chunks_kernel(const unsigned int* counts, long long n,
-                                                           long long* offsets, long long* total) {
+                                                           long long* offsets, const long long* carry_in,
+                                                           long long* carry_out) {
   __shared__ long long s_warp[32];
   __shared__ long long s_carry;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) s_carry = carry_in ? *carry_in : 0;
   __syncthreads();
   for (long long base = 0; base < n; base += 1024) {
     const long long i = base + tid;
@@ -137,15 +140,14 @@ __global__ void __launch_bounds__(1024) scan_chunks_kernel(const unsigned int* c
     if (tid == 1023) s_carry = carry + s_warp[31];
     __syncthreads();
   }
-  if (tid == 0) *total = s_carry;
+  if (tid == 0) *carry_out = s_carry;
 }
 
 __global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const UnprojParams p) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (kThreads / 32);
-  const long long n_chunks = (p.pix_count + kChunk - 1) / kChunk;
-  for (long long c = warp; c < n_chunks; c += n_warps) {
+  for (long long c = p.chunk_begin + warp; c < p.chunk_end; c += n_warps) {
     long long out = p.chunk_offsets[c];
     for (int r = 0; r < kChunk / 128; ++r) {
       const long long i = c * kChunk + r * 128 + lane * 4;
@@ -429,6 +431,16 @@ __global__ void __launch_bounds__(kThreads) to_blocked_kernel(const float* src, 
   }
 }
 
+// out[i] = (x, y, z) of point idx[i]  (X[seeds] of init="random", sklearn/_kmeans.py:1014-1021)
+__global__ void gather_points_kernel(const float* pts, const long long* idx, int m, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float* q = pts + pt_off(idx[i]);
+  out[3 * i + 0] = q[0];
+  out[3 * i + 1] = q[kGroup];
+  out[3 * i + 2] = q[2 * kGroup];
+}
+
 // zero the unused tail of the last block (and nothing else)
 __global__ void zero_tail_kernel(float* pts, long long n) {
   const long long cap = (n + kGroup - 1) / kGroup * kGroup;
@@ -445,6 +457,18 @@ __global__ void __launch_bounds__(kThreads) blocked_to_aos_kernel(const float* p
                                                                   float* out) {
   const long long total = n * 3;
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+    const long long i = t / 3;
+    const int c = (int)(t - i * 3);
+    const int src = napari ? 2 - c : c;
+    out[t] = pts[pt_off(i) + src * kGroup];
+  }
+}
+
+// same for the points [range[0], range[1]) only (one slab of a streamed unprojection)
+__global__ void __launch_bounds__(kThreads) blocked_to_aos_range_kernel(const float* pts, const long long* range,
+                                                                        int napari, float* out) {
+  const long long t0 = range[0] * 3, t1 = range[1] * 3;
+  for (long long t = t0 + (long long)blockIdx.x * kThreads + threadIdx.x; t < t1; t += (long long)gridDim.x * kThreads) {
     const long long i = t / 3;
     const int c = (int)(t - i * 3);
     const int src = napari ? 2 - c : c;

@@ -120,8 +120,12 @@ class Engine:
 
     # -- data ----------------------------------------------------------------------------
     def unproject(self, height_maps, valid_masks=None, *, max_abs_height=144.0, detrend=False,
-                  disparity_scale=None, pix_begin=0, stack_shape=None) -> int:
+                  disparity_scale=None, pix_begin=0, stack_shape=None, stream_cloud=None):
         """Height rasters -> resident XYZ cloud (plugin.py:148-171).  Returns the point count.
+
+        ``stream_cloud``: None, or "napari" / "xyz" to also stream the cloud to the host while
+        the stack is still being uploaded; the call then returns ``(n, cloud[n,3])`` and the
+        array is complete after ``wait()``.
 
         ``height_maps``: float32 ``[D,H,W]`` (NaN = nodata) or, with ``disparity_scale``
         (the reference uses -1/16), int16 OpenCV fixed-point disparity.  For a sharded
@@ -147,12 +151,19 @@ class Engine:
             if mmem != mem:
                 raise ValueError("height_maps and valid_masks must live in the same memory space")
         n = c_int64(0)
+        cloud_buf = None
+        if stream_cloud is not None:
+            cloud_buf = self._result_buffer("cloud", (max(count, 1), 3), np.float32)
+            self._check(self._lib.mdkm_bind_cloud_output(
+                self._h, c_void_p(cloud_buf.ctypes.data), int(count), 1 if stream_cloud == "napari" else 0))
         self._check(self._lib.mdkm_unproject(
             self._h, c_void_p(ptr), C.HM_I16 if is_i16 else C.HM_F32,
             float(disparity_scale) if is_i16 else 1.0, c_void_p(mptr) if mptr else None,
             int(D), int(H), int(W), int(pix_begin), int(count), float(max_abs_height),
             1 if detrend else 0, mem, byref(n)))
         del keep, keep_m
+        if stream_cloud is not None:
+            return int(n.value), cloud_buf[: int(n.value)]
         return int(n.value)
 
     def set_points(self, points, layout="aos") -> int:
@@ -184,16 +195,24 @@ class Engine:
             out.ctypes.data_as(POINTER(c_float))))
         return out
 
-    def get_cloud(self, napari_order=True, out=None):
-        """Resident cloud as float32 ``[N,3]``; (z,y,x) columns when ``napari_order``."""
+    def get_cloud(self, napari_order=True, out=None, wait=True):
+        """Resident cloud as float32 ``[N,3]``; (z,y,x) columns when ``napari_order``.
+
+        ``wait=False`` only enqueues the copy (it overlaps later calls such as ``fit``); the
+        array is complete after ``wait()``."""
         n = self.n_points
         if out is None:
             out = self._result_buffer("cloud", (n, 3), np.float32)
         ptr, mem, keep, shape, _ = _as_buffer(out)
         if int(np.prod(shape)) != n * 3:
             raise ValueError("out must hold N*3 float32")
-        self._check(self._lib.mdkm_get_cloud(self._h, c_void_p(ptr), 1 if napari_order else 0, mem))
+        fn = self._lib.mdkm_get_cloud if wait else self._lib.mdkm_get_cloud_async
+        self._check(fn(self._h, c_void_p(ptr), 1 if napari_order else 0, mem))
         return out
+
+    def wait(self):
+        """Block until every asynchronous result copy of this engine has completed."""
+        self._check(self._lib.mdkm_wait(self._h))
 
     @property
     def segment_offsets(self) -> np.ndarray:

@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_ev.set()
@@ -329,7 +329,7 @@ def run_mine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))

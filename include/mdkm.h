@@ -78,6 +78,15 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
                    int64_t pix_count, float max_abs, int detrend, int mem,
                    int64_t* n_points_out);
 
+/* Optional: have the NEXT mdkm_unproject also stream the cloud it produces into host memory
+ * (float32 [n,3]; (z,y,x) columns when napari_order != 0, i.e. plugin.py:192's
+ * `points_coords`), slab by slab while later slabs are still being uploaded and unprojected.
+ * out_host must hold capacity_points >= pix_count points (the valid count is not known in
+ * advance) and should be page-locked.  The binding is consumed by that one call; the array
+ * is complete after mdkm_wait (or any later call that touches the cloud). */
+int mdkm_bind_cloud_output(mdkm_handle* h, float* out_host, int64_t capacity_points,
+                           int napari_order);
+
 /* Load an already unprojected cloud (this rank's shard).  Replaces the `X` argument of the
  * reference's KMeans(...).fit_predict(X) call (members/jasraj/land_use_classification/
  * core.py:227-228) for d = 3. */
@@ -93,6 +102,13 @@ int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz
 /* Copy the resident cloud out as float32 [n,3].  napari_order != 0 gives (z,y,x) columns as
  * plugin.py:192 builds `points_coords`; 0 gives (x,y,z). */
 int mdkm_get_cloud(mdkm_handle* h, float* out, int napari_order, int mem);
+
+/* Same, but returns as soon as the copy is enqueued: it proceeds on a side stream while
+ * later calls on this handle (mdkm_fit) compute.  `out` (page-locked host memory for a real
+ * overlap) holds the cloud once mdkm_wait -- or any later call that touches the cloud --
+ * has returned. */
+int mdkm_get_cloud_async(mdkm_handle* h, float* out, int napari_order, int mem);
+int mdkm_wait(mdkm_handle* h);
 
 /* Segments of the resident cloud: one per day of the unprojected pixel range (the reference
  * treats every stereo pair / day separately, plugin.py:106), one for mdkm_set_points.

@@ -107,6 +107,30 @@ def test_unproject_detrend(engine, golden):
     np.testing.assert_allclose(engine.get_cloud(False)[:, 2], ref[:, 2], rtol=0, atol=2e-5)
 
 
+def test_streamed_cloud_matches_get_cloud(engine):
+    """Slab pipeline (several slabs, day-aligned cuts when detrending) == the one-shot path."""
+    import torch
+
+    hm_dev = synth.make_stack(3, 1500, 1500, seed=11, device="cuda")
+    hm = hm_dev.cpu().numpy()
+    mask = np.random.RandomState(3).rand(*hm.shape) > 0.2
+    for detrend in (False, True):
+        for src, m in ((hm, None), (hm, mask), (hm_dev, None)):
+            n, cloud = engine.unproject(src, m, detrend=detrend, stream_cloud="napari")
+            engine.wait()
+            ref = engine.get_cloud(napari_order=True, out=np.empty((n, 3), dtype=np.float32))
+            assert n == cloud.shape[0]
+            np.testing.assert_array_equal(cloud, ref)
+            if not detrend:
+                P = UO.unproject_stack(hm[:1], None if m is None else m[:1])
+                np.testing.assert_array_equal(cloud[: P.shape[0], ::-1].astype(np.float64), P)
+    n2, xyz = engine.unproject(hm, stream_cloud="xyz")
+    engine.wait()
+    np.testing.assert_array_equal(xyz, engine.get_cloud(False, out=np.empty((n2, 3), dtype=np.float32)))
+    del hm_dev
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------
 # K2+K3 single step
 # ---------------------------------------------------------------------------------------
