@@ -17,6 +17,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 HM_F32, HM_I16 = 0, 1
 POINTS_AOS, POINTS_SOA = 0, 1
 NCCL_UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 STATUS_NAMES = {
     0: "MDKM_OK",
@@ -38,6 +39,8 @@ SIGNATURES = {
     "mdkm_last_error": (c_char_p, [c_void_p]),
     "mdkm_comm_unique_id": (c_int, [POINTER(c_ubyte)]),
     "mdkm_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_ubyte)]),
+    "mdkm_comm_p2p_handle": (c_int, [c_void_p, POINTER(c_ubyte)]),
+    "mdkm_comm_p2p_open": (c_int, [c_void_p, POINTER(c_ubyte)]),
     "mdkm_unproject": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int,
                                c_int64, c_int64, c_float, c_int, c_int, POINTER(c_int64)]),
     "mdkm_bind_cloud_output": (c_int, [c_void_p, c_void_p, c_int64, c_int]),

@@ -42,7 +42,22 @@ struct DevStatus {
   double tol;      // scaled tolerance  mean(var(X)) * tol
   double inertia;  // written by the finalize pass
   float thresh;    // 2 * FP32 error bound of the fast distances for the current table
-  float pad0;
+  unsigned int ticket;            // CTAs of the running step kernel that have flushed their sums
+  unsigned long long epoch;       // fused steps completed since the communicator was created
+  int xchg_timeout;               // 1: a peer never delivered its partial sums (fatal)
+  int pad1;
+};
+
+// Peer exchange of the K x 4 partial sums over NVLink (one process per GPU, buffers shared
+// through CUDA IPC).  Every rank owns a buffer  data[2][n_ranks][slot] + flags[2][n_ranks];
+// rank r writes its partials into slot [parity][r] of EVERY rank's buffer, then the flag.
+constexpr int kMaxRanks = 8;
+struct PeerXchg {
+  unsigned long long* data[kMaxRanks];   // data base of rank q's buffer (peer-mapped pointer)
+  unsigned long long* flags[kMaxRanks];  // flags base of rank q's buffer
+  int n_ranks, rank;
+  int slot;                              // elements per slot (>= kpad*4 + 8)
+  int pad;
 };
 
 // Frame of the resident cloud: x' = x - origin (exact for pixel grids), fixed-point scale.

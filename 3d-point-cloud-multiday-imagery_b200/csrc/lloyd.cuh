@@ -34,6 +34,167 @@
 
 namespace mdkm {
 
+// ---------------------------------------------------------------------------------------
+// K4: centroid update + convergence.  One CTA.
+// ---------------------------------------------------------------------------------------
+struct UpdateParams {
+  unsigned long long* acc;  // [kpad*4 + 8], global sums (already allreduced)
+  unsigned long long* acc_saved;  // [kpad*4 + 8]: the sums as they were when the loop paused
+  unsigned char* table;     // centroid table, updated in place
+  DevStatus* st;
+  Frame fr;
+  double mean[3];           // data mean (only used for sklearn's empty-cluster copy quirk)
+  int k, kpad;
+  int allow_pause;          // 1: pause for relocation when a cluster is empty
+  int ignore_status;
+};
+
+__device__ __forceinline__ double block_sum_fixed(double v, double* s_red) {
+  // fixed-order reduction: shuffle tree inside the warp, warps combined in index order
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+  return t;
+}
+
+__device__ __forceinline__ double block_max(double v, double* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, s_red[i]);
+  return t;
+}
+
+// Executed by all kThreads threads of ONE CTA: the stand-alone update kernel, or the last CTA
+// of a fused step kernel.  Reads the accumulators through L2 (they were produced by atomics).
+__device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
+  DevStatus* st = u.st;
+  __shared__ double s_red[kThreads / 32];
+  __shared__ int s_nempty;
+  __shared__ unsigned long long s_maxcnt;  // (count << 20) | (kMaxK*... - j): argmax, first wins
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_nempty = 0;
+    s_maxcnt = 0ull;
+  }
+  __syncthreads();
+  // empty clusters and the heaviest cluster (np.argmax: first maximum)
+  int my_empty = 0;
+  unsigned long long my_max = 0ull;
+  for (int j = tid; j < u.k; j += kThreads) {
+    const unsigned long long cnt = __ldcg(&u.acc[j * 4 + 3]);
+    if (cnt == 0ull) ++my_empty;
+    const unsigned long long key = (cnt << 13) | (unsigned long long)(kMaxK * 2 - 1 - j);
+    my_max = key > my_max ? key : my_max;
+  }
+  if (my_empty) atomicAdd(&s_nempty, my_empty);
+  atomicMax(&s_maxcnt, my_max);
+  __syncthreads();
+  const int n_empty = s_nempty;
+  if (n_empty > 0 && u.allow_pause) {
+    // the sums are parked: exchanges already enqueued behind this point (NCCL path) keep
+    // running on `acc`, so the host restores it from here before it relocates
+    for (int i = tid; i < u.kpad * 4 + 8; i += kThreads) u.acc_saved[i] = __ldcg(&u.acc[i]);
+    if (tid == 0) {
+      st->paused = 1;
+      st->n_empty = n_empty;
+    }
+    return;  // the host sequences the relocation kernels and re-runs update
+  }
+  const int jmax = kMaxK * 2 - 1 - (int)(s_maxcnt & 0x1fffull);
+
+  float4* fast = reinterpret_cast<float4*>(u.table);
+  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
+
+  double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
+  for (int j = tid; j < u.kpad; j += kThreads) {
+    if (j < u.k) {
+      const double4 old = exact[j];
+      const unsigned long long cnt = __ldcg(&u.acc[j * 4 + 3]);
+      double cx, cy, cz;
+      int src = j;
+      bool raw = false;
+      if (cnt == 0ull) {
+        // sklearn/_k_means_common.pyx:289-293: copy of the heaviest cluster's row -- which is
+        // still the un-averaged sum when that row comes later in the loop.
+        src = jmax;
+        raw = jmax > j;
+      }
+      const double sc = (double)__ldcg(&u.acc[src * 4 + 3]);
+      const double qx = (double)(long long)__ldcg(&u.acc[src * 4 + 0]) / u.fr.scale[0];
+      const double qy = (double)(long long)__ldcg(&u.acc[src * 4 + 1]) / u.fr.scale[1];
+      const double qz = (double)(long long)__ldcg(&u.acc[src * 4 + 2]) / u.fr.scale[2];
+      if (!raw) {
+        const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
+        cx = qx * alpha;
+        cy = qy * alpha;
+        cz = qz * alpha;
+      } else {
+        // raw sum in sklearn's mean-centred frame, expressed in ours
+        cx = qx + sc * (u.fr.origin[0] - u.mean[0]) + (u.mean[0] - u.fr.origin[0]);
+        cy = qy + sc * (u.fr.origin[1] - u.mean[1]) + (u.mean[1] - u.fr.origin[1]);
+        cz = qz + sc * (u.fr.origin[2] - u.mean[2]) + (u.mean[2] - u.fr.origin[2]);
+      }
+      const double dx = cx - old.x, dy = cy - old.y, dz = cz - old.z;
+      const double sh = sqrt(dx * dx + dy * dy + dz * dz);  // _center_shift, pyx:298-311
+      shift2 += sh * sh;                                     // (center_shift**2).sum()
+      const double cn = cx * cx + cy * cy + cz * cz;
+      exact[j] = make_double4(cx, cy, cz, cn);
+      fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
+      m_cn = fmax(m_cn, cn);
+      m_cx = fmax(m_cx, fabs(cx));
+      m_cy = fmax(m_cy, fabs(cy));
+      m_cz = fmax(m_cz, fabs(cz));
+    } else {
+      fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+      exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
+    }
+  }
+  shift2 = block_sum_fixed(shift2, s_red);
+  m_cn = block_max(m_cn, s_red);
+  m_cx = block_max(m_cx, s_red);
+  m_cy = block_max(m_cy, s_red);
+  m_cz = block_max(m_cz, s_red);
+  const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);
+  __syncthreads();
+  for (int i = tid; i < u.kpad * 4 + 8; i += kThreads) u.acc[i] = 0ull;
+  if (tid == 0) {
+    // FP32 error bound of the fast distances (DESIGN.md "Exactness"): u = 2^-24
+    const double ue = 5.9604644775390625e-08;
+    const double E = ue * (4.0 * m_cn + 10.0 * (u.fr.halfrange[0] * m_cx + u.fr.halfrange[1] * m_cy +
+                                                 u.fr.halfrange[2] * m_cz));
+    st->thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
+    st->shift2 = shift2;
+    st->n_changed = n_changed;
+    st->n_empty = n_empty;
+    st->paused = 0;
+    const int it = st->iter + 1;
+    st->iter = it;
+    if (!st->first && n_changed == 0ull) {  // _kmeans.py:721-726
+      st->strict = 1;
+      st->done = 1;
+    } else if (shift2 <= st->tol) {         // _kmeans.py:729-738
+      st->done = 1;
+    }
+    if (it >= st->max_iter) st->done = 1;
+    st->first = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateParams u) {
+  if (!u.ignore_status && (u.st->done || (u.st->paused && u.allow_pause))) return;
+  lloyd_update_body(u);
+}
+
+
+
 struct StepParams {
   const float* pts;           // blocked cloud (common.cuh)
   long long n;
@@ -44,6 +205,10 @@ struct StepParams {
   FrameF f;
   int k, kpad;
   int ignore_status;          // 1: test hook (run even when done/paused)
+  int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
+                              //    (NVLink, no host, no NCCL) and runs the centroid update
+  UpdateParams upd;
+  PeerXchg px;
 };
 
 struct FinalParams {
@@ -304,6 +469,46 @@ __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long
 // ---------------------------------------------------------------------------------------
 constexpr int kStages = 3;
 
+// All-gather + fixed-order sum of the ranks' partial sums, inside the step kernel: every rank
+// stores its n words into slot [parity][rank] of every rank's buffer (plain stores over
+// NVLink into peer-mapped memory), publishes a flag stamped with the step's epoch, waits for
+// the n_ranks flags in its own buffer and adds the slots in rank order.  Integer sums: every
+// rank ends with bit-identical totals.  Executed by all threads of one CTA.
+__device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned long long* acc, int n,
+                                                   DevStatus* st) {
+  const int tid = threadIdx.x, R = px.n_ranks;
+  const unsigned long long epoch = st->epoch + 1ull;
+  const int par = (int)(epoch & 1ull);
+  for (int q = 0; q < R; ++q) {
+    unsigned long long* dst = px.data[q] + ((size_t)par * R + px.rank) * px.slot;
+    for (int i = tid; i < n; i += kThreads) st_relaxed_sys_u64(dst + i, __ldcg(acc + i));
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < R) {
+    st_release_sys_u64(px.flags[tid] + par * R + px.rank, epoch);
+    // bounded wait (about 4 s): a missing peer must not hang the GPU
+    const unsigned long long* mine = px.flags[px.rank] + par * R + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(mine) != epoch) {
+      if (clock64() - t0 > (8ll << 30)) {
+        st->xchg_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned long long* base = px.data[px.rank] + (size_t)par * R * px.slot;
+  for (int i = tid; i < n; i += kThreads) {
+    unsigned long long s = 0ull;
+    for (int q = 0; q < R; ++q) s += ld_relaxed_sys_u64(base + (size_t)q * px.slot + i);
+    acc[i] = s;
+  }
+  if (tid == 0) st->epoch = epoch;
+  __threadfence();
+  __syncthreads();
+}
+
 template <typename LabT>
 __host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGroup * (int)sizeof(LabT); }
 
@@ -526,155 +731,18 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     if (s_changed) atomicAdd(&p.acc[p.kpad * 4 + 0], (unsigned long long)s_changed);
     if (s_refined) atomicAdd(&p.st->n_refined, (unsigned long long)s_refined);
   }
-}
-
-// ---------------------------------------------------------------------------------------
-// K4: centroid update + convergence.  One CTA.
-// ---------------------------------------------------------------------------------------
-struct UpdateParams {
-  unsigned long long* acc;  // [kpad*4 + 8], global sums (already allreduced)
-  unsigned char* table;     // centroid table, updated in place
-  DevStatus* st;
-  Frame fr;
-  double mean[3];           // data mean (only used for sklearn's empty-cluster copy quirk)
-  int k, kpad;
-  int allow_pause;          // 1: pause for relocation when a cluster is empty
-  int ignore_status;
-};
-
-__device__ __forceinline__ double block_sum_fixed(double v, double* s_red) {
-  // fixed-order reduction: shuffle tree inside the warp, warps combined in index order
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5;
+  if (!p.fuse_update) return;
+  // ---- fused tail: the last CTA to get here owns the complete local sums ----------------
+  __shared__ bool s_is_last;
+  __threadfence();
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[w] = v;
+  if (tid == 0) s_is_last = (atomicAdd(&p.st->ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  double t = 0.0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
-  return t;
-}
-
-__device__ __forceinline__ double block_max(double v, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
-  const int w = threadIdx.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[w] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, s_red[i]);
-  return t;
-}
-
-__global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateParams u) {
-  DevStatus* st = u.st;
-  if (!u.ignore_status && (st->done || (st->paused && u.allow_pause))) return;
-  __shared__ double s_red[kThreads / 32];
-  __shared__ int s_nempty;
-  __shared__ unsigned long long s_maxcnt;  // (count << 20) | (kMaxK*... - j): argmax, first wins
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_nempty = 0;
-    s_maxcnt = 0ull;
-  }
-  __syncthreads();
-  // empty clusters and the heaviest cluster (np.argmax: first maximum)
-  int my_empty = 0;
-  unsigned long long my_max = 0ull;
-  for (int j = tid; j < u.k; j += kThreads) {
-    const unsigned long long cnt = u.acc[j * 4 + 3];
-    if (cnt == 0ull) ++my_empty;
-    const unsigned long long key = (cnt << 13) | (unsigned long long)(kMaxK * 2 - 1 - j);
-    my_max = key > my_max ? key : my_max;
-  }
-  if (my_empty) atomicAdd(&s_nempty, my_empty);
-  atomicMax(&s_maxcnt, my_max);
-  __syncthreads();
-  const int n_empty = s_nempty;
-  if (n_empty > 0 && u.allow_pause) {
-    if (tid == 0) {
-      st->paused = 1;
-      st->n_empty = n_empty;
-    }
-    return;  // sums are kept; the host sequences the relocation kernels and re-runs update
-  }
-  const int jmax = kMaxK * 2 - 1 - (int)(s_maxcnt & 0x1fffull);
-
-  float4* fast = reinterpret_cast<float4*>(u.table);
-  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
-
-  double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
-  for (int j = tid; j < u.kpad; j += kThreads) {
-    if (j < u.k) {
-      const double4 old = exact[j];
-      const unsigned long long cnt = u.acc[j * 4 + 3];
-      double cx, cy, cz;
-      int src = j;
-      bool raw = false;
-      if (cnt == 0ull) {
-        // sklearn/_k_means_common.pyx:289-293: copy of the heaviest cluster's row -- which is
-        // still the un-averaged sum when that row comes later in the loop.
-        src = jmax;
-        raw = jmax > j;
-      }
-      const double sc = (double)u.acc[src * 4 + 3];
-      const double qx = (double)(long long)u.acc[src * 4 + 0] / u.fr.scale[0];
-      const double qy = (double)(long long)u.acc[src * 4 + 1] / u.fr.scale[1];
-      const double qz = (double)(long long)u.acc[src * 4 + 2] / u.fr.scale[2];
-      if (!raw) {
-        const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
-        cx = qx * alpha;
-        cy = qy * alpha;
-        cz = qz * alpha;
-      } else {
-        // raw sum in sklearn's mean-centred frame, expressed in ours
-        cx = qx + sc * (u.fr.origin[0] - u.mean[0]) + (u.mean[0] - u.fr.origin[0]);
-        cy = qy + sc * (u.fr.origin[1] - u.mean[1]) + (u.mean[1] - u.fr.origin[1]);
-        cz = qz + sc * (u.fr.origin[2] - u.mean[2]) + (u.mean[2] - u.fr.origin[2]);
-      }
-      const double dx = cx - old.x, dy = cy - old.y, dz = cz - old.z;
-      const double sh = sqrt(dx * dx + dy * dy + dz * dz);  // _center_shift, pyx:298-311
-      shift2 += sh * sh;                                     // (center_shift**2).sum()
-      const double cn = cx * cx + cy * cy + cz * cz;
-      exact[j] = make_double4(cx, cy, cz, cn);
-      fast[j] = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
-      m_cn = fmax(m_cn, cn);
-      m_cx = fmax(m_cx, fabs(cx));
-      m_cy = fmax(m_cy, fabs(cy));
-      m_cz = fmax(m_cz, fabs(cz));
-    } else {
-      fast[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-      exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
-    }
-  }
-  shift2 = block_sum_fixed(shift2, s_red);
-  m_cn = block_max(m_cn, s_red);
-  m_cx = block_max(m_cx, s_red);
-  m_cy = block_max(m_cy, s_red);
-  m_cz = block_max(m_cz, s_red);
-  const unsigned long long n_changed = u.acc[u.kpad * 4 + 0];
-  __syncthreads();
-  for (int i = tid; i < u.kpad * 4 + 8; i += kThreads) u.acc[i] = 0ull;
-  if (tid == 0) {
-    // FP32 error bound of the fast distances (DESIGN.md "Exactness"): u = 2^-24
-    const double ue = 5.9604644775390625e-08;
-    const double E = ue * (4.0 * m_cn + 10.0 * (u.fr.halfrange[0] * m_cx + u.fr.halfrange[1] * m_cy +
-                                                 u.fr.halfrange[2] * m_cz));
-    st->thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
-    st->shift2 = shift2;
-    st->n_changed = n_changed;
-    st->n_empty = n_empty;
-    st->paused = 0;
-    const int it = st->iter + 1;
-    st->iter = it;
-    if (!st->first && n_changed == 0ull) {  // _kmeans.py:721-726
-      st->strict = 1;
-      st->done = 1;
-    } else if (shift2 <= st->tol) {         // _kmeans.py:729-738
-      st->done = 1;
-    }
-    if (it >= st->max_iter) st->done = 1;
-    st->first = 0;
-  }
+  if (!s_is_last) return;
+  __threadfence();
+  if (tid == 0) p.st->ticket = 0u;
+  if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
+  lloyd_update_body(p.upd);
 }
 
 // Builds the centroid table from K x 3 float64 centroids in ORIGINAL coordinates.

@@ -122,6 +122,12 @@ struct mdkm_handle {
   // communicator
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // NVLink peer exchange of the partial sums (CUDA IPC): own buffer, peers' mappings
+  unsigned long long* xchg = nullptr;
+  void* peer_base[kMaxRanks] = {};
+  PeerXchg px{};
+  bool p2p_ok = false;
+  unsigned long long epoch_base = 0;  // fused steps completed on this communicator
 
   // profiling
   bool prof = false;
@@ -230,6 +236,19 @@ int wait_pending(mdkm_handle* h) {
     h->d2h_pending = false;
   }
   return MDKM_OK;
+}
+
+void close_p2p(mdkm_handle* h) {
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (h->peer_base[q]) {
+      cudaIpcCloseMemHandle(h->peer_base[q]);
+      h->peer_base[q] = nullptr;
+    }
+  if (h->xchg) cudaFree(h->xchg);
+  h->xchg = nullptr;
+  h->p2p_ok = false;
+  h->px = PeerXchg{};
+  h->epoch_base = 0;
 }
 
 int alloc_points(mdkm_handle* h, long long n) {
@@ -405,7 +424,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
   OK(ensure(h, h->table, table_bytes(kb.kpad)));
-  OK(ensure(h, h->acc, (size_t)kb.kpad * 4 + 8));
+  OK(ensure(h, h->acc, 2 * ((size_t)kb.kpad * 4 + 8)));  // live sums + the copy parked on a pause
   OK(ensure(h, h->dscratch, (size_t)std::max(64, k * 4 + 16)));
   OK(ensure(h, h->uscratch, 16));
   const long long tiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);  // 8 warp-groups per CTA pass
@@ -429,7 +448,25 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   return MDKM_OK;
 }
 
-int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
+UpdateParams make_update_params(mdkm_handle* h, const KmBuffers& kb, int allow_pause, int ignore_status) {
+  UpdateParams up{};
+  up.acc = h->acc.p;
+  up.acc_saved = h->acc.p + ((size_t)kb.kpad * 4 + 8);
+  up.table = h->table.p;
+  up.st = h->d_status;
+  up.fr = h->fr;
+  for (int d = 0; d < 3; ++d) up.mean[d] = h->mean_ok ? h->mean[d] : h->fr.origin[d];
+  up.k = kb.k; up.kpad = kb.kpad;
+  up.allow_pause = allow_pause;
+  up.ignore_status = ignore_status;
+  return up;
+}
+
+// The Lloyd iteration is ONE kernel when the sums can be completed inside it: a single rank,
+// or ranks whose exchange buffers are mapped into each other (NVLink, CUDA IPC).
+bool can_fuse(const mdkm_handle* h) { return h->n_ranks == 1 || h->p2p_ok; }
+
+int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0) {
   StepParams sp{};
   sp.pts = h->pts.p; sp.n = h->n;
   sp.labels = h->labels.p;
@@ -439,6 +476,12 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
   sp.f = h->ff;
   sp.k = kb.k; sp.kpad = kb.kpad;
   sp.ignore_status = ignore_status;
+  sp.fuse_update = fuse_update;
+  if (fuse_update) {
+    sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
+    sp.px = h->px;
+    if (h->n_ranks == 1) sp.px.n_ranks = 1;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->prof) {
     while ((int)h->prof_ev.size() < h->prof_used + 2) {
@@ -458,15 +501,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status) {
 }
 
 int launch_update(mdkm_handle* h, const KmBuffers& kb, int allow_pause, int ignore_status) {
-  UpdateParams up{};
-  up.acc = h->acc.p;
-  up.table = h->table.p;
-  up.st = h->d_status;
-  up.fr = h->fr;
-  for (int d = 0; d < 3; ++d) up.mean[d] = h->mean_ok ? h->mean[d] : h->fr.origin[d];
-  up.k = kb.k; up.kpad = kb.kpad;
-  up.allow_pause = allow_pause;
-  up.ignore_status = ignore_status;
+  const UpdateParams up = make_update_params(h, kb, allow_pause, ignore_status);
   lloyd_update_kernel<<<1, kThreads, 0, h->stream>>>(up);
   ++h->launches;
   CU(cudaGetLastError());
@@ -615,6 +650,7 @@ void mdkm_destroy(mdkm_handle* h) {
   cudaStreamSynchronize(h->stream);
   if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
   if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
+  close_p2p(h);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   if (h->h2d_stream) {
     cudaStreamSynchronize(h->h2d_stream);
@@ -665,6 +701,7 @@ int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank, const unsigned char id
   h->n_ranks = n_ranks;
   h->rank = rank;
   h->frame_ok = false;
+  close_p2p(h);
   if (n_ranks == 1) return MDKM_OK;
   if (!id) return fail(h, MDKM_ERR_INVALID, "unique id required");
   NcclApi& api = nccl_api();
@@ -673,6 +710,54 @@ int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank, const unsigned char id
   memcpy(uid.internal, id, MDKM_NCCL_UNIQUE_ID_BYTES);
   NC(api.CommInitRank(&h->comm, n_ranks, uid, rank));
   if (h->have_points) OK(compute_frame(h));
+  return MDKM_OK;
+}
+
+int mdkm_comm_p2p_handle(mdkm_handle* h, unsigned char out[MDKM_IPC_HANDLE_BYTES]) {
+  if (!h || !out) return MDKM_ERR_INVALID;
+  if (h->n_ranks < 2 || h->n_ranks > kMaxRanks)
+    return fail(h, MDKM_ERR_STATE, "peer exchange needs 2..%d ranks (mdkm_comm_init first)", kMaxRanks);
+  CU(cudaSetDevice(h->device));
+  close_p2p(h);
+  const size_t slot = (size_t)kMaxK * 4 + 8;
+  const size_t words = 2 * (size_t)h->n_ranks * slot + 2 * (size_t)h->n_ranks;
+  CU(cudaMalloc(&h->xchg, words * 8));
+  CU(cudaMemset(h->xchg, 0, words * 8));
+  cudaIpcMemHandle_t ih;
+  CU(cudaIpcGetMemHandle(&ih, h->xchg));
+  static_assert(sizeof(ih) == MDKM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(out, &ih, sizeof(ih));
+  return MDKM_OK;
+}
+
+int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles) {
+  if (!h || !handles) return MDKM_ERR_INVALID;
+  if (!h->xchg) return fail(h, MDKM_ERR_STATE, "call mdkm_comm_p2p_handle first");
+  CU(cudaSetDevice(h->device));
+  const size_t slot = (size_t)kMaxK * 4 + 8;
+  PeerXchg px{};
+  px.n_ranks = h->n_ranks; px.rank = h->rank; px.slot = (int)slot;
+  for (int q = 0; q < h->n_ranks; ++q) {
+    void* base = h->xchg;
+    if (q != h->rank) {
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, handles + (size_t)q * MDKM_IPC_HANDLE_BYTES, sizeof(ih));
+      cudaError_t e = cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (int r = 0; r < q; ++r)
+          if (h->peer_base[r]) { cudaIpcCloseMemHandle(h->peer_base[r]); h->peer_base[r] = nullptr; }
+        return fail(h, MDKM_ERR_NCCL, "cudaIpcOpenMemHandle(rank %d) failed: %s -- the NCCL exchange stays in use", q,
+                    cudaGetErrorString(e));
+      }
+      h->peer_base[q] = base;
+    }
+    px.data[q] = static_cast<unsigned long long*>(base);
+    px.flags[q] = px.data[q] + 2 * (size_t)h->n_ranks * slot;
+  }
+  h->px = px;
+  h->p2p_ok = true;
+  h->epoch_base = 0;
   return MDKM_OK;
 }
 
@@ -993,6 +1078,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   st0.k = k;
   st0.first = 1;
   st0.tol = tol_scaled;
+  st0.epoch = h->epoch_base;
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
@@ -1008,9 +1094,13 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
     while (inflight < 2 && enq < max_iter) {
       const int nb = std::min(kBatch, max_iter - enq);
       for (int b = 0; b < nb; ++b) {
-        OK(launch_step(h, kb, 0));
-        OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
-        OK(launch_update(h, kb, /*allow_pause=*/1, 0));
+        if (can_fuse(h)) {
+          OK(launch_step(h, kb, 0, /*fuse_update=*/1));
+        } else {
+          OK(launch_step(h, kb, 0));
+          OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
+          OK(launch_update(h, kb, /*allow_pause=*/1, 0));
+        }
       }
       OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
       CU(cudaEventRecord(h->batch_ev[tail], h->stream));
@@ -1030,6 +1120,8 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       inflight = 0;
       head = tail = 0;
       if (!h->mean_ok) OK(compute_moments(h, nullptr));
+      CU(cudaMemcpyAsync(h->acc.p, h->acc.p + ((size_t)kb.kpad * 4 + 8), ((size_t)kb.kpad * 4 + 8) * 8,
+                         cudaMemcpyDeviceToDevice, h->stream));
       OK(relocate_empty(h, kb, s.n_empty));
       relocs += s.n_empty;
       OK(launch_update(h, kb, /*allow_pause=*/0, 0));
@@ -1063,6 +1155,8 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
     CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
   OK(sync_small(h));
   const DevStatus& fin = h->h_status[0];
+  h->epoch_base = fin.epoch;
+  if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "peer exchange of the partial sums timed out (a rank is missing)");
   if (n_iter_out) *n_iter_out = fin.iter;
   if (inertia_out) *inertia_out = fin.inertia;
   h->stat_refined = (long long)fin.n_refined;
@@ -1090,6 +1184,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   st0.max_iter = 1;
   st0.k = k;
   st0.first = 1;
+  st0.epoch = h->epoch_base;
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));

@@ -43,8 +43,26 @@ def exchange_unique_id(make_id, rank: int, world: int, device=None) -> bytes:
     return bytes(t.cpu().tolist())
 
 
-def init_engine_comm(engine, rank: int, world: int):
-    """Give ``engine`` a NCCL communicator spanning the torch.distributed world."""
+def gather_bytes(raw: bytes, rank: int, world: int, device=None) -> bytes:
+    """All-gather of equal-length byte strings, concatenated in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend()
+    dev = torch.device("cuda", device) if (backend == "nccl" and device is not None) else torch.device("cpu")
+    mine = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().tolist()) for p in parts)
+
+
+def init_engine_comm(engine, rank: int, world: int, p2p: bool = True):
+    """Give ``engine`` a communicator spanning the torch.distributed world: NCCL for the
+    one-off collectives, and (``p2p``) peer-mapped exchange buffers so that the Lloyd step
+    kernel completes the K x 4 partial sums itself over NVLink."""
+    import torch
+    import torch.distributed as dist
+
     from .engine import Engine
 
     if world == 1:
@@ -52,3 +70,13 @@ def init_engine_comm(engine, rank: int, world: int):
         return
     uid = exchange_unique_id(Engine.make_unique_id, rank, world, device=engine.device)
     engine.init_comm(world, rank, uid)
+    if p2p and world <= 8:
+        handles = gather_bytes(engine.p2p_handle(), rank, world, device=engine.device)
+        ok = engine.p2p_open(handles)
+        # all ranks or none: one rank without peer access sends everybody back to NCCL
+        backend = dist.get_backend()
+        dev = torch.device("cuda", engine.device) if backend == "nccl" else torch.device("cpu")
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and ok:
+            engine.init_comm(world, rank, exchange_unique_id(Engine.make_unique_id, rank, world, device=engine.device))

@@ -62,6 +62,7 @@ class Engine:
         self.device = int(device)
         self.n_ranks = 1
         self.rank = 0
+        self.p2p = False
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
@@ -108,6 +109,20 @@ class Engine:
             buf = (c_ubyte * C.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._check(self._lib.mdkm_comm_init(self._h, int(n_ranks), int(rank), buf))
         self.n_ranks, self.rank = int(n_ranks), int(rank)
+
+    def p2p_handle(self) -> bytes:
+        """CUDA IPC handle of this rank's partial-sum exchange buffer (64 bytes)."""
+        buf = (c_ubyte * C.IPC_HANDLE_BYTES)()
+        self._check(self._lib.mdkm_comm_p2p_handle(self._h, buf))
+        return bytes(buf)
+
+    def p2p_open(self, handles: bytes) -> bool:
+        """Map every rank's exchange buffer (handles in rank order).  False: NCCL stays in use."""
+        assert len(handles) == C.IPC_HANDLE_BYTES * self.n_ranks
+        buf = (c_ubyte * len(handles)).from_buffer_copy(handles)
+        rc = self._lib.mdkm_comm_p2p_open(self._h, buf)
+        self.p2p = rc == C.MDKM_OK
+        return self.p2p
 
     @staticmethod
     def make_unique_id() -> bytes:

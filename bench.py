@@ -315,7 +315,9 @@ def run_mine(args):
             "config": {"workload": workload_name(args.config, world), "points_total": n_total,
                        "iters_per_step": n_iter_sum / args.steps, "l2_policy": "inputs_exceed_l2 "
                        f"({n_local * 12 / 1e6:.0f} MB of xyz per GPU vs 126 MB L2)",
-                       "exchange": "ncclAllReduce of K*4+8 int64 per iteration" if world > 1 else "none"},
+                       "exchange": ("none" if world == 1 else
+                                    "in-kernel NVLink peer exchange of K*4+8 int64 per iteration (CUDA IPC), no NCCL"
+                                    if eng.p2p else "ncclAllReduce of K*4+8 int64 per iteration")},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches,
         }

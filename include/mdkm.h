@@ -45,6 +45,7 @@ enum { MDKM_HM_F32 = 0, MDKM_HM_I16 = 1 };      /* height raster element type */
 enum { MDKM_POINTS_AOS = 0, MDKM_POINTS_SOA = 1 }; /* xyzxyz... or x[n] y[n] z[n] */
 
 #define MDKM_NCCL_UNIQUE_ID_BYTES 128
+#define MDKM_IPC_HANDLE_BYTES 64
 
 /* Library / build identification ("mdkm <ver> sm_100a"). */
 const char* mdkm_version(void);
@@ -61,6 +62,16 @@ const char* mdkm_last_error(const mdkm_handle* h);
 int mdkm_comm_unique_id(unsigned char out[MDKM_NCCL_UNIQUE_ID_BYTES]);
 int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank,
                    const unsigned char id[MDKM_NCCL_UNIQUE_ID_BYTES]);
+
+/* Optional, after mdkm_comm_init on every rank (one process per GPU, one node): let the Lloyd
+ * step kernel exchange the K x 4 partial sums itself, by stores into peer memory over
+ * NVLink, instead of an ncclAllReduce between two kernels.  Each rank exports a CUDA IPC
+ * handle of its exchange buffer (mdkm_comm_p2p_handle), the caller gathers the 64-byte
+ * handles of all ranks in rank order (the Python host uses torch.distributed) and hands the
+ * n_ranks * 64 bytes to mdkm_comm_p2p_open.  If the open fails (no peer access) the call
+ * returns MDKM_ERR_NCCL and the NCCL path stays in use.  Collective: all ranks or none. */
+int mdkm_comm_p2p_handle(mdkm_handle* h, unsigned char out[MDKM_IPC_HANDLE_BYTES]);
+int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles);
 
 /* ---- K1: unprojection ----------------------------------------------------------------
  * Replaces members/rafael/disparity/plugin.py:148 (h = -disp/16), :151-152 (validity:
