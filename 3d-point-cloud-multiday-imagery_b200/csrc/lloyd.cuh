@@ -195,36 +195,6 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
 
 
 
-struct StepParams {
-  const float* pts;           // blocked cloud (common.cuh)
-  long long n;
-  void* labels;               // uint8 (k <= 256) or uint16, capacity = whole groups
-  const unsigned char* table; // centroid table (see common.cuh)
-  unsigned long long* acc;    // [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed
-  DevStatus* st;
-  FrameF f;
-  int k, kpad;
-  int ignore_status;          // 1: test hook (run even when done/paused)
-  int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
-                              //    (NVLink, no host, no NCCL) and runs the centroid update
-  UpdateParams upd;
-  PeerXchg px;
-};
-
-struct FinalParams {
-  const float* pts;
-  long long n;
-  const void* labels;         // stored labels of the last step
-  int* labels_out;            // int32[n] or nullptr
-  const unsigned char* table;
-  double* partials;           // [gridDim.x] inertia partials
-  unsigned int* ticket;
-  DevStatus* st;
-  FrameF f;
-  int k, kpad;
-  int force_assign;           // 1: always recompute labels (predict / test hook)
-};
-
 // exact centroid row through the read-only path (two 16 B loads)
 __device__ __forceinline__ double4 ld_c64(const double4* p) {
   const double2 a = __ldg(reinterpret_cast<const double2*>(p));
@@ -240,6 +210,251 @@ __device__ __forceinline__ float min_gap_over_box(const float4 row, const float4
   const float ax = row.x - ref.x, ay = row.y - ref.y, az = row.z - ref.z, aw = row.w - ref.w;
   return aw + fminf(ax * bx0, ax * bx1) + fminf(ay * by0, ay * by1) + fminf(az * bz0, az * bz1);
 }
+
+struct StepParams {
+  const float* pts;           // blocked cloud (common.cuh)
+  long long n;
+  void* labels;               // uint8 (k <= 256) or uint16, capacity = whole groups
+  const unsigned char* table; // centroid table (see common.cuh)
+  unsigned long long* acc;    // [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed
+  DevStatus* st;
+  FrameF f;
+  int k, kpad;
+  int ignore_status;          // 1: test hook (run even when done/paused)
+  int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
+                              //    (NVLink, no host, no NCCL) and runs the centroid update
+  const int* worklist;        // groups the classification pass could not settle (nullptr: all groups)
+  int* work_count;            // number of entries; cleared by the fused tail
+  int* glabel;                // per group: its label when all its points share one, else -1
+  UpdateParams upd;
+  PeerXchg px;
+};
+
+// ---------------------------------------------------------------------------------------
+// Group summaries.  A group's bounding box and fixed-point coordinate sums never change while
+// the cloud and its frame stay the same, so they are computed once (48 B per 128 points).
+// With them a whole group can be settled WITHOUT touching its points: if one centroid beats
+// every other one over the whole box (the same conservative linear-gap test assign_group
+// uses), all 128 points take that label and the cached sums are added to its accumulator.
+// On raster-ordered clouds that covers most groups; only the rest (a cluster boundary crosses
+// them) are streamed through the per-point kernel.  Results are identical to brute force.
+// ---------------------------------------------------------------------------------------
+struct __align__(16) GroupSummary {
+  float lo[3], hi[3];  // box of the centred FP32 coordinates
+  int q[3];            // sum of the fixed-point coordinates of the group's points
+  int n;               // points in the group (128 except the cloud's tail)
+  int pad[2];
+};
+
+__global__ void __launch_bounds__(kThreads) group_summary_kernel(const float* pts, long long n, FrameF f,
+                                                                 GroupSummary* out) {
+  const int lane = threadIdx.x & 31;
+  const long long n_groups = (n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < n_groups; g += stride) {
+    const float* blk = pts + g * kBlockFloats + lane * 4;
+    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
+    const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w}, zs[4] = {vz.x, vz.y, vz.z, vz.w};
+    float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+    int q[3] = {0, 0, 0};
+    int cnt = 0;
+    const long long i0 = g * kGroup + lane * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // the unused tail of the last block is zero-filled and belongs to the box, exactly as
+      // the per-point kernel sees it; it does not belong to the sums
+      const float xc = xs[e] - f.ox, yc = ys[e] - f.oy, zc = zs[e] - f.oz;
+      lo[0] = fminf(lo[0], xc); hi[0] = fmaxf(hi[0], xc);
+      lo[1] = fminf(lo[1], yc); hi[1] = fmaxf(hi[1], yc);
+      lo[2] = fminf(lo[2], zc); hi[2] = fmaxf(hi[2], zc);
+      if (i0 + e < n) {
+        q[0] += (int)(__float_as_uint(fmaf(xc, f.sx, kMagic)) - kMagicBits);
+        q[1] += (int)(__float_as_uint(fmaf(yc, f.sy, kMagic)) - kMagicBits);
+        q[2] += (int)(__float_as_uint(fmaf(zc, f.sz, kMagic)) - kMagicBits);
+        ++cnt;
+      }
+    }
+    GroupSummary gs;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      gs.lo[d] = redux_min_f32(lo[d]);
+      gs.hi[d] = redux_max_f32(hi[d]);
+      gs.q[d] = __reduce_add_sync(0xffffffffu, q[d]);
+    }
+    gs.n = __reduce_add_sync(0xffffffffu, cnt);
+    gs.pad[0] = gs.pad[1] = 0;
+    if (lane == 0) out[g] = gs;
+  }
+}
+
+struct ClassifyParams {
+  const GroupSummary* gsum;
+  long long n;                // points on this rank
+  void* labels;               // uint8 / uint16 per point, capacity whole groups
+  int* glabel;                // [n_groups]
+  int* worklist;              // [n_groups]
+  int* work_count;
+  const unsigned char* table;
+  unsigned long long* acc;
+  const DevStatus* st;
+  int k, kpad;
+  int ignore_status;
+};
+
+// One THREAD per group.  ref = the group's label of the previous iteration when it had one
+// (it usually still wins), else the centroid nearest to the box centre.
+template <typename LabT>
+__global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const ClassifyParams p) {
+  if (!p.ignore_status && (p.st->done | p.st->paused)) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* s_fast = reinterpret_cast<float4*>(smem_raw);
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_fast + p.kpad);
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ unsigned int s_changed;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    s_changed = 0;
+  }
+  for (int i = tid; i < p.kpad * 4; i += kThreads) s_acc[i] = 0ull;
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
+    tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+  }
+  const float margin = 4.0f * p.st->thresh;
+  const bool first_iter = p.st->first != 0;
+  LabT* labels = reinterpret_cast<LabT*>(p.labels);
+  const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
+  mbar_wait(&s_bar, 0);
+
+  unsigned int n_chg = 0;
+  const int span = (int)gridDim.x * kThreads;
+  for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // warp-uniform trip count
+    const int g = base + tid;
+    const bool valid = g < n_groups;
+    int label = -1;  // settled label, or -1: needs the per-point kernel
+    int prev = -1;
+    GroupSummary gs;
+    if (valid) {
+      const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
+      const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+      gs.lo[0] = a.x; gs.lo[1] = a.y; gs.lo[2] = a.z; gs.hi[0] = a.w; gs.hi[1] = b.x; gs.hi[2] = b.y;
+      gs.q[0] = __float_as_int(b.z); gs.q[1] = __float_as_int(b.w); gs.q[2] = __float_as_int(c.x);
+      gs.n = __float_as_int(c.y);
+      prev = first_iter ? -1 : p.glabel[g];
+      if (gs.n == kGroup) {
+        const float mx = 0.5f * (gs.lo[0] + gs.hi[0]), my = 0.5f * (gs.lo[1] + gs.hi[1]),
+                    mz = 0.5f * (gs.lo[2] + gs.hi[2]);
+        int ref = prev;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2 && label < 0; ++attempt) {
+          if (ref < 0) {  // nearest centroid to the box centre, lowest index on ties
+            float dmin = __int_as_float(0x7f800000);
+            ref = 0;
+            for (int j = 0; j < p.k; ++j) {
+              const float4 r = s_fast[j];
+              const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
+              if (d < dmin) { dmin = d; ref = j; }
+            }
+          }
+          const float4 rr = s_fast[ref];
+          int ncand = 0;
+          for (int j = 0; j < p.k; ++j) {
+            const float gap = min_gap_over_box(s_fast[j], rr, gs.lo[0], gs.hi[0], gs.lo[1], gs.hi[1], gs.lo[2], gs.hi[2]);
+            ncand += (gap <= margin) ? 1 : 0;
+          }
+          if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
+          else if (attempt == 0 && prev >= 0) ref = -1;  // the old owner lost ground: try the nearest
+          else break;
+        }
+      }
+    }
+    // ---- settled groups: labels / changed count / cached sums -------------------------
+    if (label >= 0) {
+      if (first_iter || prev != label) {
+        unsigned int changed = kGroup;
+        uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)g * kGroup);
+        constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;
+        if (!first_iter && prev < 0) {  // was mixed: compare with the stored per-point labels
+          changed = 0;
+#pragma unroll
+          for (int v = 0; v < kVec; ++v) {
+            const uint4 o = lp[v];
+            const unsigned int w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (sizeof(LabT) == 1) {
+                changed += 4u - (unsigned int)__popc(__vcmpeq4(w[t], (unsigned int)label * 0x01010101u)) / 8u;
+              } else {
+                changed += 2u - (unsigned int)__popc(__vcmpeq2(w[t], (unsigned int)label * 0x00010001u)) / 16u;
+              }
+            }
+          }
+        }
+        n_chg += changed;
+        const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
+#pragma unroll
+        for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
+        p.glabel[g] = label;
+      }
+    }
+    // cached sums, one round per distinct label in the warp (usually one)
+    unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
+    while (todo) {
+      const int L = __shfl_sync(0xffffffffu, label, __ffs(todo) - 1);
+      const bool hit = label == L;
+      long long sum[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        // 32 groups x 2^29 overflows 32 bits: reduce the two halves of q separately
+        const int hi = __reduce_add_sync(0xffffffffu, hit ? (gs.q[d] >> 15) : 0);
+        const int lo = __reduce_add_sync(0xffffffffu, hit ? (gs.q[d] & 0x7fff) : 0);
+        sum[d] = ((long long)hi << 15) + (long long)lo;
+      }
+      const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) {
+        atomicAdd(&s_acc[L * 4 + 0], (unsigned long long)sum[0]);
+        atomicAdd(&s_acc[L * 4 + 1], (unsigned long long)sum[1]);
+        atomicAdd(&s_acc[L * 4 + 2], (unsigned long long)sum[2]);
+        atomicAdd(&s_acc[L * 4 + 3], (unsigned long long)__popc(hits) * kGroup);
+      }
+      todo &= ~hits;
+    }
+    // ---- the rest goes to the per-point kernel --------------------------------------------
+    const unsigned int heavy = __ballot_sync(0xffffffffu, valid && label < 0);
+    if (heavy) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(p.work_count, __popc(heavy));
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (valid && label < 0) p.worklist[slot + __popc(heavy & ((1u << lane) - 1u))] = g;
+    }
+  }
+  n_chg = __reduce_add_sync(0xffffffffu, n_chg);
+  if (lane == 0 && n_chg) atomicAdd(&s_changed, n_chg);
+  __syncthreads();
+  for (int i = tid; i < p.kpad * 4; i += kThreads) {
+    const unsigned long long v = s_acc[i];
+    if (v) atomicAdd(&p.acc[i], v);
+  }
+  if (tid == 0 && s_changed) atomicAdd(&p.acc[p.kpad * 4 + 0], (unsigned long long)s_changed);
+}
+
+struct FinalParams {
+  const float* pts;
+  long long n;
+  const void* labels;         // stored labels of the last step
+  int* labels_out;            // int32[n] or nullptr
+  const unsigned char* table;
+  double* partials;           // [gridDim.x] inertia partials
+  unsigned int* ticket;
+  DevStatus* st;
+  FrameF f;
+  int k, kpad;
+  int force_assign;           // 1: always recompute labels (predict / test hook)
+};
 
 // ---------------------------------------------------------------------------------------
 // Assignment of one warp-group.  xc/yc/zc: centred FP32 coordinates of this lane's 4 points;
@@ -562,10 +777,13 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
   // each warp owns a CONTIGUOUS range of groups: consecutive groups are neighbours in the
   // raster, so label runs are long and the register accumulators below rarely flush
-  const int per_warp = (n_groups + (int)gridDim.x * kWarps - 1) / ((int)gridDim.x * kWarps);
+  // (with a worklist the "groups" below are positions in the list)
+  const int n_items = p.worklist ? *p.work_count : n_groups;
+  const int per_warp = (n_items + (int)gridDim.x * kWarps - 1) / ((int)gridDim.x * kWarps);
   const int g0 = ((int)blockIdx.x * kWarps + warp) * per_warp;
-  const int g_end = min(n_groups, g0 + per_warp);
+  const int g_end = min(n_items, g0 + per_warp);
   constexpr int stride = 1;
+  const int* __restrict__ wl = p.worklist;
   const uint32_t ring_a = smem_u32(s_ring) + warp * (kStages * kStageB);
   const uint32_t gbar_a = smem_u32(s_gbar) + warp * (kStages * 8);
   const float* pts = p.pts;
@@ -581,11 +799,16 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       tma_load_1d_a(dst + kBlockFloats * 4, labels + (size_t)gf * kGroup, kLabB, bar);
     }
   };
-#pragma unroll
-  for (int s = 0; s < kStages; ++s) {
-    if (g_fetch < g_end) issue(s, g_fetch);
-    g_fetch += stride;
-  }
+  // group index of the three stages in flight (warp-uniform registers)
+  int gq0 = 0, gq1 = 0, gq2 = 0;
+  static_assert(kStages == 3, "the group-index queue below is written for three stages");
+  if (g_fetch < g_end) { gq0 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(0, gq0); }
+  ++g_fetch;
+  if (g_fetch < g_end) { gq1 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(1, gq1); }
+  ++g_fetch;
+  if (g_fetch < g_end) { gq2 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(2, gq2); }
+  ++g_fetch;
+  int g_pref = (wl && g_fetch < g_end) ? __ldg(wl + g_fetch) : g_fetch;  // list entry of the next fetch
   mbar_wait(&s_bar, 0);
 
   // run accumulator: while consecutive groups of this warp carry one label, every lane just
@@ -610,7 +833,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   int stage = 0;
   uint32_t parity = 0;
 
-  for (int g = g0; g < g_end; g += stride) {
+  for (int it = g0; it < g_end; it += stride) {
+    const int g = gq0;
     const uint32_t st_a = ring_a + stage * kStageB + lane * 16;
     mbar_wait_a(gbar_a + stage * 8, parity);
     const float4 vx = lds_f4(st_a);
@@ -629,8 +853,12 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     // every value read from the stage has been consumed: refill it with the group kStages
     // ahead (the reads completed before this point, so the async-proxy write cannot race)
     __syncwarp();
-    if (g_fetch < g_end) issue(stage, g_fetch);
+    gq0 = gq1;
+    gq1 = gq2;
+    gq2 = g_pref;
+    if (g_fetch < g_end) issue(stage, g_pref);
     g_fetch += stride;
+    g_pref = (wl && g_fetch < g_end) ? __ldg(wl + g_fetch) : g_fetch;
     if (++stage == kStages) {
       stage = 0;
       parity ^= 1u;
@@ -667,6 +895,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       l0 = __shfl_sync(0xffffffffu, lab[0], 0);
       uniform = __all_sync(0xffffffffu, (lab[0] == l0) && (lab[1] == l0) && (lab[2] == l0) && (lab[3] == l0));
     }
+    if (p.glabel && lane == 0) p.glabel[g] = uniform ? l0 : -1;
     if (uniform) {
       if (l0 != wlab || run_groups == kRunMax) {  // warp-uniform
         flush_run();
@@ -740,7 +969,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  if (tid == 0) p.st->ticket = 0u;
+  if (tid == 0) {
+    p.st->ticket = 0u;
+    if (p.work_count) *p.work_count = 0;
+  }
   if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
   lloyd_update_body(p.upd);
 }

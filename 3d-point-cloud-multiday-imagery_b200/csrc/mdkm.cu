@@ -71,6 +71,10 @@ struct mdkm_handle {
   DevBuf<double> partials;    // inertia / moments partials
   DevBuf<unsigned int> uscratch;  // tickets, minmax
   DevBuf<unsigned long long> reloc;  // relocation scratch
+  DevBuf<unsigned char> gsum;        // GroupSummary per 128-point group (static per cloud + frame)
+  DevBuf<int> glabel;                // per group: uniform label or -1
+  DevBuf<int> worklist;              // [n_groups] + 1 counter at the end
+  bool summary_ok = false;
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
@@ -332,6 +336,7 @@ int compute_frame(mdkm_handle* h) {
   h->ff.sx = (float)h->fr.scale[0]; h->ff.sy = (float)h->fr.scale[1]; h->ff.sz = (float)h->fr.scale[2];
   h->frame_ok = true;
   h->mean_ok = false;
+  h->summary_ok = false;
   return MDKM_OK;
 }
 
@@ -406,6 +411,9 @@ struct KmBuffers {
   bool wide;     // uint16 labels
   bool priv;     // per-warp accumulator slices in shared memory
   StepKernel step_fn;
+  int classify_grid;
+  size_t classify_smem;
+  long long n_groups;
 };
 
 int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
@@ -438,6 +446,26 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
   OK(ensure(h, h->partials, (size_t)std::max(kb.final_grid, h->sm_count * 8) * 8 + 16));
+  // group summaries + classification pass
+  kb.n_groups = cap / kGroup;
+  kb.classify_smem = (size_t)kb.kpad * (16 + 32);
+  kb.classify_grid = grid_for(h, (kb.n_groups + kThreads - 1) / kThreads, 8);
+  if (kb.wide)
+    CU(cudaFuncSetAttribute(lloyd_classify_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kb.classify_smem));
+  else
+    CU(cudaFuncSetAttribute(lloyd_classify_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kb.classify_smem));
+  OK(ensure(h, h->gsum, (size_t)kb.n_groups * sizeof(GroupSummary)));
+  OK(ensure(h, h->glabel, (size_t)kb.n_groups));
+  OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
+  if (!h->summary_ok) {
+    group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
+        h->pts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
+    ++h->launches;
+    CU(cudaGetLastError());
+    h->summary_ok = true;
+  }
   if (!h->d_status) {
     CU(cudaMalloc(&h->d_status, sizeof(DevStatus)));
     CU(cudaMallocHost(&h->h_status, 2 * sizeof(DevStatus)));
@@ -482,6 +510,23 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
     sp.px = h->px;
     if (h->n_ranks == 1) sp.px.n_ranks = 1;
   }
+  // pass 1: settle whole groups from their summaries; the rest lands in the worklist
+  int* work_count = h->worklist.p + kb.n_groups;
+  ClassifyParams cp{};
+  cp.gsum = reinterpret_cast<const GroupSummary*>(h->gsum.p);
+  cp.n = h->n;
+  cp.labels = h->labels.p;
+  cp.glabel = h->glabel.p;
+  cp.worklist = h->worklist.p;
+  cp.work_count = work_count;
+  cp.table = h->table.p;
+  cp.acc = h->acc.p;
+  cp.st = h->d_status;
+  cp.k = kb.k; cp.kpad = kb.kpad;
+  cp.ignore_status = ignore_status;
+  sp.worklist = h->worklist.p;
+  sp.work_count = work_count;
+  sp.glabel = h->glabel.p;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->prof) {
     while ((int)h->prof_ev.size() < h->prof_used + 2) {
@@ -493,9 +538,17 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
     e1 = h->prof_ev[h->prof_used++];
     CU(cudaEventRecord(e0, h->stream));
   }
+  if (h->n > 0) {
+    if (kb.wide)
+      lloyd_classify_kernel<unsigned short><<<kb.classify_grid, kThreads, kb.classify_smem, h->stream>>>(cp);
+    else
+      lloyd_classify_kernel<unsigned char><<<kb.classify_grid, kThreads, kb.classify_smem, h->stream>>>(cp);
+    ++h->launches;
+  }
   kb.step_fn<<<kb.step_grid, kThreads, kb.step_smem, h->stream>>>(sp);
   ++h->launches;
   CU(cudaGetLastError());
+  if (!fuse_update) CU(cudaMemsetAsync(work_count, 0, 4, h->stream));
   if (h->prof) CU(cudaEventRecord(e1, h->stream));
   return MDKM_OK;
 }
@@ -664,6 +717,7 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->pts);
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
+  release(h->gsum); release(h->glabel); release(h->worklist);
   release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
   release(h->d_seg_off); release(h->sel_hist); release(h->sel_targets);
   release(h->kpp_closest); release(h->kpp_cell); release(h->kpp_blk); release(h->kpp_prefix);
@@ -1082,6 +1136,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
+  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 4, h->stream));
   OK(upload_table(h, kb, init));
 
   // Lloyd loop: batches of iterations are enqueued back to back; the host only looks at the
@@ -1188,6 +1243,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
+  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 4, h->stream));
   OK(upload_table(h, kb, centroids));
   OK(launch_step(h, kb, 1));
   OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));

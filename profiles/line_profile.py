@@ -55,7 +55,7 @@ def main():
         st[key] += int(r[ist])
     tot, stot = sum(ex.values()), sum(st.values())
     srcs = {}
-    for (f, ln), v in ex.most_common(45):
+    for (f, ln), v in (sorted(ex.items()) if os.environ.get("ALL_LINES") else ex.most_common(45)):
         path = None
         for root in ("3d-point-cloud-multiday-imagery_b200/csrc", "."):
             p = os.path.join(root, f)
