@@ -302,8 +302,11 @@ struct ClassifyParams {
   int ignore_status;
 };
 
-// One THREAD per group.  ref = the group's label of the previous iteration when it had one
-// (it usually still wins), else the centroid nearest to the box centre.
+// One THREAD per group.  A group that was settled with label L in the previous iteration is
+// re-tested against L only (one pass over the centroid table); a group that was not settled
+// goes straight to the per-point kernel, which hands it back here (glabel >= 0) as soon as one
+// centroid owns its whole box.  In the first iteration every group is tested against the
+// centroid nearest to its box centre.
 template <typename LabT>
 __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const ClassifyParams p) {
   if (!p.ignore_status && (p.st->done | p.st->paused)) return;
@@ -328,78 +331,58 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
   const bool first_iter = p.st->first != 0;
   LabT* labels = reinterpret_cast<LabT*>(p.labels);
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
+  // the summaries do not depend on the centroids: fetch the first one while the table arrives
+  const int span = (int)gridDim.x * kThreads;
+  int g = (int)blockIdx.x * kThreads + tid;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+  int prev = -1;
+  if (g < n_groups) {
+    const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
+    a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
+    prev = first_iter ? -1 : p.glabel[g];
+  }
   mbar_wait(&s_bar, 0);
 
   unsigned int n_chg = 0;
-  const int span = (int)gridDim.x * kThreads;
   for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // warp-uniform trip count
-    const int g = base + tid;
     const bool valid = g < n_groups;
     int label = -1;  // settled label, or -1: needs the per-point kernel
-    int prev = -1;
-    GroupSummary gs;
-    if (valid) {
-      const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
-      const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-      gs.lo[0] = a.x; gs.lo[1] = a.y; gs.lo[2] = a.z; gs.hi[0] = a.w; gs.hi[1] = b.x; gs.hi[2] = b.y;
-      gs.q[0] = __float_as_int(b.z); gs.q[1] = __float_as_int(b.w); gs.q[2] = __float_as_int(c.x);
-      gs.n = __float_as_int(c.y);
-      prev = first_iter ? -1 : p.glabel[g];
-      if (gs.n == kGroup) {
-        const float mx = 0.5f * (gs.lo[0] + gs.hi[0]), my = 0.5f * (gs.lo[1] + gs.hi[1]),
-                    mz = 0.5f * (gs.lo[2] + gs.hi[2]);
-        int ref = prev;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2 && label < 0; ++attempt) {
-          if (ref < 0) {  // nearest centroid to the box centre, lowest index on ties
-            float dmin = __int_as_float(0x7f800000);
-            ref = 0;
-            for (int j = 0; j < p.k; ++j) {
-              const float4 r = s_fast[j];
-              const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
-              if (d < dmin) { dmin = d; ref = j; }
-            }
-          }
-          const float4 rr = s_fast[ref];
-          int ncand = 0;
-          for (int j = 0; j < p.k; ++j) {
-            const float gap = min_gap_over_box(s_fast[j], rr, gs.lo[0], gs.hi[0], gs.lo[1], gs.hi[1], gs.lo[2], gs.hi[2]);
-            ncand += (gap <= margin) ? 1 : 0;
-          }
-          if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
-          else if (attempt == 0 && prev >= 0) ref = -1;  // the old owner lost ground: try the nearest
-          else break;
+    int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
+    if (valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
+      const float lo0 = a.x, lo1 = a.y, lo2 = a.z, hi0 = a.w, hi1 = b.x, hi2 = b.y;
+      int ref = prev;
+      if (ref < 0) {  // nearest centroid to the box centre, lowest index on ties
+        const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
+        float dmin = __int_as_float(0x7f800000);
+        ref = 0;
+        for (int j = 0; j < p.k; ++j) {
+          const float4 r = s_fast[j];
+          const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
+          if (d < dmin) { dmin = d; ref = j; }
         }
       }
+      const float4 rr = s_fast[ref];
+      int ncand = 0;
+      for (int j = 0; j < p.k; ++j)
+        ncand += (min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) ? 1 : 0;
+      if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
     }
-    // ---- settled groups: labels / changed count / cached sums -------------------------
-    if (label >= 0) {
-      if (first_iter || prev != label) {
-        unsigned int changed = kGroup;
-        uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)g * kGroup);
-        constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;
-        if (!first_iter && prev < 0) {  // was mixed: compare with the stored per-point labels
-          changed = 0;
+    if (label >= 0 && first_iter) {  // later iterations: label == prev, nothing to write
+      n_chg += kGroup;
+      uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)g * kGroup);
+      constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;
+      const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
 #pragma unroll
-          for (int v = 0; v < kVec; ++v) {
-            const uint4 o = lp[v];
-            const unsigned int w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              if (sizeof(LabT) == 1) {
-                changed += 4u - (unsigned int)__popc(__vcmpeq4(w[t], (unsigned int)label * 0x01010101u)) / 8u;
-              } else {
-                changed += 2u - (unsigned int)__popc(__vcmpeq2(w[t], (unsigned int)label * 0x00010001u)) / 16u;
-              }
-            }
-          }
-        }
-        n_chg += changed;
-        const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
-#pragma unroll
-        for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
-        p.glabel[g] = label;
-      }
+      for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
+      p.glabel[g] = label;
+    }
+    const int g_now = g;
+    // next group of this thread: its summary loads overlap the bookkeeping below
+    g += span;
+    if (g < n_groups) {
+      const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
+      a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
+      prev = first_iter ? -1 : p.glabel[g];
     }
     // cached sums, one round per distinct label in the warp (usually one)
     unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
@@ -410,8 +393,8 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         // 32 groups x 2^29 overflows 32 bits: reduce the two halves of q separately
-        const int hi = __reduce_add_sync(0xffffffffu, hit ? (gs.q[d] >> 15) : 0);
-        const int lo = __reduce_add_sync(0xffffffffu, hit ? (gs.q[d] & 0x7fff) : 0);
+        const int hi = __reduce_add_sync(0xffffffffu, hit ? (q[d] >> 15) : 0);
+        const int lo = __reduce_add_sync(0xffffffffu, hit ? (q[d] & 0x7fff) : 0);
         sum[d] = ((long long)hi << 15) + (long long)lo;
       }
       const unsigned int hits = __ballot_sync(0xffffffffu, hit);
@@ -429,7 +412,7 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
       int slot = 0;
       if (lane == 0) slot = atomicAdd(p.work_count, __popc(heavy));
       slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (valid && label < 0) p.worklist[slot + __popc(heavy & ((1u << lane) - 1u))] = g;
+      if (valid && label < 0) p.worklist[slot + __popc(heavy & ((1u << lane) - 1u))] = g_now;
     }
   }
   n_chg = __reduce_add_sync(0xffffffffu, n_chg);
@@ -895,7 +878,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       l0 = __shfl_sync(0xffffffffu, lab[0], 0);
       uniform = __all_sync(0xffffffffu, (lab[0] == l0) && (lab[1] == l0) && (lab[2] == l0) && (lab[3] == l0));
     }
-    if (p.glabel && lane == 0) p.glabel[g] = uniform ? l0 : -1;
+    // settled (one centroid owns the whole box): the classification pass takes over from here
+    if (p.glabel && lane == 0) p.glabel[g] = (full && ncand <= 1) ? lab[0] : -1;
     if (uniform) {
       if (l0 != wlab || run_groups == kRunMax) {  // warp-uniform
         flush_run();
