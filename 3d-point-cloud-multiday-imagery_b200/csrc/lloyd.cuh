@@ -567,27 +567,53 @@ __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&
     }
   }
   // FP64 refine of the points the FP32 pass cannot decide (rare; see file header), from the
-  // ORIGINAL coordinates, so no FP32 rounding of x - origin enters.
+  // ORIGINAL coordinates, so no FP32 rounding of x - origin enters.  Only the group's
+  // candidates can be the exact nearest (see above), so only they are re-evaluated, and the
+  // warp walks them together: the cost does not grow with k.
+  bool ambig[4];
   bool amb = false;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) amb |= !(second[e] - best[e] > thresh);
-  if (amb) {
+  for (int e = 0; e < 4; ++e) {
+    ambig[e] = !(second[e] - best[e] > thresh);
+    amb |= ambig[e];
+  }
+  if (__any_sync(0xffffffffu, amb)) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (!(second[e] - best[e] > thresh)) {
-        const double X = (double)orig_x[e] - (double)f.ox;
-        const double Y = (double)orig_y[e] - (double)f.oy;
-        const double Z = (double)orig_z[e] - (double)f.oz;
-        double bd = 1.0 / 0.0;
-        int bi = 0;
-        for (int j = 0; j < k; ++j) {
-          const double4 c = ld_c64(&c64[j]);
-          const double d = fma(-2.0, fma(X, c.x, fma(Y, c.y, Z * c.z)), c.w);
-          if (d < bd) {
-            bd = d;
-            bi = j;
+      if (!__any_sync(0xffffffffu, ambig[e])) continue;  // warp-uniform
+      const double X = (double)orig_x[e] - (double)f.ox;
+      const double Y = (double)orig_y[e] - (double)f.oy;
+      const double Z = (double)orig_z[e] - (double)f.oz;
+      double bd = 1.0 / 0.0;
+      int bi = 0;
+      auto eval64 = [&](int j) {  // ascending j, strict '<': lowest index on exact ties
+        const double4 c = ld_c64(&c64[j]);
+        const double d = fma(-2.0, fma(X, c.x, fma(Y, c.y, Z * c.z)), c.w);
+        if (d < bd) {
+          bd = d;
+          bi = j;
+        }
+      };
+      if (kChunks > 0) {
+#pragma unroll
+        for (int c = 0; c < kM; ++c) {
+          unsigned int m = masks[c];
+          while (m) {
+            eval64(c * 32 + __ffs(m) - 1);
+            m &= m - 1;
           }
         }
+      } else {
+        for (int base = 0; base < kp32; base += 32) {
+          const float gap = min_gap_over_box(s_fast[base + lane], ref, bx0, bx1, by0, by1, bz0, bz1);
+          unsigned int m = __ballot_sync(0xffffffffu, gap <= margin);
+          while (m) {
+            eval64(base + __ffs(m) - 1);
+            m &= m - 1;
+          }
+        }
+      }
+      if (ambig[e]) {
         lab[e] = bi;
         ++n_refined;
       }
