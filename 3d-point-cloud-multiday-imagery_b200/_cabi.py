@@ -46,6 +46,7 @@ SIGNATURES = {
     "mdkm_bind_cloud_output": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
     "mdkm_set_points": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int]),
     "mdkm_num_points": (c_int64, [c_void_p]),
+    "mdkm_num_points_global": (c_int64, [c_void_p]),
     "mdkm_gather_points": (c_int, [c_void_p, POINTER(c_int64), c_int, POINTER(c_float)]),
     "mdkm_get_cloud": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "mdkm_get_cloud_async": (c_int, [c_void_p, c_void_p, c_int, c_int]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "mdkm_fit_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_double)]),
     "mdkm_lloyd_step": (c_int, [c_void_p, c_int, POINTER(c_double), c_void_p, c_int, POINTER(c_double),
                                 POINTER(c_int64)]),
+    "mdkm_predict": (c_int, [c_void_p, c_int, POINTER(c_double), c_void_p, c_int, POINTER(c_double)]),
     "mdkm_kmeans_plusplus": (c_int, [c_void_p, c_int, c_int64, POINTER(c_double), c_int,
                                      POINTER(c_double), POINTER(c_int64)]),
     "mdkm_profile_enable": (c_int, [c_void_p, c_int]),

@@ -102,7 +102,7 @@ def _random_seeds(rs, n: int, k: int) -> np.ndarray:
 
 def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True):
     """KMeans.fit driver (sklearn/_kmeans.py:1436-1563): init, n_init restarts, best inertia."""
-    n = eng.n_points
+    n = eng.n_points_global  # with a communicator: every rank draws the same seeds
     k = int(n_clusters)
     if k < 1:
         raise ValueError("n_clusters must be >= 1")
@@ -128,11 +128,15 @@ def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_
         else:
             centers0, _ = eng.kmeans_plusplus(k, rs)
         r = eng.fit(centers0, max_iter=max_iter, tol=tol, want_labels=want_labels)
-        if best is None or (
-            r["inertia"] < best["inertia"]
-            and not (want_labels and _is_same_clustering(r["labels"], best["labels"], k))
-        ):
+        # sklearn/_kmeans.py:1534-1541.  With a communicator the labels are this rank's shard
+        # only, so the "same clustering up to a permutation" escape is skipped there: the
+        # decision must be identical on every rank, and the (global) inertia is.
+        same = (want_labels and eng.n_ranks == 1 and best is not None
+                and _is_same_clustering(r["labels"], best["labels"], k))
+        if best is None or (r["inertia"] < best["inertia"] and not same):
             best = r
+            if int(n_init) > 1 and r["labels"] is not None:
+                best = dict(r, labels=r["labels"].copy())  # result buffers are reused by the next run
     return best
 
 

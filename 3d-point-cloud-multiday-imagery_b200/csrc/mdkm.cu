@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,6 +56,8 @@ struct mdkm_handle {
   DevBuf<float> pts;  // blocked cloud (common.cuh), capacity = whole 128-point blocks
   long long n = 0;        // points on this rank
   long long n_total = 0;  // points over all ranks
+  long long rank_offset = 0;            // global index of this rank's first point
+  std::vector<long long> shard_sizes;   // points per rank (valid with the frame)
   bool have_points = false;
   bool frame_ok = false;
   Frame fr{};
@@ -285,7 +288,7 @@ int allreduce(mdkm_handle* h, void* buf, size_t count, int dtype, int op) {
 // per-dimension min and max.
 int compute_frame(mdkm_handle* h) {
   OK(ensure(h, h->uscratch, 16));
-  OK(ensure(h, h->dscratch, 64));
+  OK(ensure(h, h->dscratch, 64 + (size_t)h->n_ranks));
   unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   if (h->n > 0) {
@@ -300,18 +303,26 @@ int compute_frame(mdkm_handle* h) {
   float mm[6];
   for (int i = 0; i < 6; ++i) mm[i] = ord2f(ord[i]);
   long long ntot = h->n;
+  h->shard_sizes.assign((size_t)h->n_ranks, 0);
+  h->shard_sizes[h->rank] = h->n;
+  h->rank_offset = 0;
   if (h->n_ranks > 1) {
-    // exchange min / max / count (tiny, once per cloud)
+    // exchange min / max / shard sizes (tiny, once per cloud)
     float* dmm = reinterpret_cast<float*>(h->dscratch.p);
     long long* dn = reinterpret_cast<long long*>(h->dscratch.p + 8);
     CU(cudaMemcpyAsync(dmm, mm, sizeof(mm), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(dn, &ntot, 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dn, h->shard_sizes.data(), 8 * (size_t)h->n_ranks, cudaMemcpyHostToDevice, h->stream));
     OK(allreduce(h, dmm, 3, kNcclFloat32, kNcclMin));
     OK(allreduce(h, dmm + 3, 3, kNcclFloat32, kNcclMax));
-    OK(allreduce(h, dn, 1, kNcclInt64, kNcclSum));
+    OK(allreduce(h, dn, h->n_ranks, kNcclInt64, kNcclSum));
     OK(small_d2h(h, mm, dmm, sizeof(mm)));
-    OK(small_d2h(h, &ntot, dn, 8));
+    OK(small_d2h(h, h->shard_sizes.data(), dn, 8 * (size_t)h->n_ranks));
     OK(sync_small(h));
+    ntot = 0;
+    for (int r = 0; r < h->n_ranks; ++r) {
+      if (r == h->rank) h->rank_offset = ntot;
+      ntot += h->shard_sizes[r];
+    }
   }
   h->n_total = ntot;
   for (int d = 0; d < 3; ++d) {
@@ -595,18 +606,7 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
   //          [6] taken count, [8 .. 8+kMaxK) taken global indices
   OK(ensure(h, h->reloc, 8 + 2 * (size_t)kMaxK));
   CU(cudaMemsetAsync(h->reloc.p, 0, (8 + 2 * (size_t)kMaxK) * 8, h->stream));
-  long long rank_offset = 0;
-  if (h->n_ranks > 1) {
-    // global index of this rank's first point: exclusive prefix of the shard sizes
-    std::vector<long long> sizes(h->n_ranks, 0);
-    sizes[h->rank] = h->n;
-    long long* d = reinterpret_cast<long long*>(h->dscratch.p);
-    CU(cudaMemcpyAsync(d, sizes.data(), sizeof(long long) * h->n_ranks, cudaMemcpyHostToDevice, h->stream));
-    OK(allreduce(h, d, h->n_ranks, kNcclInt64, kNcclSum));
-    OK(small_d2h(h, sizes.data(), d, sizeof(long long) * h->n_ranks));
-    OK(sync_small(h));
-    for (int r = 0; r < h->rank; ++r) rank_offset += sizes[r];
-  }
+  const long long rank_offset = h->rank_offset;  // global index of this rank's first point
   RelocParams rp{};
   rp.pts = h->pts.p; rp.n = h->n;
   rp.labels = h->labels.p; rp.wide = kb.wide ? 1 : 0;
@@ -844,21 +844,31 @@ int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int
 
 int64_t mdkm_num_points(const mdkm_handle* h) { return h ? h->n : -1; }
 
+int64_t mdkm_num_points_global(mdkm_handle* h) {
+  if (!h || !h->have_points) return -1;
+  if (!h->frame_ok && compute_frame(h) != MDKM_OK) return -1;
+  return h->n_total;
+}
+
 int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz) {
   if (!h || !idx || !out_xyz || m < 0) return fail(h, MDKM_ERR_INVALID, "bad gather argument");
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
   CU(cudaSetDevice(h->device));
+  if (!h->frame_ok) OK(compute_frame(h));
   for (int i = 0; i < m; ++i)
-    if (idx[i] < 0 || idx[i] >= h->n) return fail(h, MDKM_ERR_INVALID, "gather index %lld out of range", (long long)idx[i]);
+    if (idx[i] < 0 || idx[i] >= h->n_total)
+      return fail(h, MDKM_ERR_INVALID, "gather index %lld out of range", (long long)idx[i]);
   if (m == 0) return MDKM_OK;
   if ((size_t)m * 12 > kMappedBytes / 2) return fail(h, MDKM_ERR_INVALID, "gather of %d points is too large", m);
   OK(ensure(h, h->dscratch, (size_t)m * 3 + 16));
   long long* d_idx = reinterpret_cast<long long*>(h->dscratch.p);
   float* d_out = reinterpret_cast<float*>(h->dscratch.p + m);
   CU(cudaMemcpyAsync(d_idx, idx, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
-  gather_points_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(h->pts.p, d_idx, m, d_out);
+  // indices are global: a rank contributes the points it owns and zeros for the others
+  gather_points_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(h->pts.p, d_idx, m, h->rank_offset, h->n, d_out);
   ++h->launches;
   CU(cudaGetLastError());
+  OK(allreduce(h, d_out, (size_t)m * 3, kNcclFloat32, kNcclSum));
   OK(small_d2h(h, out_xyz, d_out, (size_t)m * 12));
   OK(sync_small(h));
   return MDKM_OK;
@@ -1276,6 +1286,41 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   return MDKM_OK;
 }
 
+int mdkm_predict(mdkm_handle* h, int k, const double* centroids, int32_t* labels_out, int labels_mem,
+                 double* inertia_out) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (!centroids) return fail(h, MDKM_ERR_INVALID, "centroids required");
+  CU(cudaSetDevice(h->device));
+  KmBuffers kb{};
+  OK(prepare_kmeans(h, k, kb));
+  DevStatus st0{};
+  st0.max_iter = 1;
+  st0.k = k;
+  st0.first = 1;
+  st0.epoch = h->epoch_base;
+  h->h_status[0] = st0;
+  CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
+  OK(upload_table(h, kb, centroids));
+  int* labels_dev = nullptr;
+  if (labels_out) {
+    labels_dev = labels_out;
+    if (labels_mem != MDKM_MEM_DEVICE) {
+      OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
+      labels_dev = h->labels32.p;
+    }
+  }
+  OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
+  if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
+  OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
+  if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
+    CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+  OK(sync_small(h));
+  if (inertia_out) *inertia_out = h->h_status[0].inertia;
+  h->stat_refined = (long long)h->h_status[0].n_refined;
+  h->stat_reloc = 0;
+  return MDKM_OK;
+}
+
 int mdkm_num_segments(const mdkm_handle* h) { return h && h->have_points ? (int)h->seg_off.size() - 1 : -1; }
 
 int mdkm_segment_offsets(const mdkm_handle* h, int64_t* out) {
@@ -1383,14 +1428,16 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
                          double* centers_out, int64_t* indices_out) {
   if (!h) return MDKM_ERR_INVALID;
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident");
-  if (h->n_ranks > 1) return fail(h, MDKM_ERR_STATE, "mdkm_kmeans_plusplus is single-rank");
-  if (k < 1 || k > kMaxK || (long long)k > h->n) return fail(h, MDKM_ERR_INVALID, "bad k");
-  if (first_index < 0 || first_index >= h->n) return fail(h, MDKM_ERR_INVALID, "first_index out of range");
+  if (!h->frame_ok) OK(compute_frame(h));  // also counts the points of all ranks
+  if (k < 1 || k > kMaxK || (long long)k > h->n_total) return fail(h, MDKM_ERR_INVALID, "bad k");
+  if (first_index < 0 || first_index >= h->n_total) return fail(h, MDKM_ERR_INVALID, "first_index out of range");
   if (k > 1 && (!rand_vals || n_local_trials < 1 || n_local_trials > kKppMaxTrials))
     return fail(h, MDKM_ERR_INVALID, "rand_vals required and 1 <= n_local_trials <= %d", kKppMaxTrials);
   if (!centers_out) return fail(h, MDKM_ERR_INVALID, "centers_out required");
+  if (h->n_ranks > kMaxRanks) return fail(h, MDKM_ERR_STATE, "at most %d ranks", kMaxRanks);
   CU(cudaSetDevice(h->device));
-  const long long cap = round_up(h->n, kGroup);
+  const bool sharded = h->n_ranks > 1;
+  const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   const long long n_cells = cap / kGroup;
   const long long n_blk = (n_cells + kKppCellsPerBlock - 1) / kKppCellsPerBlock;
   const int T = k > 1 ? n_local_trials : 1;
@@ -1399,10 +1446,10 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
   OK(ensure(h, h->kpp_cell, (size_t)n_cells));
   OK(ensure(h, h->kpp_blk, (size_t)n_blk));
   OK(ensure(h, h->kpp_prefix, (size_t)n_blk));
-  OK(ensure(h, h->kpp_partials, (size_t)grid * kKppMaxTrials));
+  OK(ensure(h, h->kpp_partials, (size_t)grid * kKppMaxTrials + kXWords));
   OK(ensure(h, h->kpp_rand, (size_t)std::max(1, (k - 1) * T)));
   OK(ensure(h, h->kpp_state, sizeof(KppState)));
-  OK(ensure(h, h->dscratch, (size_t)k * 4 + 16));
+  OK(ensure(h, h->dscratch, (size_t)k * 4 + 16 + 2 * kMaxRanks));
   CU(cudaMemsetAsync(h->kpp_state.p, 0, sizeof(KppState), h->stream));
   if (k > 1)
     CU(cudaMemcpyAsync(h->kpp_rand.p, rand_vals, (size_t)(k - 1) * T * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1415,14 +1462,50 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
   kp.indices_out = reinterpret_cast<long long*>(h->dscratch.p + (size_t)k * 3);
   kp.n_trials = T;
   kp.first_index = first_index;
+  kp.n_ranks = h->n_ranks; kp.rank = h->rank;
+  kp.xbuf = h->kpp_partials.p + (size_t)grid * kKppMaxTrials;
+  kp.choose = sharded ? 0 : 1;
+  double* d_pots = reinterpret_cast<double*>(h->kpp_state.p + offsetof(KppState, pots));
+  if (sharded) {
+    // who owns centre 0, and which ranks have points at all
+    double cnt[kMaxRanks] = {};
+    for (int r = 0; r < h->n_ranks; ++r) cnt[r] = (double)h->shard_sizes[r];
+    kp.rank_offset = h->rank_offset;
+    const long long local = first_index - kp.rank_offset;
+    kp.first_index = (local >= 0 && local < h->n) ? local : -1;
+    CU(cudaMemsetAsync(kp.xbuf, 0, kXWords * 8, h->stream));
+    CU(cudaMemcpyAsync(kp.xbuf + kXCnt, cnt, sizeof(cnt), cudaMemcpyHostToDevice, h->stream));
+  }
   KppPotKernel pot_fn = kpp_pot_variant(T);
   // all k rounds are enqueued back to back; nothing returns to the host until the end
   for (int c = 0; c < k; ++c) {
     kp.round = c;
-    if (c > 0) {
+    if (sharded) CU(cudaMemsetAsync(kp.xbuf, 0, kXCnt * 8, h->stream));
+    if (c == 0) {
+      if (sharded) {
+        kpp_first_candidate_kernel<<<1, 32, 0, h->stream>>>(kp);
+        OK(allreduce(h, kp.xbuf + kXCand, 4, kNcclFloat64, kNcclSum));
+        kpp_unpack_candidates_kernel<<<1, 32, 0, h->stream>>>(kp);
+        kpp_choose_kernel<<<1, 32, 0, h->stream>>>(kp);
+        h->launches += 3;
+      }
+    } else {
       kpp_search_kernel<<<1, 1024, 0, h->stream>>>(kp, n_blk);
+      ++h->launches;
+      if (sharded) {
+        OK(allreduce(h, kp.xbuf + kXTot, kMaxRanks, kNcclFloat64, kNcclSum));
+        kpp_search_sharded_kernel<<<1, kKppMaxTrials * 32, 0, h->stream>>>(kp, n_blk);
+        OK(allreduce(h, kp.xbuf + kXCand, (size_t)T * 4, kNcclFloat64, kNcclSum));
+        kpp_unpack_candidates_kernel<<<1, 32, 0, h->stream>>>(kp);
+        h->launches += 2;
+      }
       pot_fn<<<grid, kThreads, 0, h->stream>>>(kp);
-      h->launches += 2;
+      ++h->launches;
+      if (sharded) {
+        OK(allreduce(h, d_pots, T, kNcclFloat64, kNcclSum));
+        kpp_choose_kernel<<<1, 32, 0, h->stream>>>(kp);
+        ++h->launches;
+      }
     }
     if (c == 0 || c < k - 1) {  // the last centre has no later draw to prepare
       kpp_commit_kernel<<<(unsigned int)n_blk, kThreads, 0, h->stream>>>(kp);

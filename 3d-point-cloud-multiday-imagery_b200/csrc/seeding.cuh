@@ -25,6 +25,11 @@ namespace mdkm {
 constexpr int kKppCellsPerBlock = 32;                    // 4096 points per block
 constexpr int kKppBlockPts = kKppCellsPerBlock * kGroup;
 constexpr int kKppMaxTrials = 16;
+// exchange scratch of the sharded variant (doubles): rank totals | candidates | rank point counts
+constexpr int kXTot = 0;
+constexpr int kXCand = kMaxRanks;
+constexpr int kXCnt = kMaxRanks + 4 * kKppMaxTrials;
+constexpr int kXWords = kXCnt + kMaxRanks;
 
 struct KppState {
   double pot;                          // current potential = C[n-1]
@@ -51,7 +56,12 @@ struct KppParams {
   long long* indices_out;  // [k] device
   int n_trials;
   int round;               // index of the centre being chosen (1..k-1); 0 = first centre
-  long long first_index;   // centre 0
+  long long first_index;   // centre 0 (local index; -1: another rank owns it, see st->best_xyz)
+  // multi-rank (points sharded over ranks, one cumulative sum over all of them in rank order)
+  int n_ranks, rank;
+  long long rank_offset;   // global index of this rank's first point
+  double* xbuf;            // exchange scratch, layout kXTot / kXCand / kXCnt
+  int choose;              // pot kernel: 1 = pick the winner in-kernel, 0 = the host reduces first
 };
 
 __device__ __forceinline__ double kpp_dist(float x, float y, float z, double cx, double cy, double cz) {
@@ -66,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) kpp_commit_kernel(const KppParams p)
   __shared__ double s_cell[kKppCellsPerBlock];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double cx, cy, cz;
-  if (p.round == 0) {
+  if (p.round == 0 && p.n_ranks <= 1) {
     const float* q = p.pts + pt_off(p.first_index);
     cx = (double)q[0]; cy = (double)q[kGroup]; cz = (double)q[2 * kGroup];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -115,40 +125,11 @@ __global__ void __launch_bounds__(kThreads) kpp_commit_kernel(const KppParams p)
   }
 }
 
-// Inclusive prefix over the block sums (single CTA, fixed order), the potential, and the
-// search of this round's n_trials draws:  cand = searchsorted(C, rand * pot), clipped to n-1.
-__global__ void __launch_bounds__(1024) kpp_search_kernel(const KppParams p, long long n_blk) {
-  __shared__ double s_part[1024];
-  __shared__ double s_pot;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // each thread owns a contiguous run of blocks; runs are combined in thread order
-  const long long per = (n_blk + 1023) / 1024;
-  const long long b0 = (long long)tid * per, b1 = min(n_blk, b0 + per);
-  double t = 0.0;
-  for (long long b = b0; b < b1; ++b) t += p.blk_sum[b];
-  s_part[tid] = t;
-  __syncthreads();
-  if (tid == 0) {
-    double run = 0.0;
-    for (int i = 0; i < 1024; ++i) {
-      const double v = s_part[i];
-      s_part[i] = run;  // exclusive
-      run += v;
-    }
-    s_pot = run;
-    p.st->pot = run;
-  }
-  __syncthreads();
-  double run = s_part[tid];
-  for (long long b = b0; b < b1; ++b) {
-    run += p.blk_sum[b];
-    p.blk_prefix[b] = run;
-  }
-  __syncthreads();
-  __threadfence_block();
-  if (warp >= p.n_trials) return;
-  // one warp per trial
-  const double r = p.rand_vals[(size_t)(p.round - 1) * p.n_trials + warp] * s_pot;
+// searchsorted(C, r) on this rank's cumulative sum, clipped to the last point; one warp.
+// The candidate goes to the state block (single rank) or, as (global index, x, y, z), to
+// `out` for the exchange between ranks.
+__device__ __forceinline__ void kpp_locate(const KppParams& p, long long n_blk, double r, int trial, int lane,
+                                           double* out) {
   // first block whose inclusive prefix reaches r
   long long lo = 0, hi = n_blk - 1;
   while (lo < hi) {
@@ -186,11 +167,124 @@ __global__ void __launch_bounds__(1024) kpp_search_kernel(const KppParams p, lon
   if (idx > p.n - 1) idx = p.n - 1;  // np.clip(candidate_ids, None, n - 1)
   if (lane == 0) {
     const float* q = p.pts + pt_off(idx);
-    p.st->cand_idx[warp] = idx;
-    p.st->cand_xyz[warp][0] = (double)q[0];
-    p.st->cand_xyz[warp][1] = (double)q[kGroup];
-    p.st->cand_xyz[warp][2] = (double)q[2 * kGroup];
+    if (out) {
+      out[0] = (double)(p.rank_offset + idx);
+      out[1] = (double)q[0];
+      out[2] = (double)q[kGroup];
+      out[3] = (double)q[2 * kGroup];
+    } else {
+      p.st->cand_idx[trial] = idx;
+      p.st->cand_xyz[trial][0] = (double)q[0];
+      p.st->cand_xyz[trial][1] = (double)q[kGroup];
+      p.st->cand_xyz[trial][2] = (double)q[2 * kGroup];
+    }
   }
+}
+
+// Inclusive prefix over the block sums (single CTA, fixed order), the potential, and -- on a
+// single rank -- the search of this round's n_trials draws:
+// cand = searchsorted(C, rand * pot), clipped to n-1.
+__global__ void __launch_bounds__(1024) kpp_search_kernel(const KppParams p, long long n_blk) {
+  __shared__ double s_part[1024];
+  __shared__ double s_pot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // each thread owns a contiguous run of blocks; runs are combined in thread order
+  const long long per = (n_blk + 1023) / 1024;
+  const long long b0 = (long long)tid * per, b1 = min(n_blk, b0 + per);
+  double t = 0.0;
+  for (long long b = b0; b < b1; ++b) t += p.blk_sum[b];
+  s_part[tid] = t;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int i = 0; i < 1024; ++i) {
+      const double v = s_part[i];
+      s_part[i] = run;  // exclusive
+      run += v;
+    }
+    s_pot = run;
+    p.st->pot = run;
+    if (p.n_ranks > 1) p.xbuf[kXTot + p.rank] = run;  // this rank's slot; the others stay zero for the exchange
+  }
+  __syncthreads();
+  double run = s_part[tid];
+  for (long long b = b0; b < b1; ++b) {
+    run += p.blk_sum[b];
+    p.blk_prefix[b] = run;
+  }
+  __syncthreads();
+  if (p.n_ranks > 1) return;  // the draws need every rank's total: kpp_search_sharded_kernel
+  if (warp >= p.n_trials) return;
+  const double r = p.rand_vals[(size_t)(p.round - 1) * p.n_trials + warp] * s_pot;  // one warp per trial
+  kpp_locate(p, n_blk, r, warp, lane, nullptr);
+}
+
+// Sharded variant, once the ranks' totals are gathered in xbuf[0..n_ranks): the global
+// cumulative sum is the concatenation of the ranks' sums in rank order; the rank whose range
+// contains a draw locates it and publishes the candidate in xbuf[kXCand + 4*trial ..),
+// everybody else leaves zeros there for the sum-exchange that follows.
+__global__ void __launch_bounds__(kKppMaxTrials * 32) kpp_search_sharded_kernel(const KppParams p, long long n_blk) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= p.n_trials) return;
+  double pot = 0.0, before = 0.0;
+  for (int q = 0; q < p.n_ranks; ++q) {
+    if (q == p.rank) before = pot;
+    pot += p.xbuf[q];
+  }
+  if (lane == 0 && warp == 0) p.st->pot = pot;
+  const double r = p.rand_vals[(size_t)(p.round - 1) * p.n_trials + warp] * pot;
+  // owner: the first rank with points whose inclusive prefix reaches r; overshoots (rounding)
+  // go to the last rank that has points, like np.clip does on one rank
+  int owner = -1, last_nonempty = -1;
+  double acc = 0.0;
+  for (int q = 0; q < p.n_ranks; ++q) {
+    const double tq = p.xbuf[q];
+    const bool has = p.xbuf[kXCnt + q] > 0.0;  // point counts, gathered once per call
+    if (has) last_nonempty = q;
+    acc += tq;
+    if (owner < 0 && has && acc >= r) owner = q;
+  }
+  if (owner < 0) owner = last_nonempty;
+  if (owner != p.rank) return;
+  kpp_locate(p, n_blk, r - before, warp, lane, p.xbuf + kXCand + warp * 4);
+}
+
+// After the candidate exchange: unpack xbuf into the state block (all ranks, identical).
+__global__ void kpp_unpack_candidates_kernel(const KppParams p) {
+  const int t = threadIdx.x;
+  if (t >= p.n_trials) return;
+  const double* in = p.xbuf + kXCand + t * 4;
+  p.st->cand_idx[t] = (long long)in[0];
+  p.st->cand_xyz[t][0] = in[1];
+  p.st->cand_xyz[t][1] = in[2];
+  p.st->cand_xyz[t][2] = in[3];
+}
+
+// Sharded: np.argmin over the exchanged potentials, or (round 0) the exchanged first centre.
+__global__ void kpp_choose_kernel(const KppParams p) {
+  if (threadIdx.x != 0) return;
+  int best = 0;
+  if (p.round > 0) {
+    for (int t = 1; t < p.n_trials; ++t)
+      if (p.st->pots[t] < p.st->pots[best]) best = t;  // first minimum
+  }
+  for (int d = 0; d < 3; ++d) {
+    p.st->best_xyz[d] = p.st->cand_xyz[best][d];
+    p.centers_out[(size_t)p.round * 3 + d] = p.st->cand_xyz[best][d];
+  }
+  p.st->best_idx = p.st->cand_idx[best];
+  p.indices_out[p.round] = p.st->cand_idx[best];
+}
+
+// Sharded round 0: the owner of the first centre publishes it as candidate 0.
+__global__ void kpp_first_candidate_kernel(const KppParams p) {
+  if (threadIdx.x != 0 || p.first_index < 0) return;
+  const float* q = p.pts + pt_off(p.first_index);
+  double* out = p.xbuf + kXCand;
+  out[0] = (double)(p.rank_offset + p.first_index);
+  out[1] = (double)q[0];
+  out[2] = (double)q[kGroup];
+  out[3] = (double)q[2 * kGroup];
 }
 
 // Potential of every candidate: sum_i min(closest[i], d(x_i, cand_t)); fixed-order reductions;
@@ -251,7 +345,8 @@ __global__ void __launch_bounds__(kThreads) kpp_pot_kernel(const KppParams p) {
     p.st->pots[threadIdx.x] = s;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !p.choose) p.st->ticket = 0u;  // sharded: the ranks' potentials are summed first
+  if (threadIdx.x == 0 && p.choose) {
     int best = 0;
     for (int t = 1; t < T; ++t)
       if (p.st->pots[t] < p.st->pots[best]) best = t;  // np.argmin: first minimum

@@ -432,13 +432,17 @@ __global__ void __launch_bounds__(kThreads) to_blocked_kernel(const float* src, 
 }
 
 // out[i] = (x, y, z) of point idx[i]  (X[seeds] of init="random", sklearn/_kmeans.py:1014-1021)
-__global__ void gather_points_kernel(const float* pts, const long long* idx, int m, float* out) {
+// idx are global indices; a rank owns [rank_offset, rank_offset + n) and writes zeros elsewhere
+__global__ void gather_points_kernel(const float* pts, const long long* idx, int m, long long rank_offset,
+                                     long long n, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float* q = pts + pt_off(idx[i]);
-  out[3 * i + 0] = q[0];
-  out[3 * i + 1] = q[kGroup];
-  out[3 * i + 2] = q[2 * kGroup];
+  const long long l = idx[i] - rank_offset;
+  const bool mine = l >= 0 && l < n;
+  const float* q = pts + pt_off(mine ? l : 0);
+  out[3 * i + 0] = mine ? q[0] : 0.f;
+  out[3 * i + 1] = mine ? q[kGroup] : 0.f;
+  out[3 * i + 2] = mine ? q[2 * kGroup] : 0.f;
 }
 
 // zero the unused tail of the last block (and nothing else)

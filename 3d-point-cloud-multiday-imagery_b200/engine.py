@@ -202,6 +202,14 @@ class Engine:
     def n_points(self) -> int:
         return int(self._lib.mdkm_num_points(self._h))
 
+    @property
+    def n_points_global(self) -> int:
+        """Points over all ranks (== ``n_points`` without a communicator)."""
+        n = int(self._lib.mdkm_num_points_global(self._h))
+        if n < 0:
+            self._check(C.STATUS_BY_NAME["MDKM_ERR_STATE"])
+        return n
+
     def gather_points(self, idx) -> np.ndarray:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         out = np.empty((idx.shape[0], 3), dtype=np.float32)
@@ -298,11 +306,23 @@ class Engine:
         self._lib.mdkm_fit_stats(self._h, byref(nref), None, None)
         return labels, sums, counts, int(nref.value)
 
+    def predict(self, centroids, want_labels=True):
+        """E-step only (KMeans.predict): returns (labels int32[N] or None, inertia)."""
+        c = np.ascontiguousarray(centroids, dtype=np.float64)
+        if c.ndim != 2 or c.shape[1] != 3:
+            raise ValueError("centroids must be [K,3]")
+        labels = self._result_buffer("labels", (self.n_points,), np.int32) if want_labels else None
+        inertia = c_double(0.0)
+        self._check(self._lib.mdkm_predict(
+            self._h, int(c.shape[0]), c.ctypes.data_as(POINTER(c_double)),
+            c_void_p(labels.ctypes.data) if labels is not None else None, C.MEM_HOST, byref(inertia)))
+        return labels, float(inertia.value)
+
     def kmeans_plusplus(self, n_clusters: int, random_state):
         """k-means++ seeding (sklearn/_kmeans.py:180-278); RNG draws come from ``random_state``
         (a ``numpy.random.RandomState``) in scikit-learn's order, distances run on the GPU."""
         k = int(n_clusters)
-        n = self.n_points
+        n = self.n_points_global
         n_local_trials = 2 + int(np.log(k))
         # RandomState.choice(n, p=w/w.sum()) (sklearn/_kmeans.py:228): one uniform draw inverted
         # through cdf = cumsum(p)/cdf[-1] with searchsorted(side="right") -- reproduced exactly

@@ -98,6 +98,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def measured_traffic(cfg):
+    """DRAM bytes per Lloyd iteration from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))[cfg]
+        return float(t["dram_bytes_per_iteration"]), t.get("source", "")
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,9 +280,14 @@ def run_mine(args):
     peak, peak_src = measured_peak()
     step_avg_ms = step_ms / max(n_steps, 1)
     achieved = ALGO_BYTES_PER_POINT_ITER * n_local / (step_avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.config)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "lloyd_step_kernel", "avg_launch_ms": step_avg_ms,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "one Lloyd iteration = lloyd_classify_kernel + lloyd_step_kernel (update fused in its tail)",
+                "avg_launch_ms": step_avg_ms,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT_ITER * n_local, "peak_source": peak_src,
+                "note": "achieved = 16 B x points / measured iteration time; the kernels move fewer bytes than "
+                        "that (cached group summaries), so frac can exceed what a 16 B/point stream allows",
                 "fma_bound_points_iters_per_s": 148 * 128 * 1.965e9 / (3 * k)}
 
     # ---- end to end through the public API: pinned host rasters in, host results out ------------

@@ -103,11 +103,15 @@ int mdkm_bind_cloud_output(mdkm_handle* h, float* out_host, int64_t capacity_poi
  * core.py:227-228) for d = 3. */
 int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int mem);
 
-/* Number of resident points on this rank. */
+/* Number of resident points on this rank / over all ranks of the communicator (the second
+ * one is a collective the first time it is called for a cloud). */
 int64_t mdkm_num_points(const mdkm_handle* h);
+int64_t mdkm_num_points_global(mdkm_handle* h);
 
-/* Fetch m resident points by local index as float32 [m,3] (x,y,z) into host memory (what
- * `X[seeds]` does for init="random", sklearn/cluster/_kmeans.py:1014-1021). */
+/* Fetch m points by index as float32 [m,3] (x,y,z) into host memory (what `X[seeds]` does for
+ * init="random", sklearn/cluster/_kmeans.py:1014-1021).  With a communicator the indices
+ * are global (shards concatenated in rank order), the call is collective and every rank
+ * receives all m points. */
 int mdkm_gather_points(mdkm_handle* h, const int64_t* idx, int m, float* out_xyz);
 
 /* Copy the resident cloud out as float32 [n,3].  napari_order != 0 gives (z,y,x) columns as
@@ -163,6 +167,12 @@ int mdkm_fit_stats(const mdkm_handle* h, int64_t* n_refined, int64_t* n_relocati
 int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* labels_out,
                     int labels_mem, double* sums_out, int64_t* counts_out);
 
+/* Labels of the resident points for given centroids and the resulting inertia: the E-step
+ * alone, i.e. KMeans.predict / -KMeans.score (sklearn/cluster/_kmeans.py:742-756, 1068-1095;
+ * inertia: _k_means_common.pyx:94-124).  labels_out may be NULL; inertia is global over ranks. */
+int mdkm_predict(mdkm_handle* h, int k, const double* centroids, int32_t* labels_out,
+                 int labels_mem, double* inertia_out);
+
 /* k-means++ seeding on the device (sklearn/cluster/_kmeans.py:180-278).  The random draws
  * of numpy.random.RandomState stay on the host and are supplied by the caller in
  * scikit-learn's order: `first_index` is the result of RandomState.choice(n) for the first
@@ -171,7 +181,10 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
  * 2 + int(ln k)); the device does the distances (float64), the potentials, the
  * cumulative-sum search and the greedy choice among the trials, all k centres without a
  * host round trip.  centers_out: float64[k*3]; indices_out: int64[k] (may be NULL).
- * Single rank only. */
+ * With a communicator the cloud is the concatenation of the ranks' shards in rank order:
+ * first_index and the returned indices are GLOBAL, every rank passes the same arguments and
+ * gets the same centres (the ranks' sums are exchanged with NCCL, three small all-reduces
+ * per centre). */
 int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals,
                          int n_local_trials, double* centers_out, int64_t* indices_out);
 

@@ -274,6 +274,18 @@ def test_fit_is_deterministic_and_idempotent(engine):
     assert n == a["labels"].shape[0]
 
 
+def test_predict_matches_oracle_e_step(engine):
+    hm = synth.make_stack(2, 200, 256, seed=6, n_buildings=7).numpy()
+    P = UO.unproject_stack(hm)
+    engine.unproject(hm)
+    C = P[np.sort(np.random.RandomState(1).choice(P.shape[0], 24, replace=False))] + 0.123
+    labels, inertia = engine.predict(C)
+    mean = P.mean(axis=0)
+    ref = KO.e_step(P - mean, C - mean)
+    check_labels(P, C, ref, labels, allow_near=0)
+    np.testing.assert_allclose(inertia, KO.inertia(P, C, ref), rtol=1e-9)
+
+
 def test_fit_errors(engine):
     engine.set_points(np.zeros((3, 3), dtype=np.float32))
     with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):

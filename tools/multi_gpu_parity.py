@@ -53,6 +53,11 @@ def main():
     refs["reloc"] = single.fit(bad, max_iter=12, tol=0.0)
     check("single-GPU relocation happened", refs["reloc"]["n_relocations"] >= 1)
     off = single.segment_offsets
+    kpp_ref = {(k, seed): single.kmeans_plusplus(k, np.random.RandomState(seed)) for k, seed in ((8, 0), (40, 1))}
+    rand_ref = single.gather_points(np.array([0, 5, n_all - 1, n_all // 2], dtype=np.int64))
+    full_ref = pkg.fuse_multiday_kmeans(hm, n_clusters=6, init="k-means++", n_init=3, random_state=7, max_iter=15,
+                                        tol=0.0, engine=single)
+    full_ref_labels = full_ref.labels.copy()
     single.close()
 
     # sharded: rank r owns days [2r, 2r+2)
@@ -72,6 +77,18 @@ def main():
             check(tag + "labels", np.array_equal(r["labels"], ref["labels"][off[b]:off[e]]))
             check(tag + "inertia", abs(r["inertia"] - ref["inertia"]) <= 1e-12 * ref["inertia"])
             check(tag + "relocations", r["n_relocations"] == ref["n_relocations"])
+        # sharded k-means++ / global gather / the public API with restarts
+        for (k, seed), (c_ref, i_ref) in kpp_ref.items():
+            c, i = eng.kmeans_plusplus(k, np.random.RandomState(seed))
+            check(f"p2p={p2p} kmeans++ k={k}: indices", np.array_equal(i, i_ref))
+            check(f"p2p={p2p} kmeans++ k={k}: centres", np.array_equal(c, c_ref))
+        got = eng.gather_points(np.array([0, 5, n_all - 1, n_all // 2], dtype=np.int64))
+        check(f"p2p={p2p} global gather", np.array_equal(got, rand_ref))
+        res = pkg.fuse_multiday_kmeans(hm[b:e].reshape(-1), n_clusters=6, init="k-means++", n_init=3, random_state=7,
+                                       max_iter=15, tol=0.0, engine=eng, stack_shape=(D, H, W), pix_begin=b * H * W)
+        check(f"p2p={p2p} API k-means++ n_init=3: centroids", res.centroids.tobytes() == full_ref.centroids.tobytes())
+        check(f"p2p={p2p} API k-means++ n_init=3: labels", np.array_equal(res.labels, full_ref_labels[off[b]:off[e]]))
+        check(f"p2p={p2p} API k-means++ n_init=3: n_iter", res.n_iter == full_ref.n_iter)
         # time per Lloyd iteration (k=16, 40 iterations, no convergence)
         name, k = "k16_tol0", 16
         for _ in range(3):
