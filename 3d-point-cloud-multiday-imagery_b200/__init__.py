@@ -4,8 +4,8 @@ Drop-in for the one hot path of rafael-alani/3d-point-cloud-multiday-imagery des
 SURVEY.md section 8.  The heavy lifting is in ``libmdkm.so`` (hand-written sm_100a CUDA behind
 the C ABI of ``include/mdkm.h``); there is no CPU fallback.
 """
-from .api import (FusionResult, Layer, MultiDayFusionPlugin, fuse_multiday_kmeans, kmeans_points,
-                  to_layers)
+from .api import (FusionResult, Layer, MultiDayFusionPlugin, fuse_height_rasters, fuse_multiday_kmeans,
+                  kmeans_points, to_layers)
 from .build import build_library
 from .dist import init_engine_comm, shard_range
 from .engine import Engine
@@ -13,6 +13,6 @@ from .synth import init_from_points, make_stack
 
 __all__ = [
     "Engine", "FusionResult", "Layer", "MultiDayFusionPlugin", "build_library",
-    "fuse_multiday_kmeans", "init_engine_comm", "init_from_points", "kmeans_points",
+    "fuse_height_rasters", "fuse_multiday_kmeans", "init_engine_comm", "init_from_points", "kmeans_points",
     "make_stack", "shard_range", "to_layers",
 ]

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmdkm.so")
 
 MDKM_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
-HM_F32, HM_I16 = 0, 1
+HM_F32, HM_I16, HM_F32_GTIFF3 = 0, 1, 2
 POINTS_AOS, POINTS_SOA = 0, 1
 NCCL_UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64

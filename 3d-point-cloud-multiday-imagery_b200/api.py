@@ -144,7 +144,7 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
                          max_iter=300, tol=1e-4, random_state=None, max_abs_height=MAX_ABS_HEIGHT,
                          detrend=False, disparity_scale=None, ground_level=False, return_cloud=True,
                          device=0, engine: Optional[Engine] = None, stack_shape=None,
-                         pix_begin=0) -> FusionResult:
+                         pix_begin=0, raster_layout=None) -> FusionResult:
     """Unproject a multi-day height-map stack into one XYZ cloud and cluster it (Lloyd).
 
     height_maps : float32 ``[D,H,W]`` (NaN = nodata), numpy or torch (CPU or CUDA); or int16
@@ -155,6 +155,8 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     ground_level : per day, shift z so that its 2nd percentile is 0 and return the 'height'
         colour property (plugin.py:181-192), before clustering -- with ``detrend=True`` this
         is the reference's whole per-pair tail, applied to every day of the stack.
+    raster_layout : "gtiff3" when ``height_maps`` is ``[D,H,W,3]`` float32 in the pixel layout of the
+        reference's ``5-out-F.tif`` (see ``fuse_height_rasters``).
     engine : reuse an existing ``Engine`` (keeps device buffers, and with
         ``Engine(pinned_results=True)`` page-locked result buffers, across calls); with a
         multi-rank engine pass this rank's flat slice plus ``stack_shape`` / ``pix_begin``.
@@ -168,7 +170,7 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
         stream = "napari" if (return_cloud and not ground_level) else None
         n = eng.unproject(height_maps, valid_masks, max_abs_height=max_abs_height, detrend=detrend,
                           disparity_scale=disparity_scale, stack_shape=stack_shape, pix_begin=pix_begin,
-                          stream_cloud=stream)
+                          stream_cloud=stream, raster_layout=raster_layout)
         cloud = None
         if stream is not None:
             n, cloud = n
@@ -190,6 +192,17 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     finally:
         if own:
             eng.close()
+
+
+def fuse_height_rasters(paths, **kwargs) -> FusionResult:
+    """``fuse_multiday_kmeans`` on the reference's own per-pair height rasters: the
+    ``5-out-F.tif`` files its stereo stage writes (disparity.py:213-224; 3-band Float32 GTiff,
+    band 0 = -disparity/16, band 2 = final_defined).  The pixels go to the GPU as they are in
+    the files; validity (band 2) and the |h| <= 144 test are applied there."""
+    from .tiff_io import load_height_rasters
+
+    stack = load_height_rasters(list(paths))
+    return fuse_multiday_kmeans(stack, raster_layout="gtiff3", **kwargs)
 
 
 def kmeans_points(points, *, n_clusters=8, init="k-means++", n_init=1, max_iter=300, tol=1e-4,

@@ -188,10 +188,7 @@ __global__ void day_offsets_kernel(const UnprojParams p, int n_days, long long* 
   unsigned int cnt = 0;
   for (long long i = c * kChunk + lane; i < bl; i += 32) {
     float hv;
-    if (p.dtype == 0) hv = __ldg(reinterpret_cast<const float*>(p.hm) + i);
-    else hv = p.scale * (float)__ldg(reinterpret_cast<const short*>(p.hm) + i);
-    bool ok = fabsf(hv) <= p.max_abs;
-    if (p.mask) ok = ok && (__ldg(p.mask + i) != 0);
+    const bool ok = load_height1(p, i, hv);
     cnt += ok ? 1u : 0u;
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);

@@ -899,7 +899,8 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   if (D < 0 || H <= 0 || W <= 0 || pix_begin < 0 || pix_count < 0 ||
       pix_begin + pix_count > (int64_t)D * H * W || (pix_count > 0 && !hm))
     return fail(h, MDKM_ERR_INVALID, "bad stack geometry");
-  if (hm_dtype != MDKM_HM_F32 && hm_dtype != MDKM_HM_I16) return fail(h, MDKM_ERR_INVALID, "bad hm_dtype");
+  if (hm_dtype != MDKM_HM_F32 && hm_dtype != MDKM_HM_I16 && hm_dtype != MDKM_HM_F32_GTIFF3)
+    return fail(h, MDKM_ERR_INVALID, "bad hm_dtype");
   const long long HW = (long long)H * W;
   if (detrend && ((pix_begin % HW) != 0 || (pix_count % HW) != 0))
     return fail(h, MDKM_ERR_INVALID, "detrend needs whole days in [pix_begin, pix_begin+pix_count)");
@@ -908,7 +909,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
                 (long long)pix_count);
   CU(cudaSetDevice(h->device));
   OK(wait_pending(h));
-  const size_t esz = hm_dtype == MDKM_HM_F32 ? 4 : 2;
+  const size_t esz = hm_dtype == MDKM_HM_F32 ? 4 : (hm_dtype == MDKM_HM_I16 ? 2 : 12);
   const bool from_host = mem != MDKM_MEM_DEVICE;
   const void* d_hm = hm;
   const uint8_t* d_mask = mask;

@@ -25,7 +25,7 @@ struct UnprojParams {
   long long pix_count;
   long long HW;
   int W, H;
-  int dtype;              // MDKM_HM_F32 / MDKM_HM_I16
+  int dtype;              // MDKM_HM_F32 / MDKM_HM_I16 / MDKM_HM_F32_GTIFF3
   int vec_ok;             // hm (and mask) aligned for 16 B / 4 B vector loads
   float scale;            // for I16
   float max_abs;
@@ -37,6 +37,25 @@ struct UnprojParams {
   long long chunk_begin;  // this launch handles chunks [chunk_begin, chunk_end) of the range
   long long chunk_end;
 };
+
+// One pixel: height and validity (plugin.py:151-152).  dtype 2 is the reference's own
+// "5-out-F.tif" raster (disparity.py:213-224): three pixel-interleaved float32 bands, band 0
+// the height (-disp/16), band 2 `final_defined`.
+__device__ __forceinline__ bool load_height1(const UnprojParams& p, long long i, float& hv) {
+  bool ok = true;
+  if (p.dtype == 0) {
+    hv = __ldg(reinterpret_cast<const float*>(p.hm) + i);
+  } else if (p.dtype == 1) {
+    hv = p.scale * (float)__ldg(reinterpret_cast<const short*>(p.hm) + i);
+  } else {
+    const float* s3 = reinterpret_cast<const float*>(p.hm) + 3 * i;
+    hv = __ldg(s3);
+    ok = __ldg(s3 + 2) != 0.f;
+  }
+  ok = ok && (fabsf(hv) <= p.max_abs);
+  if (p.mask) ok = ok && (__ldg(p.mask + i) != 0);
+  return ok;
+}
 
 // Loads 4 consecutive pixel heights starting at local index i (i % 4 == 0); invalid -> NaN.
 __device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i, float (&h)[4],
@@ -52,7 +71,7 @@ __device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i
 #pragma unroll
       for (int e = 0; e < 4; ++e) h[e] = (i + e < p.pix_count) ? __ldg(src + i + e) : __int_as_float(0x7fc00000);
     }
-  } else {
+  } else if (p.dtype == 1) {
     const short* src = reinterpret_cast<const short*>(p.hm);
     if (full && p.vec_ok) {
       const uint2 v = ldg_stream_u64(src + i);
@@ -65,6 +84,24 @@ __device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i
       for (int e = 0; e < 4; ++e)
         h[e] = (i + e < p.pix_count) ? p.scale * (float)__ldg(src + i + e) : __int_as_float(0x7fc00000);
     }
+  } else {
+    // 4 pixels = 12 floats (h a d | h a d | h a d | h a d): three aligned 16 B loads
+    const float* src = reinterpret_cast<const float*>(p.hm) + 3 * i;
+    float d[4];
+    if (full && p.vec_ok) {
+      const float4 v0 = ldg_stream_f4(src), v1 = ldg_stream_f4(src + 4), v2 = ldg_stream_f4(src + 8);
+      h[0] = v0.x; d[0] = v0.z; h[1] = v0.w; d[1] = v1.y; h[2] = v1.z; d[2] = v2.x; h[3] = v2.y; d[3] = v2.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = i + e < p.pix_count;
+        h[e] = in ? __ldg(src + 3 * e) : __int_as_float(0x7fc00000);
+        d[e] = in ? __ldg(src + 3 * e + 2) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (d[e] == 0.f) h[e] = __int_as_float(0x7fc00000);  // not `final_defined` -> nodata
   }
   unsigned int m4 = 0x01010101u;
   if (p.mask) {
@@ -226,11 +263,7 @@ __global__ void __launch_bounds__(kThreads) plane_moments_kernel(const UnprojPar
       if (l >= p.HW) break;
       const long long i = day_begin + l;
       float hv;
-      if (p.dtype == 0) hv = __ldg(reinterpret_cast<const float*>(p.hm) + i);
-      else hv = p.scale * (float)__ldg(reinterpret_cast<const short*>(p.hm) + i);
-      bool ok = fabsf(hv) <= p.max_abs;
-      if (p.mask) ok = ok && (__ldg(p.mask + i) != 0);
-      if (ok) {
+      if (load_height1(p, i, hv)) {
         const int row = (int)(l / p.W);
         const int col = (int)(l - (long long)row * p.W);
         const double X = (double)col - px, Y = (double)row - py, Z = (double)hv;

@@ -135,9 +135,13 @@ class Engine:
 
     # -- data ----------------------------------------------------------------------------
     def unproject(self, height_maps, valid_masks=None, *, max_abs_height=144.0, detrend=False,
-                  disparity_scale=None, pix_begin=0, stack_shape=None, stream_cloud=None):
+                  disparity_scale=None, pix_begin=0, stack_shape=None, stream_cloud=None,
+                  raster_layout=None):
         """Height rasters -> resident XYZ cloud (plugin.py:148-171).  Returns the point count.
 
+        ``raster_layout="gtiff3"``: ``height_maps`` is float32 ``[D,H,W,3]``, the pixel layout of
+        the reference's ``5-out-F.tif`` (``tiff_io.load_height_rasters``): band 0 height, band 2
+        ``final_defined``.
         ``stream_cloud``: None, or "napari" / "xyz" to also stream the cloud to the host while
         the stack is still being uploaded; the call then returns ``(n, cloud[n,3])`` and the
         array is complete after ``wait()``.
@@ -148,6 +152,14 @@ class Engine:
         """
         is_i16 = disparity_scale is not None
         ptr, mem, keep, shape, _ = _as_buffer(height_maps, np.int16 if is_i16 else np.float32)
+        gtiff3 = raster_layout == "gtiff3"
+        if gtiff3:
+            # the reference's 5-out-F.tif pixels: [..., 3] float32 = height, unused, final_defined
+            if is_i16 or len(shape) < 3 or shape[-1] != 3:
+                raise ValueError("raster_layout='gtiff3' needs float32 [D,H,W,3] (or [H,W,3])")
+            shape = tuple(shape[:-1])
+        elif raster_layout is not None:
+            raise ValueError("raster_layout must be None or 'gtiff3'")
         if stack_shape is None:
             if len(shape) == 2:
                 shape = (1,) + tuple(shape)
@@ -172,7 +184,7 @@ class Engine:
             self._check(self._lib.mdkm_bind_cloud_output(
                 self._h, c_void_p(cloud_buf.ctypes.data), int(count), 1 if stream_cloud == "napari" else 0))
         self._check(self._lib.mdkm_unproject(
-            self._h, c_void_p(ptr), C.HM_I16 if is_i16 else C.HM_F32,
+            self._h, c_void_p(ptr), C.HM_I16 if is_i16 else (C.HM_F32_GTIFF3 if gtiff3 else C.HM_F32),
             float(disparity_scale) if is_i16 else 1.0, c_void_p(mptr) if mptr else None,
             int(D), int(H), int(W), int(pix_begin), int(count), float(max_abs_height),
             1 if detrend else 0, mem, byref(n)))

@@ -41,7 +41,10 @@ typedef enum mdkm_status {
 } mdkm_status;
 
 enum { MDKM_MEM_HOST = 0, MDKM_MEM_DEVICE = 1 };
-enum { MDKM_HM_F32 = 0, MDKM_HM_I16 = 1 };      /* height raster element type */
+/* height raster element type: float32 heights; int16 OpenCV fixed-point disparity; or the
+ * reference's own "5-out-F.tif" pixel layout (disparity.py:213-224): three pixel-interleaved
+ * float32 bands per pixel, band 0 = height (-disp/16), band 2 = final_defined (0 = invalid) */
+enum { MDKM_HM_F32 = 0, MDKM_HM_I16 = 1, MDKM_HM_F32_GTIFF3 = 2 };
 enum { MDKM_POINTS_AOS = 0, MDKM_POINTS_SOA = 1 }; /* xyzxyz... or x[n] y[n] z[n] */
 
 #define MDKM_NCCL_UNIQUE_ID_BYTES 128
@@ -80,7 +83,8 @@ int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles);
  * [pix_begin, pix_begin+pix_count) of the flattened [D,H,W] stack.  `hm` / `mask` point at
  * pixel `pix_begin`.  hm_dtype MDKM_HM_F32: heights, used as is (hm_scale ignored);
  * MDKM_HM_I16: OpenCV fixed-point disparity, h = hm_scale * disp (the reference uses
- * -1/16).  mask may be NULL.  detrend != 0 additionally applies the per-day plane fit of
+ * -1/16); MDKM_HM_F32_GTIFF3: 12 bytes per pixel, band 2 acts as the validity mask (ANDed
+ * with `mask` when that is given too).  mask may be NULL.  detrend != 0 additionally applies the per-day plane fit of
  * plugin.py:161-171 (z becomes the signed distance to the day's least-squares plane); it
  * needs whole days in the range.  The points stay resident in the handle, in np.where
  * order (day-major, row-major); *n_points_out receives how many there are on this rank. */

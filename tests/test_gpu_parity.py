@@ -107,6 +107,38 @@ def test_unproject_detrend(engine, golden):
     np.testing.assert_allclose(engine.get_cloud(False)[:, 2], ref[:, 2], rtol=0, atol=2e-5)
 
 
+def test_unproject_reference_raster_files(pkg, engine, tmp_path):
+    """f3: the reference's 5-out-F.tif rasters (disparity.py:213-224) go to the GPU as stored."""
+    tio = importlib.import_module("3d-point-cloud-multiday-imagery_b200.tiff_io")
+    rs = np.random.RandomState(5)
+    paths, days = [], []
+    for d, (h, w) in enumerate([(90, 130), (75, 141), (90, 141)]):
+        bands = np.zeros((3, h, w), dtype=np.float32)
+        bands[0] = synth.make_stack(1, h, w, seed=30 + d, n_buildings=4).numpy()[0]
+        bands[0][rs.rand(h, w) < 0.02] = 18 * 16.0  # WLS sentinel: |h| > 144 (disparity.py:182-187)
+        bands[2] = rs.rand(h, w) > 0.15
+        p = str(tmp_path / f"{d}-5-out-F.tif")
+        tio.write_tiff(p, bands, planar=(d == 1))
+        paths.append(p)
+        days.append(bands)
+    stack = tio.load_height_rasters(paths)
+    ref = UO.unproject_stack(stack[..., 0].astype(np.float64), stack[..., 2] != 0)
+    n = engine.unproject(stack, raster_layout="gtiff3")
+    assert n == ref.shape[0]
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), ref)
+    # and with the per-day plane fit + extra mask, against the separate-plane path
+    extra = rs.rand(*stack.shape[:3]) > 0.1
+    n1 = engine.unproject(stack, extra, raster_layout="gtiff3", detrend=True)
+    c1 = engine.get_cloud(False).copy()
+    hm = np.ascontiguousarray(stack[..., 0])
+    n2 = engine.unproject(hm, (stack[..., 2] != 0) & extra, detrend=True)
+    assert n1 == n2
+    np.testing.assert_array_equal(c1, engine.get_cloud(False))
+    res = pkg.fuse_height_rasters(paths, n_clusters=4, init="k-means++", random_state=0, max_iter=10, engine=engine)
+    assert res.n_points == ref.shape[0]
+    np.testing.assert_array_equal(res.fused_cloud[:, ::-1].astype(np.float64), ref)
+
+
 def test_streamed_cloud_matches_get_cloud(engine):
     """Slab pipeline (several slabs, day-aligned cuts when detrending) == the one-shot path."""
     import torch
