@@ -80,7 +80,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MDKM_LIB") or LIB_PATH  # MDKM_LIB: an instrumented build (tools/)
     if not os.path.exists(p):
         raise FileNotFoundError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

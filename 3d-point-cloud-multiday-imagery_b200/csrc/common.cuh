@@ -45,8 +45,16 @@ struct DevStatus {
   unsigned int ticket;            // CTAs of the running step kernel that have flushed their sums
   unsigned long long epoch;       // fused steps completed since the communicator was created
   int xchg_timeout;               // 1: a peer never delivered its partial sums (fatal)
-  int pad1;
+  unsigned int grid_bar;          // arrival counter of the step kernel's grid barrier
+  // diagnostics (MDKM_TIMING builds only): globaltimer stamps of the last fused step, ns
+  unsigned long long t_start, t_first_done, t_last_done, t_update_done, t_classify_start, t_classify_done;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Peer exchange of the K x 4 partial sums over NVLink (one process per GPU, buffers shared
 // through CUDA IPC).  Every rank owns a buffer  data[2][n_ranks][slot] + flags[2][n_ranks];

@@ -211,6 +211,13 @@ __device__ __forceinline__ float min_gap_over_box(const float4 row, const float4
   return aw + fminf(ax * bx0, ax * bx1) + fminf(ay * by0, ay * by1) + fminf(az * bz0, az * bz1);
 }
 
+struct __align__(16) GroupSummary {
+  float lo[3], hi[3];  // box of the centred FP32 coordinates
+  int q[3];            // sum of the fixed-point coordinates of the group's points
+  int n;               // points in the group (128 except the cloud's tail)
+  int pad[2];
+};
+
 struct StepParams {
   const float* pts;           // blocked cloud (common.cuh)
   long long n;
@@ -223,9 +230,11 @@ struct StepParams {
   int ignore_status;          // 1: test hook (run even when done/paused)
   int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
                               //    (NVLink, no host, no NCCL) and runs the centroid update
-  const int* worklist;        // groups the classification pass could not settle (nullptr: all groups)
-  int* work_count;            // number of entries; cleared by the fused tail
-  int* glabel;                // per group: its label when all its points share one, else -1
+  const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
+  int* worklist;              // groups the classification pass could not settle
+  int* work_count;            // number of entries; cleared by the tail of the kernel
+  int* glabel;                // per group: the label that owns its whole box, else -1
+  unsigned int* grid_bar;     // arrival counter of the in-kernel grid barrier
   UpdateParams upd;
   PeerXchg px;
 };
@@ -239,13 +248,6 @@ struct StepParams {
 // On raster-ordered clouds that covers most groups; only the rest (a cluster boundary crosses
 // them) are streamed through the per-point kernel.  Results are identical to brute force.
 // ---------------------------------------------------------------------------------------
-struct __align__(16) GroupSummary {
-  float lo[3], hi[3];  // box of the centred FP32 coordinates
-  int q[3];            // sum of the fixed-point coordinates of the group's points
-  int n;               // points in the group (128 except the cloud's tail)
-  int pad[2];
-};
-
 __global__ void __launch_bounds__(kThreads) group_summary_kernel(const float* pts, long long n, FrameF f,
                                                                  GroupSummary* out) {
   const int lane = threadIdx.x & 31;
@@ -288,66 +290,42 @@ __global__ void __launch_bounds__(kThreads) group_summary_kernel(const float* pt
   }
 }
 
-struct ClassifyParams {
-  const GroupSummary* gsum;
-  long long n;                // points on this rank
-  void* labels;               // uint8 / uint16 per point, capacity whole groups
-  int* glabel;                // [n_groups]
-  int* worklist;              // [n_groups]
-  int* work_count;
-  const unsigned char* table;
-  unsigned long long* acc;
-  const DevStatus* st;
-  int k, kpad;
-  int ignore_status;
-};
-
+// Classification pass, run by every CTA of the step kernel before the per-point work.
 // One THREAD per group.  A group that was settled with label L in the previous iteration is
 // re-tested against L only (one pass over the centroid table); a group that was not settled
-// goes straight to the per-point kernel, which hands it back here (glabel >= 0) as soon as one
+// goes straight to the per-point pass, which hands it back here (glabel >= 0) as soon as one
 // centroid owns its whole box.  In the first iteration every group is tested against the
-// centroid nearest to its box centre.
-template <typename LabT>
-__global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const ClassifyParams p) {
-  if (!p.ignore_status && (p.st->done | p.st->paused)) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* s_fast = reinterpret_cast<float4*>(smem_raw);
-  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_fast + p.kpad);
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ unsigned int s_changed;
+// centroid nearest to its box centre.  Settled groups add their cached sums to `s_acc` (the
+// warp's accumulator slice) and never touch their points; the others are appended to the
+// global worklist (staged in shared memory, one global atomic per kClassifyList entries).
+constexpr int kClassifyList = 2048;  // shared-memory staging of the worklist (entries per CTA)
+
+template <bool kPrivate>
+__device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long long sx, long long sy,
+                                        long long sz, unsigned int cnt);
+
+template <typename LabT, bool kPrivate>
+__device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__ gsum, int n_groups,
+                                                LabT* labels, int* glabel, int* worklist, int* work_count,
+                                                const float4* __restrict__ s_fast, int k, float margin,
+                                                bool first_iter, unsigned long long* s_acc, int* s_wcnt,
+                                                int* s_wbase, int* s_list, unsigned int& n_chg) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    fence_mbar_init();
-    s_changed = 0;
-  }
-  for (int i = tid; i < p.kpad * 4; i += kThreads) s_acc[i] = 0ull;
+  if (tid == 0) *s_wbase = 0;
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
-    tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
-  }
-  const float margin = 4.0f * p.st->thresh;
-  const bool first_iter = p.st->first != 0;
-  LabT* labels = reinterpret_cast<LabT*>(p.labels);
-  const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
-  // the summaries do not depend on the centroids: fetch the first one while the table arrives
   const int span = (int)gridDim.x * kThreads;
   int g = (int)blockIdx.x * kThreads + tid;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
   int prev = -1;
   if (g < n_groups) {
-    const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
+    const float4* src = reinterpret_cast<const float4*>(gsum + g);
     a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-    prev = first_iter ? -1 : p.glabel[g];
+    prev = first_iter ? -1 : glabel[g];
   }
-  mbar_wait(&s_bar, 0);
-
-  unsigned int n_chg = 0;
-  for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // warp-uniform trip count
+  for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // CTA-uniform trip count
     const bool valid = g < n_groups;
-    int label = -1;  // settled label, or -1: needs the per-point kernel
-    int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
+    int label = -1;  // settled label, or -1: needs the per-point pass
+    const int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
     if (valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
       const float lo0 = a.x, lo1 = a.y, lo2 = a.z, hi0 = a.w, hi1 = b.x, hi2 = b.y;
       int ref = prev;
@@ -355,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
         const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
         float dmin = __int_as_float(0x7f800000);
         ref = 0;
-        for (int j = 0; j < p.k; ++j) {
+        for (int j = 0; j < k; ++j) {
           const float4 r = s_fast[j];
           const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
           if (d < dmin) { dmin = d; ref = j; }
@@ -363,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
       }
       const float4 rr = s_fast[ref];
       int ncand = 0;
-      for (int j = 0; j < p.k; ++j)
+      for (int j = 0; j < k; ++j)
         ncand += (min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) ? 1 : 0;
       if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
     }
@@ -374,15 +352,15 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
       const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
 #pragma unroll
       for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
-      p.glabel[g] = label;
+      glabel[g] = label;
     }
     const int g_now = g;
     // next group of this thread: its summary loads overlap the bookkeeping below
     g += span;
     if (g < n_groups) {
-      const float4* src = reinterpret_cast<const float4*>(p.gsum + g);
+      const float4* src = reinterpret_cast<const float4*>(gsum + g);
       a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-      prev = first_iter ? -1 : p.glabel[g];
+      prev = first_iter ? -1 : glabel[g];
     }
     // cached sums, one round per distinct label in the warp (usually one)
     unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
@@ -398,31 +376,58 @@ __global__ void __launch_bounds__(kThreads) lloyd_classify_kernel(const Classify
         sum[d] = ((long long)hi << 15) + (long long)lo;
       }
       const unsigned int hits = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) {
-        atomicAdd(&s_acc[L * 4 + 0], (unsigned long long)sum[0]);
-        atomicAdd(&s_acc[L * 4 + 1], (unsigned long long)sum[1]);
-        atomicAdd(&s_acc[L * 4 + 2], (unsigned long long)sum[2]);
-        atomicAdd(&s_acc[L * 4 + 3], (unsigned long long)__popc(hits) * kGroup);
-      }
+      // the warp's private slice when there is one (plain read-modify-write): 64-bit
+      // shared-memory atomics are compare-and-swap loops and collapse under contention
+      if (lane == 0) acc_add<kPrivate>(s_acc, L, sum[0], sum[1], sum[2], (unsigned int)__popc(hits) * kGroup);
       todo &= ~hits;
     }
-    // ---- the rest goes to the per-point kernel --------------------------------------------
+    // the rest goes to the per-point pass: collected in shared memory, handed to the global
+    // worklist with one atomic per kClassifyList entries (not one per trip: the round trip
+    // of a global atomic would dominate this pass)
     const unsigned int heavy = __ballot_sync(0xffffffffu, valid && label < 0);
-    if (heavy) {
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(p.work_count, __popc(heavy));
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (valid && label < 0) p.worklist[slot + __popc(heavy & ((1u << lane) - 1u))] = g_now;
+    if (lane == 0) s_wcnt[tid >> 5] = __popc(heavy);
+    __syncthreads();
+    int before = *s_wbase;  // entries already in the shared list
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) before += (w < (tid >> 5)) ? s_wcnt[w] : 0;
+    if (valid && label < 0) s_list[before + __popc(heavy & ((1u << lane) - 1u))] = g_now;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = *s_wbase;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_wcnt[w];
+      *s_wbase = tot;
+    }
+    __syncthreads();
+    const bool last_trip = base + span >= n_groups;
+    if (last_trip || *s_wbase + kThreads > kClassifyList) {  // CTA-uniform
+      const int cnt = *s_wbase;
+      __syncthreads();
+      if (tid == 0) {
+        s_wcnt[0] = cnt ? atomicAdd(work_count, cnt) : 0;
+        *s_wbase = 0;
+      }
+      __syncthreads();
+      const int dst = s_wcnt[0];
+      for (int i = tid; i < cnt; i += kThreads) worklist[dst + i] = s_list[i];
+      __syncthreads();
     }
   }
-  n_chg = __reduce_add_sync(0xffffffffu, n_chg);
-  if (lane == 0 && n_chg) atomicAdd(&s_changed, n_chg);
+}
+
+// Grid-wide barrier of a cooperatively launched (fully resident) grid: a monotonically
+// increasing arrival counter, one generation per use.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter) {
   __syncthreads();
-  for (int i = tid; i < p.kpad * 4; i += kThreads) {
-    const unsigned long long v = s_acc[i];
-    if (v) atomicAdd(&p.acc[i], v);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int arrived = atomicAdd(counter, 1u) + 1u;
+    const unsigned int target = (arrived + gridDim.x - 1u) / gridDim.x * gridDim.x;
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) {
+    }
+    __threadfence();
   }
-  if (tid == 0 && s_changed) atomicAdd(&p.acc[p.kpad * 4 + 0], (unsigned long long)s_changed);
+  __syncthreads();
 }
 
 struct FinalParams {
@@ -756,6 +761,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+#ifdef MDKM_TIMING
+  if (blockIdx.x == 0 && tid == 0) p.st->t_start = globaltimer_ns();
+  if (tid == 0) atomicMax(&p.st->t_classify_start, globaltimer_ns());  // latest CTA entry
+#endif
   const int n_slices = kPrivate ? kWarps : 1;
   unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
   if (tid == 0) {
@@ -786,8 +795,29 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
   // each warp owns a CONTIGUOUS range of groups: consecutive groups are neighbours in the
   // raster, so label runs are long and the register accumulators below rarely flush
-  // (with a worklist the "groups" below are positions in the list)
-  const int n_items = p.worklist ? *p.work_count : n_groups;
+  LabT* labels = reinterpret_cast<LabT*>(p.labels);
+  unsigned int n_chg = 0, n_ref = 0;
+  // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
+  mbar_wait(&s_bar, 0);
+  {
+    __shared__ int s_wcnt[kWarps];
+    __shared__ int s_wbase;
+    // the ring is idle during pass 1: its first bytes stage the worklist entries
+    static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
+    classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
+                                    4.0f * thresh, first_iter, s_acc, s_wcnt, &s_wbase,
+                                    reinterpret_cast<int*>(s_ring), n_chg);
+  }
+#ifdef MDKM_TIMING
+  if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
+#endif
+  grid_barrier(p.grid_bar);  // the worklist is complete
+#ifdef MDKM_TIMING
+  if (blockIdx.x == 0 && tid == 0) p.st->t_classify_done = globaltimer_ns();
+#endif
+  // ---- pass 2: the groups a cluster boundary crosses, point by point -----------------------
+  // (the "groups" below are positions in the worklist)
+  const int n_items = *reinterpret_cast<volatile int*>(p.work_count);
   const int per_warp = (n_items + (int)gridDim.x * kWarps - 1) / ((int)gridDim.x * kWarps);
   const int g0 = ((int)blockIdx.x * kWarps + warp) * per_warp;
   const int g_end = min(n_items, g0 + per_warp);
@@ -796,7 +826,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const uint32_t ring_a = smem_u32(s_ring) + warp * (kStages * kStageB);
   const uint32_t gbar_a = smem_u32(s_gbar) + warp * (kStages * 8);
   const float* pts = p.pts;
-  LabT* labels = reinterpret_cast<LabT*>(p.labels);
   int g_fetch = g0;
 
   // one elected lane fetches group `gf` into `stage`: the 1536-byte xyz block and its labels
@@ -811,14 +840,15 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // group index of the three stages in flight (warp-uniform registers)
   int gq0 = 0, gq1 = 0, gq2 = 0;
   static_assert(kStages == 3, "the group-index queue below is written for three stages");
-  if (g_fetch < g_end) { gq0 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(0, gq0); }
+  // (the list was written by other CTAs of this very kernel: read it through L2, not the
+  // non-coherent path)
+  if (g_fetch < g_end) { gq0 = __ldcg(wl + g_fetch); issue(0, gq0); }
   ++g_fetch;
-  if (g_fetch < g_end) { gq1 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(1, gq1); }
+  if (g_fetch < g_end) { gq1 = __ldcg(wl + g_fetch); issue(1, gq1); }
   ++g_fetch;
-  if (g_fetch < g_end) { gq2 = wl ? __ldg(wl + g_fetch) : g_fetch; issue(2, gq2); }
+  if (g_fetch < g_end) { gq2 = __ldcg(wl + g_fetch); issue(2, gq2); }
   ++g_fetch;
-  int g_pref = (wl && g_fetch < g_end) ? __ldg(wl + g_fetch) : g_fetch;  // list entry of the next fetch
-  mbar_wait(&s_bar, 0);
+  int g_pref = g_fetch < g_end ? __ldcg(wl + g_fetch) : 0;  // list entry of the next fetch
 
   // run accumulator: while consecutive groups of this warp carry one label, every lane just
   // adds its own four fixed-point coordinates (int32, no cross-lane traffic); the run is
@@ -838,7 +868,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       run_groups = 0;
     }
   };
-  unsigned int n_chg = 0, n_ref = 0;
   int stage = 0;
   uint32_t parity = 0;
 
@@ -867,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     gq2 = g_pref;
     if (g_fetch < g_end) issue(stage, g_pref);
     g_fetch += stride;
-    g_pref = (wl && g_fetch < g_end) ? __ldg(wl + g_fetch) : g_fetch;
+    g_pref = g_fetch < g_end ? __ldcg(wl + g_fetch) : 0;
     if (++stage == kStages) {
       stage = 0;
       parity ^= 1u;
@@ -905,7 +934,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
       uniform = __all_sync(0xffffffffu, (lab[0] == l0) && (lab[1] == l0) && (lab[2] == l0) && (lab[3] == l0));
     }
     // settled (one centroid owns the whole box): the classification pass takes over from here
-    if (p.glabel && lane == 0) p.glabel[g] = (full && ncand <= 1) ? lab[0] : -1;
+    if (lane == 0) p.glabel[g] = (full && ncand <= 1) ? lab[0] : -1;
     if (uniform) {
       if (l0 != wlab || run_groups == kRunMax) {  // warp-uniform
         flush_run();
@@ -975,7 +1004,13 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __shared__ bool s_is_last;
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_is_last = (atomicAdd(&p.st->ticket, 1u) == gridDim.x - 1);
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&p.st->ticket, 1u);
+    s_is_last = (t == gridDim.x - 1);
+#ifdef MDKM_TIMING
+    if (s_is_last) p.st->t_last_done = globaltimer_ns();
+#endif
+  }
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
@@ -985,6 +1020,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   }
   if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
   lloyd_update_body(p.upd);
+#ifdef MDKM_TIMING
+  __syncthreads();
+  if (tid == 0) p.st->t_update_done = globaltimer_ns();
+#endif
 }
 
 // Builds the centroid table from K x 3 float64 centroids in ORIGINAL coordinates.

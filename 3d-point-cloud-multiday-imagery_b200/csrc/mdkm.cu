@@ -422,8 +422,6 @@ struct KmBuffers {
   bool wide;     // uint16 labels
   bool priv;     // per-warp accumulator slices in shared memory
   StepKernel step_fn;
-  int classify_grid;
-  size_t classify_smem;
   long long n_groups;
 };
 
@@ -457,16 +455,8 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
   OK(ensure(h, h->partials, (size_t)std::max(kb.final_grid, h->sm_count * 8) * 8 + 16));
-  // group summaries + classification pass
+  // group summaries for the classification pass
   kb.n_groups = cap / kGroup;
-  kb.classify_smem = (size_t)kb.kpad * (16 + 32);
-  kb.classify_grid = grid_for(h, (kb.n_groups + kThreads - 1) / kThreads, 8);
-  if (kb.wide)
-    CU(cudaFuncSetAttribute(lloyd_classify_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kb.classify_smem));
-  else
-    CU(cudaFuncSetAttribute(lloyd_classify_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kb.classify_smem));
   OK(ensure(h, h->gsum, (size_t)kb.n_groups * sizeof(GroupSummary)));
   OK(ensure(h, h->glabel, (size_t)kb.n_groups));
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
@@ -521,23 +511,14 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
     sp.px = h->px;
     if (h->n_ranks == 1) sp.px.n_ranks = 1;
   }
-  // pass 1: settle whole groups from their summaries; the rest lands in the worklist
+  // pass 1 (inside the kernel): whole groups settled from their summaries; the rest lands in
+  // the worklist that pass 2 streams point by point
   int* work_count = h->worklist.p + kb.n_groups;
-  ClassifyParams cp{};
-  cp.gsum = reinterpret_cast<const GroupSummary*>(h->gsum.p);
-  cp.n = h->n;
-  cp.labels = h->labels.p;
-  cp.glabel = h->glabel.p;
-  cp.worklist = h->worklist.p;
-  cp.work_count = work_count;
-  cp.table = h->table.p;
-  cp.acc = h->acc.p;
-  cp.st = h->d_status;
-  cp.k = kb.k; cp.kpad = kb.kpad;
-  cp.ignore_status = ignore_status;
+  sp.gsum = reinterpret_cast<const GroupSummary*>(h->gsum.p);
   sp.worklist = h->worklist.p;
   sp.work_count = work_count;
   sp.glabel = h->glabel.p;
+  sp.grid_bar = &h->d_status->grid_bar;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->prof) {
     while ((int)h->prof_ev.size() < h->prof_used + 2) {
@@ -549,16 +530,11 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
     e1 = h->prof_ev[h->prof_used++];
     CU(cudaEventRecord(e0, h->stream));
   }
-  if (h->n > 0) {
-    if (kb.wide)
-      lloyd_classify_kernel<unsigned short><<<kb.classify_grid, kThreads, kb.classify_smem, h->stream>>>(cp);
-    else
-      lloyd_classify_kernel<unsigned char><<<kb.classify_grid, kThreads, kb.classify_smem, h->stream>>>(cp);
-    ++h->launches;
-  }
-  kb.step_fn<<<kb.step_grid, kThreads, kb.step_smem, h->stream>>>(sp);
+  // cooperative launch: the grid barrier between the two passes needs every CTA resident
+  void* args[] = {&sp};
+  CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kb.step_fn), dim3(kb.step_grid), dim3(kThreads), args,
+                                 kb.step_smem, h->stream));
   ++h->launches;
-  CU(cudaGetLastError());
   if (!fuse_update) CU(cudaMemsetAsync(work_count, 0, 4, h->stream));
   if (h->prof) CU(cudaEventRecord(e1, h->stream));
   return MDKM_OK;
@@ -1222,6 +1198,12 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   OK(sync_small(h));
   const DevStatus& fin = h->h_status[0];
   h->epoch_base = fin.epoch;
+#ifdef MDKM_TIMING
+  fprintf(stderr, "[mdkm timing] last iteration: latest CTA entry +%.1f us | latest end of pass 1 +%.1f us | after grid barrier +%.1f us | last CTA done +%.1f us | update done +%.1f us\n",
+          ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3, ((double)fin.t_first_done - (double)fin.t_start) * 1e-3,
+          (fin.t_classify_done - fin.t_start) * 1e-3, (fin.t_last_done - fin.t_start) * 1e-3,
+          (fin.t_update_done - fin.t_start) * 1e-3);
+#endif
   if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "peer exchange of the partial sums timed out (a rank is missing)");
   if (n_iter_out) *n_iter_out = fin.iter;
   if (inertia_out) *inertia_out = fin.inertia;
