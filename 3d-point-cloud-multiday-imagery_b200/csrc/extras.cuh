@@ -19,19 +19,16 @@ namespace mdkm {
 struct RelocParams {
   const float* pts;  // blocked cloud
   long long n;
-  const void* labels;
+  const int* labels;   // int32, reference point order
   const unsigned char* table;
   unsigned long long* scratch;
   unsigned long long* acc;
   long long rank_offset;
   FrameF f;
-  int wide, k, kpad, round;
+  int k, kpad, round;
 };
 
-__device__ __forceinline__ int reloc_label(const RelocParams& p, long long i) {
-  return p.wide ? (int)reinterpret_cast<const unsigned short*>(p.labels)[i]
-                : (int)reinterpret_cast<const unsigned char*>(p.labels)[i];
-}
+__device__ __forceinline__ int reloc_label(const RelocParams& p, long long i) { return p.labels[i]; }
 
 __device__ __forceinline__ bool reloc_taken(const RelocParams& p, long long gi) {
   for (int t = 0; t < p.round; ++t)

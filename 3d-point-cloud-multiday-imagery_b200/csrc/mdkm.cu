@@ -18,6 +18,7 @@
 #include "extras.cuh"
 #include "levelling.cuh"
 #include "lloyd.cuh"
+#include "mirror.cuh"
 #include "nccl_shim.h"
 #include "seeding.cuh"
 #include "unproject.cuh"
@@ -78,6 +79,11 @@ struct mdkm_handle {
   DevBuf<int> glabel;                // per group: uniform label or -1
   DevBuf<int> worklist;              // [n_groups] + 1 counter at the end
   bool summary_ok = false;
+  // tile-ordered mirror of the cloud (mirror.cuh): what the Lloyd iterations stream
+  DevBuf<float> tpts;
+  DevBuf<unsigned int> cell_counts;
+  DevBuf<long long> cell_offsets;
+  float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
@@ -325,6 +331,7 @@ int compute_frame(mdkm_handle* h) {
     }
   }
   h->n_total = ntot;
+  for (int i = 0; i < 6; ++i) h->bounds[i] = mm[i];
   for (int d = 0; d < 3; ++d) {
     double lo = mm[d], hi = mm[3 + d];
     if (!(lo <= hi)) { lo = 0.0; hi = 0.0; }  // empty cloud
@@ -425,6 +432,43 @@ struct KmBuffers {
   long long n_groups;
 };
 
+// Re-orders the resident cloud by cells of an x-y grid (about 256 points per cell) into
+// h->tpts; see mirror.cuh.  Once per (cloud, frame).
+int build_mirror(mdkm_handle* h) {
+  const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
+  OK(ensure(h, h->tpts, (size_t)cap * 3));
+  CU(cudaMemsetAsync(h->tpts.p + (cap - kGroup) * 3, 0, kBlockFloats * 4, h->stream));  // tail of the last block
+  if (h->n == 0) return MDKM_OK;
+  const double xr = std::max((double)h->bounds[3] - (double)h->bounds[0], 1e-30);
+  const double yr = std::max((double)h->bounds[4] - (double)h->bounds[1], 1e-30);
+  const double target = std::max(1.0, (double)h->n / 256.0);
+  long long gx = (long long)llround(sqrt(target * xr / yr));
+  gx = std::max<long long>(1, std::min<long long>(gx, 1 << 15));
+  long long gy = (long long)ceil(target / (double)gx);
+  gy = std::max<long long>(1, std::min<long long>(gy, 1 << 15));
+  if (!(xr > 1e-20)) gx = 1;
+  if (!(yr > 1e-20)) gy = 1;
+  MirrorGrid g{};
+  g.x0 = h->bounds[0]; g.y0 = h->bounds[1];
+  g.inv_cx = (float)((double)gx / xr);
+  g.inv_cy = (float)((double)gy / yr);
+  g.gx = (int)gx; g.gy = (int)gy;
+  const long long n_cells = gx * gy;
+  OK(ensure(h, h->cell_counts, (size_t)n_cells + 1));
+  OK(ensure(h, h->cell_offsets, (size_t)n_cells + 2));
+  CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));
+  const int grid = grid_for(h, (h->n + 1023) / 1024, 8);
+  mirror_count_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_counts.p);
+  scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, nullptr,
+                                                h->cell_offsets.p + n_cells + 1);
+  CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));  // now the arrival cursors
+  mirror_scatter_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_offsets.p, h->cell_counts.p,
+                                                          h->tpts.p);
+  h->launches += 3;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
 int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident: call mdkm_unproject or mdkm_set_points first");
   if (k < 1 || k > kMaxK) return fail(h, MDKM_ERR_INVALID, "k must be in [1, %d]", kMaxK);
@@ -461,8 +505,9 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   OK(ensure(h, h->glabel, (size_t)kb.n_groups));
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
   if (!h->summary_ok) {
+    OK(build_mirror(h));
     group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
-        h->pts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
+        h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
     ++h->launches;
     CU(cudaGetLastError());
     h->summary_ok = true;
@@ -497,7 +542,7 @@ bool can_fuse(const mdkm_handle* h) { return h->n_ranks == 1 || h->p2p_ok; }
 
 int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0) {
   StepParams sp{};
-  sp.pts = h->pts.p; sp.n = h->n;
+  sp.pts = h->tpts.p; sp.n = h->n;  // the tile-ordered mirror; labels / summaries / worklist follow its order
   sp.labels = h->labels.p;
   sp.table = h->table.p;
   sp.acc = h->acc.p;
@@ -575,6 +620,8 @@ int collect_profile(mdkm_handle* h) {
   return MDKM_OK;
 }
 
+int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_assign);
+
 // Empty-cluster relocation (sklearn/_k_means_common.pyx:167-211), sequenced from the host
 // while the Lloyd loop is paused.  All arithmetic on the device (extras.cuh).
 int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
@@ -583,9 +630,13 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
   OK(ensure(h, h->reloc, 8 + 2 * (size_t)kMaxK));
   CU(cudaMemsetAsync(h->reloc.p, 0, (8 + 2 * (size_t)kMaxK) * 8, h->stream));
   const long long rank_offset = h->rank_offset;  // global index of this rank's first point
+  // labels in the reference's order under the OLD centroids (the paused update has not touched
+  // the table yet): what the step just assigned, recomputed point by point
+  OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
+  OK(run_final(h, kb, h->labels32.p, /*force_assign=*/1));
   RelocParams rp{};
   rp.pts = h->pts.p; rp.n = h->n;
-  rp.labels = h->labels.p; rp.wide = kb.wide ? 1 : 0;
+  rp.labels = h->labels32.p;
   rp.table = h->table.p; rp.kpad = kb.kpad; rp.k = kb.k;
   rp.f = h->ff;
   rp.scratch = h->reloc.p;
@@ -694,6 +745,7 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
   release(h->gsum); release(h->glabel); release(h->worklist);
+  release(h->tpts); release(h->cell_counts); release(h->cell_offsets);
   release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
   release(h->d_seg_off); release(h->sel_hist); release(h->sel_targets);
   release(h->kpp_closest); release(h->kpp_cell); release(h->kpp_blk); release(h->kpp_prefix);
@@ -1185,7 +1237,10 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       labels_dev = h->labels32.p;
     }
   }
-  OK(run_final(h, kb, labels_dev, 0));
+  // labels in the reference's point order: always recomputed from the final centroids (the
+  // stored ones follow the mirror's order).  After a strict exit the table equals the one the
+  // last E-step used -- the sums are integers -- so this reproduces that step's labels exactly.
+  OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
   OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
   read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
   ++h->launches;
@@ -1254,10 +1309,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
       OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
       labels_dev = h->labels32.p;
     }
-    h->h_status[1] = st0;
-    h->h_status[1].strict = 1;
-    CU(cudaMemcpyAsync(&h->d_status->strict, &h->h_status[1].strict, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    OK(run_final(h, kb, labels_dev, 0));
+    OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
     if (labels_mem != MDKM_MEM_DEVICE && h->n > 0)
       CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
