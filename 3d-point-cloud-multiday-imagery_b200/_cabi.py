@@ -62,6 +62,7 @@ SIGNATURES = {
     "mdkm_predict": (c_int, [c_void_p, c_int, POINTER(c_double), c_void_p, c_int, POINTER(c_double)]),
     "mdkm_kmeans_plusplus": (c_int, [c_void_p, c_int, c_int64, POINTER(c_double), c_int,
                                      POINTER(c_double), POINTER(c_int64)]),
+    "mdkm_drop_caches": (c_int, [c_void_p]),
     "mdkm_profile_enable": (c_int, [c_void_p, c_int]),
     "mdkm_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int), POINTER(c_int)]),
 }

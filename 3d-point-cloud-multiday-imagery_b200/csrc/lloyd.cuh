@@ -860,9 +860,14 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   int wlab = -1;
   auto flush_run = [&]() {
     if (run_groups > 0) {
-      const int sx = __reduce_add_sync(0xffffffffu, rx);
-      const int sy = __reduce_add_sync(0xffffffffu, ry);
-      const int sz = __reduce_add_sync(0xffffffffu, rz);
+      // a lane's partial can reach 2^30 and the points of a run usually lie on one side of the
+      // origin: the warp total does not fit 32 bits, so the two halves are reduced separately
+      const long long sx = ((long long)__reduce_add_sync(0xffffffffu, rx >> 15) << 15) +
+                           (long long)__reduce_add_sync(0xffffffffu, rx & 0x7fff);
+      const long long sy = ((long long)__reduce_add_sync(0xffffffffu, ry >> 15) << 15) +
+                           (long long)__reduce_add_sync(0xffffffffu, ry & 0x7fff);
+      const long long sz = ((long long)__reduce_add_sync(0xffffffffu, rz >> 15) << 15) +
+                           (long long)__reduce_add_sync(0xffffffffu, rz & 0x7fff);
       if (lane == 0) acc_add<kPrivate>(s_acc, wlab, sx, sy, sz, (unsigned int)run_groups * kGroup);
       rx = ry = rz = 0;
       run_groups = 0;

@@ -1554,6 +1554,12 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
   return MDKM_OK;
 }
 
+int mdkm_drop_caches(mdkm_handle* h) {
+  if (!h) return MDKM_ERR_INVALID;
+  h->summary_ok = false;  // tile-ordered mirror + group summaries are rebuilt by the next fit
+  return MDKM_OK;
+}
+
 int mdkm_profile_enable(mdkm_handle* h, int on) {
   if (!h) return MDKM_ERR_INVALID;
   h->prof = on != 0;

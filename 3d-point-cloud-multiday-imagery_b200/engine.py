@@ -357,6 +357,11 @@ class Engine:
             centers.ctypes.data_as(POINTER(c_double)), idx.ctypes.data_as(POINTER(c_int64))))
         return centers, idx
 
+    def drop_caches(self):
+        """Forget the tile-ordered mirror and the group summaries of the resident cloud (the next
+        fit rebuilds them)."""
+        self._check(self._lib.mdkm_drop_caches(self._h))
+
     # -- profiling -----------------------------------------------------------------------
     def profile(self, on: bool):
         self._check(self._lib.mdkm_profile_enable(self._h, 1 if on else 0))

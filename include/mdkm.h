@@ -192,6 +192,12 @@ int mdkm_predict(mdkm_handle* h, int k, const double* centroids, int32_t* labels
 int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const double* rand_vals,
                          int n_local_trials, double* centers_out, int64_t* indices_out);
 
+/* The first fit on a cloud builds two acceleration structures that later fits on the same
+ * cloud reuse: the tile-ordered mirror of the points and the per-group summaries (box +
+ * fixed-point sums).  mdkm_drop_caches discards them, so that the next fit pays for them again
+ * (bench.py times every fit that way). */
+int mdkm_drop_caches(mdkm_handle* h);
+
 /* Timing aid for bench.py: when enabled, CUDA events bracket every launch of the
  * assignment+accumulate kernel inside mdkm_fit; mdkm_profile_read returns their summed
  * duration and count and resets both. */

@@ -214,6 +214,29 @@ def test_single_step_exact_ties_lowest_index(engine):
     assert labels.tolist() == [0] * 5 and counts.tolist() == [5, 0, 0]
 
 
+def test_long_one_sided_runs_do_not_overflow(engine):
+    """Regression: boundary groups that all carry one label form long runs whose fixed-point
+    coordinates share a sign; their warp totals exceed 32 bits (bug found at config-3 size)."""
+    W, H = 4096, 1536
+    ys, xs = np.divmod(np.arange(W * H, dtype=np.int64), W)
+    X = np.stack([xs, ys, np.zeros_like(xs)], axis=1).astype(np.float32)
+    engine.set_points(X)
+    C = np.array([[2047.5, 255.5, 0.0], [2047.5, 767.5, 0.0], [2047.5, 1279.5, 0.0]])
+    for _ in range(2):  # cold and with the cached mirror / summaries
+        labels, sums, counts, _ = engine.lloyd_step(C)
+        ref = np.minimum(ys // 512, 2)
+        np.testing.assert_array_equal(labels, ref.astype(np.int32))
+        np.testing.assert_array_equal(counts, np.bincount(ref, minlength=3))
+        for d in range(2):
+            np.testing.assert_array_equal(sums[:, d], np.bincount(ref, weights=X[:, d].astype(np.float64), minlength=3))
+    init = C + [[0, 40, 0], [0, -30, 0], [0, 25, 0]]
+    r = engine.fit(init, max_iter=6, tol=0.0)
+    ref = KO.kmeans_fit(X.astype(np.float64), init, max_iter=6, tol=0.0)
+    assert r["n_iter"] == ref["n_iter"] and r["n_relocations"] == 0
+    np.testing.assert_array_equal(r["labels"], ref["labels"])
+    np.testing.assert_allclose(r["centers"], ref["centers"], rtol=1e-7, atol=1e-6)  # z is constant: no std scale
+
+
 def test_generic_float_cloud_random_order(engine):
     rs = np.random.RandomState(4)
     X32 = np.concatenate([rs.normal(c, 3.0, (5000, 3)) for c in rs.uniform(-1e3, 1e3, size=(9, 3))]).astype(np.float32)
