@@ -81,6 +81,7 @@ struct mdkm_handle {
   bool summary_ok = false;
   // tile-ordered mirror of the cloud (mirror.cuh): what the Lloyd iterations stream
   DevBuf<float> tpts;
+  int raster_w = 0;  // width of the raster the cloud was unprojected from (0: generic cloud)
   DevBuf<unsigned int> cell_counts;
   DevBuf<long long> cell_offsets;
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
@@ -432,17 +433,25 @@ struct KmBuffers {
   long long n_groups;
 };
 
-// Re-orders the resident cloud by cells of an x-y grid (about 256 points per cell) into
-// h->tpts; see mirror.cuh.  Once per (cloud, frame).
+// Re-orders the resident cloud, segment by segment, by the cells of an x-y grid (about 256
+// points per cell) into h->tpts; see mirror.cuh.  Once per (cloud, frame).
 int build_mirror(mdkm_handle* h) {
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->tpts, (size_t)cap * 3));
   CU(cudaMemsetAsync(h->tpts.p + (cap - kGroup) * 3, 0, kBlockFloats * 4, h->stream));  // tail of the last block
   if (h->n == 0) return MDKM_OK;
+  // segments: the days of the unprojected range (merged into one when there are too many)
+  std::vector<long long> seg = h->seg_off;
+  if (seg.size() < 2 || seg.back() != h->n || (int)seg.size() - 1 > kMirrorMaxSeg) seg.assign({0, h->n});
+  const int n_seg = (int)seg.size() - 1;
+  OK(ensure(h, h->d_seg_off, (size_t)n_seg + 1));
+  CU(cudaMemcpyAsync(h->d_seg_off.p, seg.data(), (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   const double xr = std::max((double)h->bounds[3] - (double)h->bounds[0], 1e-30);
   const double yr = std::max((double)h->bounds[4] - (double)h->bounds[1], 1e-30);
-  const double target = std::max(1.0, (double)h->n / 256.0);
+  const double target = std::max(1.0, (double)h->n / 256.0);  // cells (each holds points of every segment)
   long long gx = (long long)llround(sqrt(target * xr / yr));
+  // raster clouds: cells 16 pixels wide, so that every row adds a 64-byte run to a cell
+  if (h->raster_w > 0) gx = (long long)ceil(xr / 16.0);
   gx = std::max<long long>(1, std::min<long long>(gx, 1 << 15));
   long long gy = (long long)ceil(target / (double)gx);
   gy = std::max<long long>(1, std::min<long long>(gy, 1 << 15));
@@ -453,14 +462,27 @@ int build_mirror(mdkm_handle* h) {
   g.inv_cx = (float)((double)gx / xr);
   g.inv_cy = (float)((double)gy / yr);
   g.gx = (int)gx; g.gy = (int)gy;
+  g.n_seg = n_seg;
+  g.seg_off = h->d_seg_off.p;
   const long long n_cells = gx * gy;
+  // bands of rows: about 32 groups of every segment per band
+  long long max_groups = 1;
+  for (int sgm = 0; sgm < n_seg; ++sgm)
+    max_groups = std::max(max_groups, (seg[sgm + 1] + kGroup - 1) / kGroup - (seg[sgm] + kGroup - 1) / kGroup + 1);
+  g.gpb = 32;
+  const long long n_bands = (max_groups + g.gpb - 1) / g.gpb;
+  g.n_virtual = n_bands * n_seg * g.gpb;
   OK(ensure(h, h->cell_counts, (size_t)n_cells + 1));
   OK(ensure(h, h->cell_offsets, (size_t)n_cells + 2));
   CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));
   const int grid = grid_for(h, (h->n + 1023) / 1024, 8);
   mirror_count_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_counts.p);
-  scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, nullptr,
-                                                h->cell_offsets.p + n_cells + 1);
+  const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
+  OK(ensure(h, h->partials, (size_t)std::max(n_tiles, h->sm_count * 8) * 8 + 16));
+  long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
+  mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
+  mirror_scan_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, tile_sums);
+  ++h->launches;
   CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));  // now the arrival cursors
   mirror_scatter_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_offsets.p, h->cell_counts.p,
                                                           h->tpts.p);
@@ -864,6 +886,7 @@ int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int
   OK(zero_tail(h));
   h->seg_off.assign({0, (long long)n});
   h->seg_whole = true;
+  h->raster_w = 0;
   h->have_points = true;
   h->frame_ok = false;
   OK(compute_frame(h));
@@ -1095,6 +1118,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
     h->seg_whole = true;
   }
   h->n = n_out;
+  h->raster_w = W;
   OK(zero_tail(h));
   h->have_points = true;
   h->frame_ok = false;
