@@ -287,7 +287,7 @@ def run_mine(args):
     traffic, traffic_src = measured_traffic(args.config)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "one Lloyd iteration = lloyd_classify_kernel + lloyd_step_kernel (update fused in its tail)",
+                "kernel": "lloyd_step_kernel = one Lloyd iteration (classification pass, grid barrier, per-point pass, fused update)",
                 "avg_launch_ms": step_avg_ms,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT_ITER * n_local, "peak_source": peak_src,
                 "note": "achieved = 16 B x points / measured iteration time; the kernels move fewer bytes than "
