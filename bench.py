@@ -227,18 +227,14 @@ def run_mine(args):
     del hm
     torch.cuda.empty_cache()
 
-    # identical initial centroids on every rank: k points of rank 0's cloud
-    init = torch.zeros((k, 3), dtype=torch.float64, device=f"cuda:{local}")
-    if rank == 0:
-        idx = np.sort(np.random.RandomState(args.seed).choice(n_local, k, replace=False))
-        init.copy_(torch.from_numpy(eng.gather_points(idx).astype(np.float64)))
-    if world > 1:
-        dist.broadcast(init, src=0)
-    init_np = init.cpu().numpy()
+    # identical initial centroids on every rank: k points of the global cloud (gather_points is
+    # a collective with global indices, so every rank makes the same call)
     n_tot_t = torch.tensor([n_local], dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(n_tot_t)
     n_total = int(n_tot_t.item())
+    idx = np.sort(np.random.RandomState(args.seed).choice(n_total, k, replace=False))
+    init_np = eng.gather_points(idx).astype(np.float64)
 
     def barrier():
         if world > 1:

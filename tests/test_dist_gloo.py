@@ -30,6 +30,9 @@ def _worker(rank, world, port, q):
         # 1. unique-id broadcast: every rank ends with rank 0's 128 bytes
         uid = d.exchange_unique_id(lambda: bytes(range(128)), rank, world)
         assert uid == bytes(range(128))
+        # 1b. all-gather of equal-length byte strings in rank order (CUDA IPC handles travel this way)
+        got = d.gather_bytes(bytes([rank + 1]) * 64, rank, world)
+        assert got == b"".join(bytes([r + 1]) * 64 for r in range(world))
         # 2. sharding + exchange of fixed-point partial sums is exact and order independent:
         #    each rank quantises its shard like the kernels do, int64 sums are all-reduced.
         rs = np.random.RandomState(0)
