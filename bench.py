@@ -40,12 +40,16 @@ CONFIGS = {
     "c4": (12, 4096, 4096, 1024, 10),
     "c5": (30, 4096, 4096, 32, 300),
 }
+# relative tolerance of the convergence test (sklearn's tol); config 5 is the time-to-solution run
+TOL = {"c5": 1e-4}
 
 
 def workload_name(cfg, n_gpus):
     D, H, W, k, it = CONFIGS[cfg]
+    tol = TOL.get(cfg, 0.0)
+    iters = f"{it} Lloyd iters, tol=0" if tol == 0 else f"max_iter={it}, tol={tol:g} (time to solution)"
     return (f"{cfg}: synthetic {D}-day {H}x{W} height-map stack per GPU (~{D*H*W*0.975/1e6:.1f}M pts/GPU), "
-            f"k={k}, {it} Lloyd iters, tol=0, {n_gpus} GPU(s)")
+            f"k={k}, {iters}, {n_gpus} GPU(s)")
 
 
 class ClockSampler(threading.Thread):
@@ -132,14 +136,14 @@ def cpu_sample(pkg, cfg, seed=0):
     return P, init, k, iters, f"1 of {D} days of the {H}x{W} stack ({P.shape[0]} pts), k={k}, {iters} iters, float64"
 
 
-def time_cpu_reference(P, init, iters, repeats):
+def time_cpu_reference(P, init, iters, repeats, tol=0.0):
     """Returns (best pts*it/s, kind, cores).  sklearn when importable, else the C port."""
     from oracle import sklearn_ref
 
     if sklearn_ref.available():
         best = 0.0
         for _ in range(repeats):
-            r = sklearn_ref.fit(P, init, max_iter=iters, tol=0.0)
+            r = sklearn_ref.fit(P, init, max_iter=iters, tol=tol)
             best = max(best, P.shape[0] * r["n_iter"] / r["wall_s"])
         return best, "reference", sklearn_ref.n_threads()
     from oracle import c_oracle, kmeans_oracle as KO
@@ -168,12 +172,12 @@ def run_reference(args):
 
     kind = "reference" if sklearn_ref.available() else "port"
     for _ in range(args.warmup):
-        time_cpu_reference(P, init, iters, 1)
+        time_cpu_reference(P, init, iters, 1, TOL.get(args.config, 0.0))
     t0 = time.perf_counter()
     total = 0.0
     cores = 1
     for _ in range(args.steps):
-        v, kind, cores = time_cpu_reference(P, init, iters, 1)
+        v, kind, cores = time_cpu_reference(P, init, iters, 1, TOL.get(args.config, 0.0))
         total += P.shape[0] * iters / v
     wall = time.perf_counter() - t0
     value = P.shape[0] * iters * args.steps / total
@@ -246,7 +250,7 @@ def run_mine(args):
         # group summaries) are rebuilt inside the timed region, nothing is carried over
         if not args.keep_caches:
             eng.drop_caches()
-        return eng.fit(init_np, max_iter=iters, tol=0.0, want_labels=False)
+        return eng.fit(init_np, max_iter=iters, tol=TOL.get(args.config, 0.0), want_labels=False)
 
     # ---- kernel-resident number: K fits over resident points --------------------------------
     for _ in range(args.warmup):
@@ -292,7 +296,8 @@ def run_mine(args):
 
     # ---- end to end through the public API: pinned host rasters in, host results out ------------
     def one_e2e():
-        return pkg.fuse_multiday_kmeans(hm_host, n_clusters=k, init=init_np, max_iter=iters, tol=0.0,
+        return pkg.fuse_multiday_kmeans(hm_host, n_clusters=k, init=init_np, max_iter=iters,
+                                        tol=TOL.get(args.config, 0.0),
                                         engine=eng, stack_shape=(D * world, H, W), pix_begin=pix0)
 
     e2e = None
@@ -319,7 +324,7 @@ def run_mine(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         P, init_c, _, it_c, sample = cpu_sample(pkg, args.config, args.seed)
-        v, kind, cores = time_cpu_reference(P, init_c, it_c, 2)
+        v, kind, cores = time_cpu_reference(P, init_c, it_c, 2, TOL.get(args.config, 0.0))
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
