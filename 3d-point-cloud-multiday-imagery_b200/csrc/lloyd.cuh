@@ -1,24 +1,33 @@
 // Lloyd k-means kernels for d = 3 on sm_100a.
 //
-//   lloyd_step_kernel   K2+K3 fused: nearest-centroid assignment + per-cluster sum/count
-//                       (replaces sklearn/cluster/_k_means_lloyd.pyx:168-218, one pass over
-//                        the points; the reference reaches it through KMeans.fit at
-//                        members/jasraj/land_use_classification/core.py:227-228)
-//   lloyd_update_kernel K4: centroid update, centre shift, convergence, next centroid table
-//                       (sklearn/cluster/_k_means_common.pyx:274-311, _kmeans.py:721-738)
-//   lloyd_final_kernel  final E-step when the exit was not strict + inertia + int32 labels
-//                       (sklearn/cluster/_kmeans.py:742-756, _k_means_common.pyx:94-124)
+//   lloyd_step_kernel   ONE kernel per Lloyd iteration (cooperative launch):
+//                         pass 1  classification: whole 128-point groups settled from their
+//                                 cached summaries (box + fixed-point sums), no point read;
+//                         --      grid barrier;
+//                         pass 2  the groups a cluster boundary crosses, point by point:
+//                                 nearest-centroid assignment + per-cluster sum / count
+//                                 (sklearn/cluster/_k_means_lloyd.pyx:168-218; the reference
+//                                 reaches it through KMeans.fit at
+//                                 members/jasraj/land_use_classification/core.py:227-228);
+//                         tail    the last CTA completes the sums (peer exchange over NVLink
+//                                 when there are several ranks) and runs the centroid update,
+//                                 centre shift, convergence test and next centroid table
+//                                 (_k_means_common.pyx:274-311, _kmeans.py:721-738).
+//   lloyd_update_kernel the update alone (NCCL exchange path, and after a relocation)
+//   lloyd_final_kernel  labels in the reference's point order from the final centroids +
+//                       inertia + int32 labels (_kmeans.py:742-756, _k_means_common.pyx:94-124)
+//   group_summary_kernel  the per-group summaries (once per cloud and frame)
 //
-// Work unit: a warp-group of 128 consecutive points = one 1536-byte block of the resident
-// cloud (common.cuh: x[128] y[128] z[128]), fetched with ONE 1-D TMA bulk copy.  Everything
-// inside a group is warp-synchronous: no CTA barrier in the streaming loop.
+// Work unit: a group of 128 consecutive points = one 1536-byte block of the blocked cloud
+// (common.cuh: x[128] y[128] z[128]); the step kernel streams the tile-ordered mirror
+// (mirror.cuh), where a group is compact in x and y.  In pass 2 a group is fetched with 1-D
+// TMA bulk copies and everything inside it is warp-synchronous: no CTA barrier in the loop.
 //
 // Numerics (DESIGN.md "Exactness"):
-//   * candidate pruning: the group's bounding box gives, for every centroid, a lower and an
-//     upper bound of the distance to any point of the group; a centroid whose lower bound
-//     exceeds the smallest upper bound (plus a margin covering every FP32 rounding involved)
-//     cannot be the nearest of any point in the group and is skipped.  Conservative, so the
-//     result is identical to brute force; on raster-ordered clouds it leaves 1-3 candidates.
+//   * candidate pruning / classification: d_j(x) - d_ref(x) is linear in x, so its minimum
+//     over a group's bounding box is a corner value; a centroid whose minimum gap exceeds a
+//     margin covering every FP32 rounding involved cannot be the nearest of any point of the
+//     group.  Conservative, so the result is identical to brute force.
 //   * distances: FP32 CUDA cores, expanded form  ||c'||^2 - 2 x'.c'  (3 FFMA per pair) in a
 //     frame whose origin makes pixel-grid coordinates exact.  A rigorous bound E on the
 //     FP32 error of that expression is carried with every centroid table; a point whose best
@@ -27,7 +36,8 @@
 //     rounding.
 //   * sums: coordinates are rounded once to a 2^-22-of-range fixed-point grid and summed as
 //     integers (warp REDUX -> shared int64 -> global int64).  Integer addition is
-//     associative, so the sums are bit-identical for any grid size, run, or number of GPUs.
+//     associative, so the sums are bit-identical for any point order, grid size, run, or
+//     number of GPUs.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
