@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(1024) mirror_scan_kernel(const unsigned int* c
 }
 
 // dst = offsets[cell] + (arrival rank inside the cell); copies x, y, z into the mirror.
+// One point per lane and round (four rounds per group): the lanes that share a cell hold
+// consecutive points of a raster row and get consecutive slots, so every store instruction
+// writes whole runs instead of 4-byte fragments.
 __global__ void __launch_bounds__(kThreads) mirror_scatter_kernel(const float* pts, long long n, MirrorGrid g,
                                                                   const long long* offsets, unsigned int* cursor,
                                                                   float* tpts) {
@@ -192,40 +195,28 @@ __global__ void __launch_bounds__(kThreads) mirror_scatter_kernel(const float* p
     int seg;
     const long long grp = mirror_group_of(g, s_off, v, seg);
     if (grp < 0) continue;  // warp-uniform
-    const float* blk = pts + grp * kBlockFloats + lane * 4;
-    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
-    const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w}, zs[4] = {vz.x, vz.y, vz.z, vz.w};
-    int cell[4];
-    mirror_cells4(g, s_off, seg, grp * kGroup + lane * 4, n, xs, ys, cell);
-    long long dst[4];
-    const bool same = cell[0] == cell[1] && cell[0] == cell[2] && cell[0] == cell[3];
-    if (__all_sync(0xffffffffu, same)) {
-      const unsigned int peers = __match_any_sync(0xffffffffu, cell[0]);
-      const int leader = __ffs(peers) - 1;
-      unsigned int base = 0;
-      if (cell[0] >= 0 && lane == leader) base = atomicAdd(&cursor[cell[0]], 4u * (unsigned int)__popc(peers));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      const long long d0 = (cell[0] >= 0 ? offsets[cell[0]] : 0) + base + 4 * __popc(peers & ((1u << lane) - 1u));
+    const float* blk = pts + grp * kBlockFloats;
+    float xs[4], ys[4], zs[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) dst[e] = d0 + e;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned int peers = __match_any_sync(0xffffffffu, cell[e]);
-        const int leader = __ffs(peers) - 1;
-        unsigned int base = 0;
-        if (cell[e] >= 0 && lane == leader) base = atomicAdd(&cursor[cell[e]], (unsigned int)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        dst[e] = (cell[e] >= 0 ? offsets[cell[e]] : 0) + base + __popc(peers & ((1u << lane) - 1u));
-      }
+    for (int r = 0; r < 4; ++r) {
+      xs[r] = __ldg(blk + r * 32 + lane);
+      ys[r] = __ldg(blk + kGroup + r * 32 + lane);
+      zs[r] = __ldg(blk + 2 * kGroup + r * 32 + lane);
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (cell[e] >= 0) {
-        float* q = tpts + pt_off(dst[e]);
-        q[0] = xs[e];
-        q[kGroup] = ys[e];
-        q[2 * kGroup] = zs[e];
+    for (int r = 0; r < 4; ++r) {
+      const long long i = grp * kGroup + r * 32 + lane;
+      const int cell = i < n ? mirror_cell(g, seg, xs[r], ys[r]) : -1;
+      const unsigned int peers = __match_any_sync(0xffffffffu, cell);
+      const int leader = __ffs(peers) - 1;
+      unsigned int base = 0;
+      if (cell >= 0 && lane == leader) base = atomicAdd(&cursor[cell], (unsigned int)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (cell >= 0) {
+        float* q = tpts + pt_off(offsets[cell] + base + __popc(peers & ((1u << lane) - 1u)));
+        q[0] = xs[r];
+        q[kGroup] = ys[r];
+        q[2 * kGroup] = zs[r];
       }
     }
   }
