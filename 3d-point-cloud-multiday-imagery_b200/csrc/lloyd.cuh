@@ -84,28 +84,49 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
 
 // Executed by all kThreads threads of ONE CTA: the stand-alone update kernel, or the last CTA
 // of a fused step kernel.  Reads the accumulators through L2 (they were produced by atomics).
+// It sits on the critical path of every iteration, so global round trips are kept to one: a
+// thread fetches the accumulator row and the old centroid of its cluster together, and the
+// five block-wide reductions share one pair of barriers.
 __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   DevStatus* st = u.st;
-  __shared__ double s_red[kThreads / 32];
+  __shared__ double s_red[5][kThreads / 32];
   __shared__ int s_nempty;
-  __shared__ unsigned long long s_maxcnt;  // (count << 20) | (kMaxK*... - j): argmax, first wins
+  __shared__ unsigned long long s_maxcnt;  // (count << 13) | (2 * kMaxK - 1 - j): argmax, first wins
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_nempty = 0;
     s_maxcnt = 0ull;
   }
   __syncthreads();
+  float4* fast = reinterpret_cast<float4*>(u.table);
+  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
+  // rows of this thread's first cluster (the only one when k <= kThreads), fetched up front
+  const bool have0 = tid < u.k;
+  ulonglong2 a0 = make_ulonglong2(0ull, 0ull), b0 = a0;
+  double4 old0 = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (have0) {
+    a0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4));
+    b0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4 + 2));
+    old0 = exact[tid];
+  }
   // empty clusters and the heaviest cluster (np.argmax: first maximum)
   int my_empty = 0;
   unsigned long long my_max = 0ull;
   for (int j = tid; j < u.k; j += kThreads) {
-    const unsigned long long cnt = __ldcg(&u.acc[j * 4 + 3]);
+    const unsigned long long cnt = j == tid ? b0.y : __ldcg(&u.acc[j * 4 + 3]);
     if (cnt == 0ull) ++my_empty;
     const unsigned long long key = (cnt << 13) | (unsigned long long)(kMaxK * 2 - 1 - j);
     my_max = key > my_max ? key : my_max;
   }
-  if (my_empty) atomicAdd(&s_nempty, my_empty);
-  atomicMax(&s_maxcnt, my_max);
+  my_empty = __reduce_add_sync(0xffffffffu, my_empty);
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_down_sync(0xffffffffu, my_max, o);
+    my_max = t > my_max ? t : my_max;
+  }
+  if ((tid & 31) == 0) {
+    if (my_empty) atomicAdd(&s_nempty, my_empty);
+    atomicMax(&s_maxcnt, my_max);
+  }
   __syncthreads();
   const int n_empty = s_nempty;
   if (n_empty > 0 && u.allow_pause) {
@@ -120,27 +141,26 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   }
   const int jmax = kMaxK * 2 - 1 - (int)(s_maxcnt & 0x1fffull);
 
-  float4* fast = reinterpret_cast<float4*>(u.table);
-  double4* exact = reinterpret_cast<double4*>(u.table + exact_offset(u.kpad));
-
   double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
   for (int j = tid; j < u.kpad; j += kThreads) {
     if (j < u.k) {
-      const double4 old = exact[j];
-      const unsigned long long cnt = __ldcg(&u.acc[j * 4 + 3]);
+      const bool first = j == tid;
+      const double4 old = first ? old0 : exact[j];
+      ulonglong2 a = first ? a0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4));
+      ulonglong2 b = first ? b0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4 + 2));
       double cx, cy, cz;
-      int src = j;
       bool raw = false;
-      if (cnt == 0ull) {
+      if (b.y == 0ull) {
         // sklearn/_k_means_common.pyx:289-293: copy of the heaviest cluster's row -- which is
         // still the un-averaged sum when that row comes later in the loop.
-        src = jmax;
+        a = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + jmax * 4));
+        b = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + jmax * 4 + 2));
         raw = jmax > j;
       }
-      const double sc = (double)__ldcg(&u.acc[src * 4 + 3]);
-      const double qx = (double)(long long)__ldcg(&u.acc[src * 4 + 0]) / u.fr.scale[0];
-      const double qy = (double)(long long)__ldcg(&u.acc[src * 4 + 1]) / u.fr.scale[1];
-      const double qz = (double)(long long)__ldcg(&u.acc[src * 4 + 2]) / u.fr.scale[2];
+      const double sc = (double)b.y;
+      const double qx = (double)(long long)a.x / u.fr.scale[0];
+      const double qy = (double)(long long)a.y / u.fr.scale[1];
+      const double qz = (double)(long long)b.x / u.fr.scale[2];
       if (!raw) {
         const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
         cx = qx * alpha;
@@ -167,15 +187,30 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
-  shift2 = block_sum_fixed(shift2, s_red);
-  m_cn = block_max(m_cn, s_red);
-  m_cx = block_max(m_cx, s_red);
-  m_cy = block_max(m_cy, s_red);
-  m_cz = block_max(m_cz, s_red);
   const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);
-  __syncthreads();
+  // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
+  for (int o = 16; o > 0; o >>= 1) {
+    shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
+    m_cn = fmax(m_cn, __shfl_down_sync(0xffffffffu, m_cn, o));
+    m_cx = fmax(m_cx, __shfl_down_sync(0xffffffffu, m_cx, o));
+    m_cy = fmax(m_cy, __shfl_down_sync(0xffffffffu, m_cy, o));
+    m_cz = fmax(m_cz, __shfl_down_sync(0xffffffffu, m_cz, o));
+  }
+  if ((tid & 31) == 0) {
+    const int w = tid >> 5;
+    s_red[0][w] = shift2; s_red[1][w] = m_cn; s_red[2][w] = m_cx; s_red[3][w] = m_cy; s_red[4][w] = m_cz;
+  }
+  __syncthreads();  // also: every thread has read its accumulator rows
   for (int i = tid; i < u.kpad * 4 + 8; i += kThreads) u.acc[i] = 0ull;
   if (tid == 0) {
+    shift2 = 0.0; m_cn = 0.0; m_cx = 0.0; m_cy = 0.0; m_cz = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      shift2 += s_red[0][w];
+      m_cn = fmax(m_cn, s_red[1][w]);
+      m_cx = fmax(m_cx, s_red[2][w]);
+      m_cy = fmax(m_cy, s_red[3][w]);
+      m_cz = fmax(m_cz, s_red[4][w]);
+    }
     // FP32 error bound of the fast distances (DESIGN.md "Exactness"): u = 2^-24
     const double ue = 5.9604644775390625e-08;
     const double E = ue * (4.0 * m_cn + 10.0 * (u.fr.halfrange[0] * m_cx + u.fr.halfrange[1] * m_cy +
