@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) group_summary_kernel(const float* pt
 // centroid owns its whole box.  In the first iteration every group is tested against the
 // centroid nearest to its box centre.  Settled groups add their cached sums to `s_acc` (the
 // warp's accumulator slice) and never touch their points; the others are appended to the
-// global worklist (staged in shared memory, one global atomic per kClassifyList entries).
+// global worklist (staged per warp in shared memory).
 constexpr int kClassifyList = 2048;  // shared-memory staging of the worklist (entries per CTA)
 
 template <bool kPrivate>
@@ -353,11 +353,11 @@ template <typename LabT, bool kPrivate>
 __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__ gsum, int n_groups,
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
-                                                bool first_iter, unsigned long long* s_acc, int* s_wcnt,
-                                                int* s_wbase, int* s_list, unsigned int& n_chg) {
+                                                bool first_iter, unsigned long long* s_acc, int* s_list,
+                                                unsigned int& n_chg) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) *s_wbase = 0;
-  __syncthreads();
+  int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
+  int w_count = 0;                                                         // warp-uniform
   const int span = (int)gridDim.x * kThreads;
   int g = (int)blockIdx.x * kThreads + tid;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
@@ -426,36 +426,21 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
       if (lane == 0) acc_add<kPrivate>(s_acc, L, sum[0], sum[1], sum[2], (unsigned int)__popc(hits) * kGroup);
       todo &= ~hits;
     }
-    // the rest goes to the per-point pass: collected in shared memory, handed to the global
-    // worklist with one atomic per kClassifyList entries (not one per trip: the round trip
-    // of a global atomic would dominate this pass)
+    // the rest goes to the per-point pass: every warp collects its groups in its own slice of
+    // shared memory and hands them to the global worklist with one atomic per flush (not one
+    // per trip: the round trip of a global atomic would dominate this pass) -- no CTA barrier
     const unsigned int heavy = __ballot_sync(0xffffffffu, valid && label < 0);
-    if (lane == 0) s_wcnt[tid >> 5] = __popc(heavy);
-    __syncthreads();
-    int before = *s_wbase;  // entries already in the shared list
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) before += (w < (tid >> 5)) ? s_wcnt[w] : 0;
-    if (valid && label < 0) s_list[before + __popc(heavy & ((1u << lane) - 1u))] = g_now;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = *s_wbase;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_wcnt[w];
-      *s_wbase = tot;
-    }
-    __syncthreads();
+    if (valid && label < 0) w_list[w_count + __popc(heavy & ((1u << lane) - 1u))] = g_now;
+    w_count += __popc(heavy);
     const bool last_trip = base + span >= n_groups;
-    if (last_trip || *s_wbase + kThreads > kClassifyList) {  // CTA-uniform
-      const int cnt = *s_wbase;
-      __syncthreads();
-      if (tid == 0) {
-        s_wcnt[0] = cnt ? atomicAdd(work_count, cnt) : 0;
-        *s_wbase = 0;
-      }
-      __syncthreads();
-      const int dst = s_wcnt[0];
-      for (int i = tid; i < cnt; i += kThreads) worklist[dst + i] = s_list[i];
-      __syncthreads();
+    if (last_trip || w_count + 32 > kClassifyList / (kThreads / 32)) {  // warp-uniform
+      __syncwarp();
+      int dst = 0;
+      if (lane == 0 && w_count) dst = atomicAdd(work_count, w_count);
+      dst = __shfl_sync(0xffffffffu, dst, 0);
+      for (int i = lane; i < w_count; i += 32) worklist[dst + i] = w_list[i];
+      __syncwarp();
+      w_count = 0;
     }
   }
 }
@@ -476,9 +461,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter) {
 }
 
 struct FinalParams {
-  const float* pts;
+  const float* pts;           // resident cloud, reference point order
   long long n;
-  const void* labels;         // stored labels of the last step
   int* labels_out;            // int32[n] or nullptr
   const unsigned char* table;
   double* partials;           // [gridDim.x] inertia partials
@@ -486,7 +470,6 @@ struct FinalParams {
   DevStatus* st;
   FrameF f;
   int k, kpad;
-  int force_assign;           // 1: always recompute labels (predict / test hook)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -844,15 +827,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   unsigned int n_chg = 0, n_ref = 0;
   // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
   mbar_wait(&s_bar, 0);
-  {
-    __shared__ int s_wcnt[kWarps];
-    __shared__ int s_wbase;
-    // the ring is idle during pass 1: its first bytes stage the worklist entries
-    static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
-    classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
-                                    4.0f * thresh, first_iter, s_acc, s_wcnt, &s_wbase,
-                                    reinterpret_cast<int*>(s_ring), n_chg);
-  }
+  // the ring is idle during pass 1: its first bytes stage the worklist entries
+  static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
+  classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
+                                  4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring), n_chg);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
@@ -1143,13 +1121,13 @@ __global__ void read_sums_kernel(const unsigned long long* acc, int k, Frame fr,
 }
 
 // ---------------------------------------------------------------------------------------
-// Final pass: labels as int32 (recomputed with the final centroids unless the exit was
-// strict) and inertia in FP64 (direct form, fixed-order reduction).
+// Final pass over the resident cloud (reference point order): E-step with the final centroids
+// -> int32 labels, and the inertia in FP64 (direct form, fixed-order reduction).
 // ---------------------------------------------------------------------------------------
-template <typename LabT>
+template <int kChunks>
 __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int kp32 = (p.kpad + 31) & ~31;
+  const int kp32 = kChunks > 0 ? kChunks * 32 : ((p.kpad + 31) & ~31);
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ double s_red[kThreads / 32];
@@ -1173,9 +1151,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   }
   const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const float thresh = p.st->thresh;
-  const bool reassign = p.force_assign || !p.st->strict;
   const FrameF f = p.f;
-  const LabT* labels = reinterpret_cast<const LabT*>(p.labels);
   mbar_wait(&s_bar, 0);
 
   double inert = 0.0;
@@ -1188,16 +1164,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
     const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
     const long long i0 = g * kGroup + lane * 4;
     int lab[4];
-    if (reassign) {
-      const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
-      const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
-      const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
-      assign_group<0>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
-    } else {
-      const typename LabPack<LabT>::V v = LabPack<LabT>::load(labels + i0);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) lab[e] = LabPack<LabT>::get(v, e);
-    }
+    const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
+    const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
+    const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
+    assign_group<kChunks>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (i0 + e < p.n) {

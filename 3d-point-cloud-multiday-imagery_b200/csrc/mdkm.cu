@@ -408,19 +408,11 @@ int step_occupancy(mdkm_handle* h, StepKernel fn, size_t smem, int* occ) {
   return MDKM_OK;
 }
 
-template <typename LabT>
-int final_occupancy(mdkm_handle* h, size_t smem, int* occ) {
-  CU(cudaFuncSetAttribute(lloyd_final_kernel<LabT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lloyd_final_kernel<LabT>, kThreads, smem));
-  return MDKM_OK;
-}
-
-template <typename LabT>
-int launch_final_t(mdkm_handle* h, const FinalParams& fp, size_t smem, int grid) {
-  lloyd_final_kernel<LabT><<<grid, kThreads, smem, h->stream>>>(fp);
-  ++h->launches;
-  CU(cudaGetLastError());
-  return MDKM_OK;
+typedef void (*FinalKernel)(const FinalParams);
+FinalKernel pick_final_kernel(int kpad) {
+  if (kpad <= 32) return lloyd_final_kernel<1>;
+  if (kpad <= 64) return lloyd_final_kernel<2>;
+  return lloyd_final_kernel<0>;
 }
 
 struct KmBuffers {
@@ -430,6 +422,7 @@ struct KmBuffers {
   bool wide;     // uint16 labels
   bool priv;     // per-warp accumulator slices in shared memory
   StepKernel step_fn;
+  FinalKernel final_fn;
   long long n_groups;
 };
 
@@ -515,8 +508,9 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   int occ_step = 1, occ_final = 1;
   kb.step_fn = pick_step_kernel(kb.wide, kb.priv, kb.kpad);
   OK(step_occupancy(h, kb.step_fn, kb.step_smem, &occ_step));
-  if (kb.wide) OK(final_occupancy<unsigned short>(h, kb.final_smem, &occ_final));
-  else OK(final_occupancy<unsigned char>(h, kb.final_smem, &occ_final));
+  kb.final_fn = pick_final_kernel(kb.kpad);
+  CU(cudaFuncSetAttribute(kb.final_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb.final_smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, kb.final_fn, kThreads, kb.final_smem));
   if (occ_step < 1) return fail(h, MDKM_ERR_INVALID, "k=%d does not fit the shared-memory tables", k);
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
@@ -642,7 +636,7 @@ int collect_profile(mdkm_handle* h) {
   return MDKM_OK;
 }
 
-int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_assign);
+int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev);
 
 // Empty-cluster relocation (sklearn/_k_means_common.pyx:167-211), sequenced from the host
 // while the Lloyd loop is paused.  All arithmetic on the device (extras.cuh).
@@ -655,7 +649,7 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
   // labels in the reference's order under the OLD centroids (the paused update has not touched
   // the table yet): what the step just assigned, recomputed point by point
   OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
-  OK(run_final(h, kb, h->labels32.p, /*force_assign=*/1));
+  OK(run_final(h, kb, h->labels32.p));
   RelocParams rp{};
   rp.pts = h->pts.p; rp.n = h->n;
   rp.labels = h->labels32.p;
@@ -685,11 +679,10 @@ int relocate_empty(mdkm_handle* h, const KmBuffers& kb, int n_empty) {
   return MDKM_OK;
 }
 
-int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_assign) {
+int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev) {
   CU(cudaMemsetAsync(h->uscratch.p, 0, 4, h->stream));
   FinalParams fp{};
   fp.pts = h->pts.p; fp.n = h->n;
-  fp.labels = h->labels.p;
   fp.labels_out = labels_dev;
   fp.table = h->table.p;
   fp.partials = h->partials.p;
@@ -697,9 +690,9 @@ int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev, int force_as
   fp.st = h->d_status;
   fp.f = h->ff;
   fp.k = kb.k; fp.kpad = kb.kpad;
-  fp.force_assign = force_assign;
-  if (kb.wide) OK(launch_final_t<unsigned short>(h, fp, kb.final_smem, kb.final_grid));
-  else OK(launch_final_t<unsigned char>(h, fp, kb.final_smem, kb.final_grid));
+  kb.final_fn<<<kb.final_grid, kThreads, kb.final_smem, h->stream>>>(fp);
+  ++h->launches;
+  CU(cudaGetLastError());
   return MDKM_OK;
 }
 
@@ -1264,7 +1257,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   // labels in the reference's point order: always recomputed from the final centroids (the
   // stored ones follow the mirror's order).  After a strict exit the table equals the one the
   // last E-step used -- the sums are integers -- so this reproduces that step's labels exactly.
-  OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
+  OK(run_final(h, kb, labels_dev));
   OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
   read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
   ++h->launches;
@@ -1333,7 +1326,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
       OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
       labels_dev = h->labels32.p;
     }
-    OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
+    OK(run_final(h, kb, labels_dev));
     if (labels_mem != MDKM_MEM_DEVICE && h->n > 0)
       CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -1368,7 +1361,7 @@ int mdkm_predict(mdkm_handle* h, int k, const double* centroids, int32_t* labels
       labels_dev = h->labels32.p;
     }
   }
-  OK(run_final(h, kb, labels_dev, /*force_assign=*/1));
+  OK(run_final(h, kb, labels_dev));
   if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
   OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
   if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
