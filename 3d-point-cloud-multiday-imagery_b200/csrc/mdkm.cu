@@ -428,7 +428,7 @@ struct KmBuffers {
 
 // Re-orders the resident cloud, segment by segment, by the cells of an x-y grid (about 256
 // points per cell) into h->tpts; see mirror.cuh.  Once per (cloud, frame).
-int build_mirror(mdkm_handle* h) {
+int build_mirror(mdkm_handle* h, int cell_px) {
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->tpts, (size_t)cap * 3));
   CU(cudaMemsetAsync(h->tpts.p + (cap - kGroup) * 3, 0, kBlockFloats * 4, h->stream));  // tail of the last block
@@ -443,8 +443,11 @@ int build_mirror(mdkm_handle* h) {
   const double yr = std::max((double)h->bounds[4] - (double)h->bounds[1], 1e-30);
   const double target = std::max(1.0, (double)h->n / 256.0);  // cells (each holds points of every segment)
   long long gx = (long long)llround(sqrt(target * xr / yr));
-  // raster clouds: cells 16 pixels wide, so that every row adds a 64-byte run to a cell
-  if (h->raster_w > 0) gx = (long long)ceil(xr / 16.0);
+  // raster clouds: cells a fixed number of pixels wide, so that every row adds a run of that
+  // many consecutive points to a cell.  Wider cells are cheaper to build (longer write runs),
+  // narrower ones are more compact and leave fewer boundary groups per iteration, which pays
+  // once there are many centroids.
+  if (h->raster_w > 0) gx = (long long)ceil(xr / (double)cell_px);
   gx = std::max<long long>(1, std::min<long long>(gx, 1 << 15));
   long long gy = (long long)ceil(target / (double)gx);
   gy = std::max<long long>(1, std::min<long long>(gy, 1 << 15));
@@ -521,7 +524,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   OK(ensure(h, h->glabel, (size_t)kb.n_groups));
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
   if (!h->summary_ok) {
-    OK(build_mirror(h));
+    OK(build_mirror(h, k <= 16 ? 16 : 8));
     group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
         h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
     ++h->launches;
