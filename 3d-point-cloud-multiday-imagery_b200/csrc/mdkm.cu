@@ -146,6 +146,7 @@ struct mdkm_handle {
   // profiling
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_batch_launches;
   int prof_used = 0;
   double prof_ms = 0.0;
   int prof_steps = 0;
@@ -583,24 +584,12 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.work_count = work_count;
   sp.glabel = h->glabel.p;
   sp.grid_bar = &h->d_status->grid_bar;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->prof) {
-    while ((int)h->prof_ev.size() < h->prof_used + 2) {
-      cudaEvent_t e;
-      CU(cudaEventCreate(&e));
-      h->prof_ev.push_back(e);
-    }
-    e0 = h->prof_ev[h->prof_used++];
-    e1 = h->prof_ev[h->prof_used++];
-    CU(cudaEventRecord(e0, h->stream));
-  }
   // cooperative launch: the grid barrier between the two passes needs every CTA resident
   void* args[] = {&sp};
   CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kb.step_fn), dim3(kb.step_grid), dim3(kThreads), args,
                                  kb.step_smem, h->stream));
   ++h->launches;
   if (!fuse_update) CU(cudaMemsetAsync(work_count, 0, 4, h->stream));
-  if (h->prof) CU(cudaEventRecord(e1, h->stream));
   return MDKM_OK;
 }
 
@@ -633,9 +622,10 @@ int collect_profile(mdkm_handle* h) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
     h->prof_ms += ms;
-    ++h->prof_steps;
+    h->prof_steps += h->prof_batch_launches[i / 2];
   }
   h->prof_used = 0;
+  h->prof_batch_launches.clear();
   return MDKM_OK;
 }
 
@@ -1207,6 +1197,20 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   while (true) {
     while (inflight < 2 && enq < max_iter) {
       const int nb = std::min(kBatch, max_iter - enq);
+      // profiling: one event pair around the batch's step kernels (back-to-back launches, so
+      // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
+      cudaEvent_t pe1 = nullptr;
+      if (h->prof && can_fuse(h)) {
+        while ((int)h->prof_ev.size() < h->prof_used + 2) {
+          cudaEvent_t e;
+          CU(cudaEventCreate(&e));
+          h->prof_ev.push_back(e);
+        }
+        CU(cudaEventRecord(h->prof_ev[h->prof_used], h->stream));
+        pe1 = h->prof_ev[h->prof_used + 1];
+        h->prof_batch_launches.push_back(nb);
+        h->prof_used += 2;
+      }
       for (int b = 0; b < nb; ++b) {
         if (can_fuse(h)) {
           OK(launch_step(h, kb, 0, /*fuse_update=*/1));
@@ -1216,6 +1220,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
           OK(launch_update(h, kb, /*allow_pause=*/1, 0));
         }
       }
+      if (pe1) CU(cudaEventRecord(pe1, h->stream));
       OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
       CU(cudaEventRecord(h->batch_ev[tail], h->stream));
       tail ^= 1;

@@ -198,9 +198,10 @@ int mdkm_kmeans_plusplus(mdkm_handle* h, int k, int64_t first_index, const doubl
  * (bench.py times every fit that way). */
 int mdkm_drop_caches(mdkm_handle* h);
 
-/* Timing aid for bench.py: when enabled, CUDA events bracket every launch of the
- * assignment+accumulate kernel inside mdkm_fit; mdkm_profile_read returns their summed
- * duration and count and resets both. */
+/* Timing aid for bench.py: when enabled, CUDA events bracket every batch of back-to-back
+ * launches of the Lloyd step kernel inside mdkm_fit; mdkm_profile_read returns the summed
+ * duration and the number of launches it covers and resets both (average launch duration =
+ * their ratio; batches that ended early on convergence make it a lower bound). */
 int mdkm_profile_enable(mdkm_handle* h, int on);
 int mdkm_profile_read(mdkm_handle* h, double* step_kernel_ms, int* n_step_launches,
                       int* n_kernel_launches_total);
