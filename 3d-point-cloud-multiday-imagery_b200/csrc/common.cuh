@@ -84,7 +84,32 @@ struct FrameF {
 //   fast row  = (-2c'x, -2c'y, -2c'z, ||c'||^2) rounded to FP32 ; padding rows = (0,0,0,+inf)
 //   exact row = ( c'x,   c'y,   c'z,  ||c'||^2) in FP64, c' = c - origin
 __host__ __device__ inline int pad_k(int k) { return (k + 7) & ~7; }
-__host__ __device__ inline size_t table_bytes(int kpad) { return (size_t)kpad * (16 + 32); }
 __host__ __device__ inline size_t exact_offset(int kpad) { return (size_t)kpad * 16; }
+
+// Third section of the table, for k > kBucketMinK only: the centroids bucketed by an x-y grid
+// of G x G cells over the frame (G = bucket_g(k)), so that the classification pass looks at
+// the centroids near a group instead of all k:
+//   BucketHdr | uint16 start[G*G + 1] | uint16 perm[Kpad]     (16-byte aligned, zero padded)
+// perm lists the centroid indices bucket by bucket (any order inside a bucket).
+constexpr int kBucketMinK = 33;
+struct BucketHdr {
+  float hx, hy;        // half-ranges of the frame in x and y
+  float inv_x, inv_y;  // G / (2 hx), G / (2 hy)
+};
+__host__ __device__ inline int bucket_g(int k) {
+  int g = 4;
+  while (g < 32 && g * g < k) g *= 2;
+  return g;
+}
+__host__ __device__ inline size_t bucket_offset(int kpad) { return (size_t)kpad * 48; }
+__host__ __device__ inline size_t bucket_bytes(int k, int kpad) {
+  if (k < kBucketMinK) return 0;
+  const int g = bucket_g(k);
+  return (sizeof(BucketHdr) + (size_t)(g * g + 1 + kpad) * 2 + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t table_bytes(int k, int kpad) { return (size_t)kpad * 48 + bucket_bytes(k, kpad); }
+__device__ __forceinline__ int bucket_coord(float c, float h, float inv, int g) {
+  return min(g - 1, max(0, (int)floorf((c + h) * inv)));
+}
 
 }  // namespace mdkm

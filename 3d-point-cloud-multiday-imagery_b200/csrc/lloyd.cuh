@@ -82,6 +82,49 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
   return t;
 }
 
+// Buckets the k centroids of `table` by the x-y grid of common.cuh (for k >= kBucketMinK).
+// Executed by all threads of ONE CTA right after that CTA wrote the fast rows.
+__device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int k, int kpad, const Frame& fr) {
+  if (k < kBucketMinK) return;
+  __shared__ int s_cnt[32 * 32 + 1];
+  const int g = bucket_g(k), cells = g * g, tid = threadIdx.x;
+  BucketHdr hdr;
+  hdr.hx = (float)fr.halfrange[0]; hdr.hy = (float)fr.halfrange[1];
+  hdr.inv_x = (float)g / (2.0f * fmaxf(hdr.hx, 1e-30f));
+  hdr.inv_y = (float)g / (2.0f * fmaxf(hdr.hy, 1e-30f));
+  const float4* fast = reinterpret_cast<const float4*>(table);
+  unsigned char* sec = table + bucket_offset(kpad);
+  unsigned short* start = reinterpret_cast<unsigned short*>(sec + sizeof(BucketHdr));
+  unsigned short* perm = start + cells + 1;
+  __syncthreads();  // the fast rows of this CTA's other threads are visible
+  for (int i = tid; i <= cells; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int j = tid; j < k; j += blockDim.x) {
+    const float4 r = fast[j];
+    const int b = bucket_coord(-0.5f * r.y, hdr.hy, hdr.inv_y, g) * g + bucket_coord(-0.5f * r.x, hdr.hx, hdr.inv_x, g);
+    atomicAdd(&s_cnt[b], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = 0; b < cells; ++b) {
+      const int c = s_cnt[b];
+      s_cnt[b] = run;
+      start[b] = (unsigned short)run;
+      run += c;
+    }
+    start[cells] = (unsigned short)run;
+    *reinterpret_cast<BucketHdr*>(sec) = hdr;
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += blockDim.x) {
+    const float4 r = fast[j];
+    const int b = bucket_coord(-0.5f * r.y, hdr.hy, hdr.inv_y, g) * g + bucket_coord(-0.5f * r.x, hdr.hx, hdr.inv_x, g);
+    perm[atomicAdd(&s_cnt[b], 1)] = (unsigned short)j;
+  }
+  for (int j = k + tid; j < kpad; j += blockDim.x) perm[j] = 0;
+}
+
 // Executed by all kThreads threads of ONE CTA: the stand-alone update kernel, or the last CTA
 // of a fused step kernel.  Reads the accumulators through L2 (they were produced by atomics).
 // It sits on the critical path of every iteration, so global round trips are kept to one: a
@@ -188,6 +231,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
     }
   }
   const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);
+  build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
   // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
   for (int o = 16; o > 0; o >>= 1) {
     shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
@@ -354,7 +398,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
                                                 bool first_iter, unsigned long long* s_acc, int* s_list,
-                                                unsigned int& n_chg) {
+                                                const unsigned char* s_bkt, unsigned int& n_chg) {
   const int tid = threadIdx.x, lane = tid & 31;
   int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
   int w_count = 0;                                                         // warp-uniform
@@ -386,8 +430,35 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
       }
       const float4 rr = s_fast[ref];
       int ncand = 0;
-      for (int j = 0; j < k; ++j)
-        ncand += (min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) ? 1 : 0;
+      if (s_bkt == nullptr) {
+        for (int j = 0; j < k; ++j)
+          ncand += (min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) ? 1 : 0;
+      } else {
+        // Only centroids near the group can win: d_j(x) <= d_ref(x) + margin at some x of the box
+        // implies |x - c_j| <= sqrt(r^2 + margin), r = largest distance from c_ref to the box;
+        // so c_j lies in the box grown by that reach, and only those buckets are visited.
+        const BucketHdr hdr = *reinterpret_cast<const BucketHdr*>(s_bkt);
+        const int g = bucket_g(k);
+        const unsigned short* start = reinterpret_cast<const unsigned short*>(s_bkt + sizeof(BucketHdr));
+        const unsigned short* perm = start + g * g + 1;
+        const float cx = -0.5f * rr.x, cy = -0.5f * rr.y, cz = -0.5f * rr.z;
+        const float dx = fmaxf(fabsf(lo0 - cx), fabsf(hi0 - cx)), dy = fmaxf(fabsf(lo1 - cy), fabsf(hi1 - cy)),
+                    dz = fmaxf(fabsf(lo2 - cz), fabsf(hi2 - cz));
+        const float reach = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)) + 2.0f * margin) * 1.0001f + 1e-3f / hdr.inv_x;
+        const int bx0 = bucket_coord(lo0 - reach, hdr.hx, hdr.inv_x, g), bx1 = bucket_coord(hi0 + reach, hdr.hx, hdr.inv_x, g);
+        const int by0 = bucket_coord(lo1 - reach, hdr.hy, hdr.inv_y, g), by1 = bucket_coord(hi1 + reach, hdr.hy, hdr.inv_y, g);
+        ncand = 1;  // ref itself
+        for (int by = by0; by <= by1 && ncand <= 1; ++by) {
+          const int i1 = start[by * g + bx1 + 1];
+          for (int i = start[by * g + bx0]; i < i1; ++i) {
+            const int j = perm[i];
+            if (j != ref && min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) {
+              ++ncand;
+              break;
+            }
+          }
+        }
+      }
       if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
     }
     if (label >= 0 && first_iter) {  // later iterations: label == prev, nothing to write
@@ -808,10 +879,14 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
   }
   __syncthreads();
+  // bucket index of the centroids (k >= kBucketMinK), behind the accumulator slices
+  const uint32_t bkt_bytes = (uint32_t)bucket_bytes(p.k, p.kpad);
+  unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_acc_all + (size_t)(kPrivate ? kWarps : 1) * p.kpad * 4);
   if (tid == 0) {
-    // centroid rows: global -> shared through the TMA unit (1-D bulk copy)
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
+    // centroid rows (and their bucket index): global -> shared through the TMA unit (1-D bulk copies)
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
   }
   const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const float thresh = p.st->thresh;
@@ -830,7 +905,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // the ring is idle during pass 1: its first bytes stage the worklist entries
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
   classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
-                                  4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring), n_chg);
+                                  4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
+                                  bkt_bytes ? s_bkt : nullptr, n_chg);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
@@ -1095,6 +1171,7 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
                                                  u.fr.halfrange[2] * m_cz));
     u.st->thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
   }
+  build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
 }
 
 // Reads the table back as K x 3 float64 centroids in original coordinates.
