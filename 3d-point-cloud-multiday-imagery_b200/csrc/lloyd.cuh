@@ -726,6 +726,133 @@ __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&
   return ncand;
 }
 
+// ---------------------------------------------------------------------------------------
+// Assignment of one warp-group when the centroids are bucketed (many centroids): the
+// candidates are collected from the buckets the group's box, grown by its reach, touches --
+// a handful of centroids instead of three passes over all k.  `ref_hint` is any centroid index
+// (the label a point of the group had before: a good reference) or -1 to search the nearest
+// to the box centre.  Candidates come in bucket order, so ties are broken on the index
+// explicitly (lowest index wins, pyx:205-213).  `s_cand`: this warp's kCandCap slots.
+// Returns the number of candidates, or -1 when there are more than kCandCap (the caller then
+// takes the generic path).  Warp-synchronous.
+// ---------------------------------------------------------------------------------------
+constexpr int kCandCap = 64;
+
+__device__ __forceinline__ int assign_group_bucketed(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
+                                                     const float* orig_x, const float* orig_y, const float* orig_z,
+                                                     const FrameF& f, const float4* __restrict__ s_fast,
+                                                     const double4* __restrict__ c64, const unsigned char* s_bkt,
+                                                     int k, int kp32, float thresh, int ref_hint,
+                                                     unsigned short* s_cand, int lane, int (&lab)[4],
+                                                     unsigned int& n_refined) {
+  const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
+  const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
+  const float by0 = redux_min_f32(fminf(fminf(yc[0], yc[1]), fminf(yc[2], yc[3])));
+  const float by1 = redux_max_f32(fmaxf(fmaxf(yc[0], yc[1]), fmaxf(yc[2], yc[3])));
+  const float bz0 = redux_min_f32(fminf(fminf(zc[0], zc[1]), fminf(zc[2], zc[3])));
+  const float bz1 = redux_max_f32(fmaxf(fmaxf(zc[0], zc[1]), fmaxf(zc[2], zc[3])));
+  const float margin = 4.0f * thresh;
+  int iref = ref_hint;
+  if (iref < 0) {  // nearest centroid to the box centre (first iteration, final pass)
+    const float mx = 0.5f * (bx0 + bx1), my = 0.5f * (by0 + by1), mz = 0.5f * (bz0 + bz1);
+    float dmin = __int_as_float(0x7f800000);
+    for (int j = lane; j < kp32; j += 32) {
+      const float4 r = s_fast[j];
+      dmin = fminf(dmin, fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w))));
+    }
+    dmin = redux_min_f32(dmin);
+    for (int base = 0; base < kp32 && iref < 0; base += 32) {
+      const float4 r = s_fast[base + lane];
+      const unsigned int m =
+          __ballot_sync(0xffffffffu, fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w))) == dmin);
+      if (m) iref = base + __ffs(m) - 1;
+    }
+    if (iref < 0) iref = 0;
+  }
+  const float4 ref = s_fast[iref];
+  const BucketHdr hdr = *reinterpret_cast<const BucketHdr*>(s_bkt);
+  const int g = bucket_g(k);
+  const unsigned short* start = reinterpret_cast<const unsigned short*>(s_bkt + sizeof(BucketHdr));
+  const unsigned short* perm = start + g * g + 1;
+  const float cx = -0.5f * ref.x, cy = -0.5f * ref.y, cz = -0.5f * ref.z;
+  const float dx = fmaxf(fabsf(bx0 - cx), fabsf(bx1 - cx)), dy = fmaxf(fabsf(by0 - cy), fabsf(by1 - cy)),
+              dz = fmaxf(fabsf(bz0 - cz), fabsf(bz1 - cz));
+  const float reach = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)) + 2.0f * margin) * 1.0001f + 1e-3f / hdr.inv_x;
+  const int cx0 = bucket_coord(bx0 - reach, hdr.hx, hdr.inv_x, g), cx1 = bucket_coord(bx1 + reach, hdr.hx, hdr.inv_x, g);
+  const int cy0 = bucket_coord(by0 - reach, hdr.hy, hdr.inv_y, g), cy1 = bucket_coord(by1 + reach, hdr.hy, hdr.inv_y, g);
+  int ncand = 0;
+  for (int cyi = cy0; cyi <= cy1; ++cyi) {
+    const int i1 = start[cyi * g + cx1 + 1];
+    for (int base = start[cyi * g + cx0]; base < i1; base += 32) {
+      const int i = base + lane;
+      const int j = i < i1 ? (int)perm[i] : -1;
+      const bool pass = j >= 0 && min_gap_over_box(s_fast[j < 0 ? 0 : j], ref, bx0, bx1, by0, by1, bz0, bz1) <= margin;
+      const unsigned int m = __ballot_sync(0xffffffffu, pass);
+      if (ncand + __popc(m) > kCandCap) return -1;  // warp-uniform
+      if (pass) s_cand[ncand + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+      ncand += __popc(m);
+    }
+  }
+  __syncwarp();
+  if (ncand <= 1) {  // one possible owner (the reference is always a candidate)
+    const int only = ncand == 1 ? (int)s_cand[0] : iref;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lab[e] = only;
+    return ncand;
+  }
+  float best[4], second[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    best[e] = __int_as_float(0x7f800000);
+    second[e] = __int_as_float(0x7f800000);
+    lab[e] = 0x7fffffff;
+  }
+  for (int c = 0; c < ncand; ++c) {
+    const int j = s_cand[c];
+    const float4 cf = s_fast[j];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = fmaf(xc[e], cf.x, fmaf(yc[e], cf.y, fmaf(zc[e], cf.z, cf.w)));
+      const bool lt = d < best[e] || (d == best[e] && j < lab[e]);
+      second[e] = fminf(second[e], fmaxf(d, best[e]));
+      best[e] = fminf(best[e], d);
+      lab[e] = lt ? j : lab[e];
+    }
+  }
+  bool ambig[4];
+  bool amb = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    ambig[e] = !(second[e] - best[e] > thresh);
+    amb |= ambig[e];
+  }
+  if (__any_sync(0xffffffffu, amb)) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!__any_sync(0xffffffffu, ambig[e])) continue;  // warp-uniform
+      const double X = (double)orig_x[e] - (double)f.ox;
+      const double Y = (double)orig_y[e] - (double)f.oy;
+      const double Z = (double)orig_z[e] - (double)f.oz;
+      double bd = 1.0 / 0.0;
+      int bi = 0x7fffffff;
+      for (int c = 0; c < ncand; ++c) {
+        const int j = s_cand[c];
+        const double4 cc = ld_c64(&c64[j]);
+        const double d = fma(-2.0, fma(X, cc.x, fma(Y, cc.y, Z * cc.z)), cc.w);
+        if (d < bd || (d == bd && j < bi)) {
+          bd = d;
+          bi = j;
+        }
+      }
+      if (ambig[e]) {
+        lab[e] = bi;
+        ++n_refined;
+      }
+    }
+  }
+  return ncand;
+}
+
 template <typename LabT>
 struct LabPack;
 template <>
@@ -856,6 +983,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __shared__ __align__(8) uint64_t s_gbar[kWarps * kStages];
   __shared__ unsigned int s_changed;
   __shared__ unsigned int s_refined;
+  __shared__ unsigned short s_cand[kWarps * kCandCap];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -988,10 +1116,20 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const float yc[4] = {vy.x - f.oy, vy.y - f.oy, vy.z - f.oy, vy.w - f.oy};
     const float zc[4] = {vz.x - f.oz, vz.y - f.oz, vz.z - f.oz, vz.w - f.oz};
     int lab[4];
-    const int ncand = assign_group<kChunks>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
-                                            reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
-                                            reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast,
-                                            c64, p.k, kp32, thresh, lane, lab, n_ref);
+    int ncand = -1;
+    if (kChunks == 0 && bkt_bytes) {
+      // many centroids: candidates from the bucket index, reference = a label the group had
+      const int hint = first_iter ? -1 : __shfl_sync(0xffffffffu, LabPack<LabT>::get(oldl, 0), 0);
+      ncand = assign_group_bucketed(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
+                                    reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
+                                    reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast, c64,
+                                    s_bkt, p.k, kp32, thresh, hint, s_cand + warp * kCandCap, lane, lab, n_ref);
+    }
+    if (ncand < 0)
+      ncand = assign_group<kChunks>(xc, yc, zc, reinterpret_cast<const float*>(src + lane * 16),
+                                    reinterpret_cast<const float*>(src + kGroup * 4 + lane * 16),
+                                    reinterpret_cast<const float*>(src + kGroup * 8 + lane * 16), f, s_fast, c64,
+                                    p.k, kp32, thresh, lane, lab, n_ref);
     // every value read from the stage has been consumed: refill it with the group kStages
     // ahead (the reads completed before this point, so the async-proxy write cannot race)
     __syncwarp();
