@@ -1348,9 +1348,12 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   __shared__ double s_red[kThreads / 32];
   __shared__ unsigned int s_refined;
   __shared__ bool s_last;
+  __shared__ unsigned short s_cand[(kThreads / 32) * kCandCap];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const uint32_t bkt_bytes = kChunks == 0 ? (uint32_t)bucket_bytes(p.k, p.kpad) : 0u;
+  unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_fast + kp32);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
@@ -1361,8 +1364,9 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u);
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
+    if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
   }
   const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const float thresh = p.st->thresh;
@@ -1371,6 +1375,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
 
   double inert = 0.0;
   unsigned int n_ref = 0;
+  int hint = -1;  // many centroids: the previous group's label is the reference of the next one
   const long long n_groups = (p.n + kGroup - 1) / kGroup;
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long g = (long long)blockIdx.x * (kThreads / 32) + warp; g < n_groups; g += stride) {
@@ -1382,7 +1387,12 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
     const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
     const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
     const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
-    assign_group<kChunks>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
+    int ncand = -1;
+    if (kChunks == 0 && bkt_bytes)
+      ncand = assign_group_bucketed(xc, yc, zc, xo, yo, zo, f, s_fast, c64, s_bkt, p.k, kp32, thresh, hint,
+                                    s_cand + warp * kCandCap, lane, lab, n_ref);
+    if (ncand < 0) assign_group<kChunks>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
+    hint = __shfl_sync(0xffffffffu, lab[0], 0);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (i0 + e < p.n) {

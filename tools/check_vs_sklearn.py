@@ -8,7 +8,7 @@ pkg = importlib.import_module("3d-point-cloud-multiday-imagery_b200")
 from oracle import sklearn_ref, kmeans_oracle as KO, unproject_oracle as UO
 
 eng = pkg.Engine(0)
-for (D, H, W, k, iters) in [(4, 256, 2048, 64, 20), (20, 256, 2048, 64, 20), (6, 512, 512, 300, 10)]:
+for (D, H, W, k, iters) in [(4, 256, 2048, 64, 20), (20, 256, 2048, 64, 20), (6, 512, 512, 300, 10), (6, 1024, 1024, 1024, 8)]:
     hm = pkg.make_stack(D, H, W, seed=1).numpy()
     P = UO.unproject_stack(hm)
     n = eng.unproject(hm)
