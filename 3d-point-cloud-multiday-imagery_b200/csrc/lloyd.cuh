@@ -1377,8 +1377,13 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   unsigned int n_ref = 0;
   int hint = -1;  // many centroids: the previous group's label is the reference of the next one
   const long long n_groups = (p.n + kGroup - 1) / kGroup;
-  const long long stride = (long long)gridDim.x * (kThreads / 32);
-  for (long long g = (long long)blockIdx.x * (kThreads / 32) + warp; g < n_groups; g += stride) {
+  // every warp owns a contiguous run of groups: neighbours in the raster, so the label of one
+  // group is a good reference centroid for the next (bucketed path)
+  const long long n_warps = (long long)gridDim.x * (kThreads / 32);
+  const long long per_warp = (n_groups + n_warps - 1) / n_warps;
+  const long long g_first = ((long long)blockIdx.x * (kThreads / 32) + warp) * per_warp;
+  const long long g_last = min(n_groups, g_first + per_warp);
+  for (long long g = g_first; g < g_last; ++g) {
     const float* blk = p.pts + g * kBlockFloats + lane * 4;
     const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
     const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
