@@ -938,9 +938,9 @@ __device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned 
     unsigned long long* dst = px.data[q] + ((size_t)par * R + px.rank) * px.slot;
     for (int i = tid; i < n; i += kThreads) st_relaxed_sys_u64(dst + i, __ldcg(acc + i));
   }
-  __threadfence_system();
   __syncthreads();
   if (tid < R) {
+    // release at system scope after the CTA barrier: cumulative over the stores above
     st_release_sys_u64(px.flags[tid] + par * R + px.rank, epoch);
     // bounded wait (about 4 s): a missing peer must not hang the GPU
     const unsigned long long* mine = px.flags[px.rank] + par * R + tid;
