@@ -180,59 +180,49 @@ __global__ void __launch_bounds__(1024) scan_chunks_kernel(const unsigned int* c
   if (tid == 0) *carry_out = s_carry;
 }
 
+// Pass 2.  One pixel per lane and round (32 consecutive pixels per warp instruction): the
+// valid pixels of a round are ranked with one ballot and land on consecutive output slots, so
+// the stores of x, y and z are contiguous runs instead of 4-byte fragments.  (Pass 1 keeps
+// the float4 loads: it has nothing to write.)
 __global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const UnprojParams p) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (kThreads / 32);
   for (long long c = p.chunk_begin + warp; c < p.chunk_end; c += n_warps) {
     long long out = p.chunk_offsets[c];
-    for (int r = 0; r < kChunk / 128; ++r) {
-      const long long i = c * kChunk + r * 128 + lane * 4;
-      float h[4];
-      unsigned int vb;
-      load_heights4(p, i, h, vb);
-      const int cnt = __popc(vb);
-      int incl = cnt;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (vb) {
-        // pixel coordinates of the first of the four pixels
-        const long long gp = p.pix_begin + i;
-        const long long day = gp / p.HW;
-        const long long rem = gp - day * p.HW;
-        int row = (int)(rem / p.W);
-        int col = (int)(rem - (long long)row * p.W);
-        int dcur = (int)day;
-        long long o = out + (incl - cnt);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (vb & (1u << e)) {
-            float zz = h[e];
-            if (p.planes) {
-              // plugin.py:171: height_rel = dot(P - center, normal)
-              const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
-              zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] +
-                           ((double)h[e] - pl[2]) * pl[5]);
-            }
-            float* dst = p.pts + pt_off(o);
-            dst[0] = (float)col;
-            dst[kGroup] = (float)row;
-            dst[2 * kGroup] = zz;
-            ++o;
-          }
-          if (++col == p.W) {
-            col = 0;
-            if (++row == p.H) {
-              row = 0;
-              ++dcur;
-            }
-          }
+    // position of the chunk's first pixel in the stack: once per chunk in 64 bits
+    const long long gp0 = p.pix_begin + c * kChunk;
+    const long long day0 = gp0 / p.HW;
+    const long long rem0 = gp0 - day0 * p.HW;
+    const long long left = min((long long)kChunk, p.pix_count - c * kChunk);
+#pragma unroll 4
+    for (int r = 0; r < kChunk / 32; ++r) {
+      const int o = r * 32 + lane;
+      float hv = 0.f;
+      bool ok = false;
+      if (o < left) ok = load_height1(p, c * kChunk + o, hv);
+      const unsigned int m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        long long rem = rem0 + o;
+        int dcur = (int)day0;
+        while (rem >= p.HW) {  // a chunk may run into the next day(s)
+          rem -= p.HW;
+          ++dcur;
         }
+        const int row = (int)(rem / p.W);
+        const int col = (int)(rem - (long long)row * p.W);
+        float zz = hv;
+        if (p.planes) {
+          // plugin.py:171: height_rel = dot(P - center, normal)
+          const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
+          zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)hv - pl[2]) * pl[5]);
+        }
+        float* dst = p.pts + pt_off(out + __popc(m & ((1u << lane) - 1u)));
+        dst[0] = (float)col;
+        dst[kGroup] = (float)row;
+        dst[2 * kGroup] = zz;
       }
-      out += total;
+      out += __popc(m);
     }
   }
 }
