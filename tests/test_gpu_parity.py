@@ -523,3 +523,40 @@ def test_config2_full_size_single_step(engine):
     # checksum-of-sums property: total of the per-cluster sums equals the column sums
     col = np.array([cloud[:, i].sum(dtype=np.float64) for i in range(3)])
     np.testing.assert_allclose(sums.sum(axis=0), col, rtol=1e-9)
+
+
+def test_config2_full_size_fit(engine):
+    """BASELINE.json configs[1] at full size: a 5-iteration fit (cold mirror / summaries, fused
+    update, final pass) against the C oracle iterated step by step."""
+    import torch
+
+    D, H, W, k, iters = 10, 2048, 2048, 16, 5
+    hm = synth.make_stack(D, H, W, seed=1, device="cuda")
+    n = engine.unproject(hm)
+    del hm
+    torch.cuda.empty_cache()
+    cloud = engine.get_cloud(False)
+    x, y, z = (np.ascontiguousarray(cloud[:, i]) for i in range(3))
+    init = synth.init_from_points(cloud, k, 1)
+    C = init.copy()
+    for _ in range(iters):
+        _, sums_ref, counts_ref, _ = c_oracle.lloyd_step_f32soa(x, y, z, C)
+        C = sums_ref / np.maximum(counts_ref, 1)[:, None]
+    lab_ref, _, counts_final, _ = c_oracle.lloyd_step_f32soa(x, y, z, C)  # final E-step (not strict)
+    r = engine.fit(init, max_iter=iters, tol=0.0)
+    assert r["n_iter"] == iters and r["n_relocations"] == 0
+    std = np.array([cloud[:, i].std(dtype=np.float64) for i in range(3)])
+    err = (np.abs(r["centers"] - C) / np.maximum(np.abs(C), std)).max()
+    print("full-size fit: centroid rel err", err, "refined", r["n_refined"], "of", n * iters)
+    assert err < CENTROID_TOL
+    bad = np.nonzero(r["labels"] != lab_ref)[0]
+    cmp = KO.compare_labels(cloud[bad].astype(np.float64), C, lab_ref[bad], r["labels"][bad])
+    print("full-size fit: label mismatches", bad.size, cmp)
+    assert cmp["n_hard"] == 0
+    np.testing.assert_array_equal(np.bincount(r["labels"], minlength=k)[: k] if bad.size == 0 else counts_final,
+                                  counts_final.astype(np.int64))
+    # the same fit again with the cached structures: bit-identical
+    r2 = engine.fit(init, max_iter=iters, tol=0.0)
+    assert r2["centers"].tobytes() == r["centers"].tobytes() and np.array_equal(r2["labels"], r["labels"])
+    d = ((cloud.astype(np.float64) - r["centers"][r["labels"]]) ** 2).sum()
+    np.testing.assert_allclose(r["inertia"], d, rtol=1e-9)
