@@ -989,8 +989,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
 #ifdef MDKM_TIMING
-  if (blockIdx.x == 0 && tid == 0) p.st->t_start = globaltimer_ns();
-  if (tid == 0) atomicMax(&p.st->t_classify_start, globaltimer_ns());  // latest CTA entry
+  if (blockIdx.x == 0 && tid == 0) {
+    p.st->t_start = globaltimer_ns();
+    p.st->t_update_done = 0ull;
+  }
 #endif
   const int n_slices = kPrivate ? kWarps : 1;
   unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
@@ -1024,8 +1026,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
   const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
-  // each warp owns a CONTIGUOUS range of groups: consecutive groups are neighbours in the
-  // raster, so label runs are long and the register accumulators below rarely flush
   LabT* labels = reinterpret_cast<LabT*>(p.labels);
   unsigned int n_chg = 0, n_ref = 0;
   // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
@@ -1045,10 +1045,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // ---- pass 2: the groups a cluster boundary crosses, point by point -----------------------
   // (the "groups" below are positions in the worklist)
   const int n_items = *reinterpret_cast<volatile int*>(p.work_count);
-  const int per_warp = (n_items + (int)gridDim.x * kWarps - 1) / ((int)gridDim.x * kWarps);
-  const int g0 = ((int)blockIdx.x * kWarps + warp) * per_warp;
-  const int g_end = min(n_items, g0 + per_warp);
-  constexpr int stride = 1;
+  // round-robin over the warps of the grid: neighbouring list entries are neighbouring groups
+  // with similar cost, so interleaving them evens out the warps' loads
+  const int stride = (int)gridDim.x * kWarps;
+  const int g0 = (int)blockIdx.x * kWarps + warp;
+  const int g_end = n_items;
   const int* __restrict__ wl = p.worklist;
   const uint32_t ring_a = smem_u32(s_ring) + warp * (kStages * kStageB);
   const uint32_t gbar_a = smem_u32(s_gbar) + warp * (kStages * 8);
@@ -1070,11 +1071,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // (the list was written by other CTAs of this very kernel: read it through L2, not the
   // non-coherent path)
   if (g_fetch < g_end) { gq0 = __ldcg(wl + g_fetch); issue(0, gq0); }
-  ++g_fetch;
+  g_fetch += stride;
   if (g_fetch < g_end) { gq1 = __ldcg(wl + g_fetch); issue(1, gq1); }
-  ++g_fetch;
+  g_fetch += stride;
   if (g_fetch < g_end) { gq2 = __ldcg(wl + g_fetch); issue(2, gq2); }
-  ++g_fetch;
+  g_fetch += stride;
   int g_pref = g_fetch < g_end ? __ldcg(wl + g_fetch) : 0;  // list entry of the next fetch
 
   // run accumulator: while consecutive groups of this warp carry one label, every lane just
@@ -1250,6 +1251,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const unsigned int t = atomicAdd(&p.st->ticket, 1u);
     s_is_last = (t == gridDim.x - 1);
 #ifdef MDKM_TIMING
+    atomicAdd(&p.st->t_update_done, globaltimer_ns() - p.st->t_start);  // sum of the CTAs' finish times
     if (s_is_last) p.st->t_last_done = globaltimer_ns();
 #endif
   }
@@ -1264,7 +1266,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   lloyd_update_body(p.upd);
 #ifdef MDKM_TIMING
   __syncthreads();
-  if (tid == 0) p.st->t_update_done = globaltimer_ns();
+  if (tid == 0) p.st->t_classify_start = globaltimer_ns();  // (field reused: end of the update)
 #endif
 }
 

@@ -1279,10 +1279,10 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   const DevStatus& fin = h->h_status[0];
   h->epoch_base = fin.epoch;
 #ifdef MDKM_TIMING
-  fprintf(stderr, "[mdkm timing] last iteration: latest CTA entry +%.1f us | latest end of pass 1 +%.1f us | after grid barrier +%.1f us | last CTA done +%.1f us | update done +%.1f us\n",
-          ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3, ((double)fin.t_first_done - (double)fin.t_start) * 1e-3,
-          (fin.t_classify_done - fin.t_start) * 1e-3, (fin.t_last_done - fin.t_start) * 1e-3,
-          (fin.t_update_done - fin.t_start) * 1e-3);
+  fprintf(stderr, "[mdkm timing] last iteration: latest end of pass 1 +%.1f us | after grid barrier +%.1f us | CTAs done on average +%.1f us, last +%.1f us | update done +%.1f us\n",
+          ((double)fin.t_first_done - (double)fin.t_start) * 1e-3, (fin.t_classify_done - fin.t_start) * 1e-3,
+          (double)fin.t_update_done * 1e-3 / std::max(1, kb.step_grid), (fin.t_last_done - fin.t_start) * 1e-3,
+          ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3);
 #endif
   if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "peer exchange of the partial sums timed out (a rank is missing)");
   if (n_iter_out) *n_iter_out = fin.iter;
