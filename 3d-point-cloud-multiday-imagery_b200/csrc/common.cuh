@@ -44,7 +44,7 @@ struct DevStatus {
   float thresh;    // 2 * FP32 error bound of the fast distances for the current table
   unsigned int ticket;            // CTAs of the running step kernel that have flushed their sums
   unsigned long long epoch;       // fused steps completed since the communicator was created
-  int xchg_timeout;               // 1: a peer never delivered its partial sums (fatal)
+  int xchg_timeout;               // 1: a kernel-side wait (peer sums, grid barrier) timed out (fatal)
   unsigned int grid_bar;          // arrival counter of the step kernel's grid barrier
   // diagnostics (MDKM_TIMING builds only): globaltimer stamps of the last fused step, ns
   unsigned long long t_start, t_first_done, t_last_done, t_update_done, t_classify_start, t_classify_done;

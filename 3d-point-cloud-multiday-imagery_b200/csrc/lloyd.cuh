@@ -518,13 +518,20 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
 
 // Grid-wide barrier of a cooperatively launched (fully resident) grid: a monotonically
 // increasing arrival counter, one generation per use.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter) {
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, int* timeout_flag) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int arrived = atomicAdd(counter, 1u) + 1u;
     const unsigned int target = (arrived + gridDim.x - 1u) / gridDim.x * gridDim.x;
+    // bounded wait (about 4 s): the launch is cooperative, so every CTA is resident and this
+    // never triggers; if it ever did, a flagged wrong result beats a hung GPU
+    const long long t0 = clock64();
     while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) {
+      if (clock64() - t0 > (8ll << 30)) {
+        *timeout_flag = 1;
+        break;
+      }
     }
     __threadfence();
   }
@@ -1038,7 +1045,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
-  grid_barrier(p.grid_bar);  // the worklist is complete
+  grid_barrier(p.grid_bar, &p.st->xchg_timeout);  // the worklist is complete
 #ifdef MDKM_TIMING
   if (blockIdx.x == 0 && tid == 0) p.st->t_classify_done = globaltimer_ns();
 #endif

@@ -1284,7 +1284,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
           (double)fin.t_update_done * 1e-3 / std::max(1, kb.step_grid), (fin.t_last_done - fin.t_start) * 1e-3,
           ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3);
 #endif
-  if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "peer exchange of the partial sums timed out (a rank is missing)");
+  if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "a kernel-side wait timed out (peer exchange of the partial sums: a rank is missing; or the grid barrier)");
   if (n_iter_out) *n_iter_out = fin.iter;
   if (inertia_out) *inertia_out = fin.inertia;
   h->stat_refined = (long long)fin.n_refined;
@@ -1343,6 +1343,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   h->stat_refined = (long long)h->h_status[0].n_refined;
   h->stat_reloc = 0;
   OK(collect_profile(h));
+  if (h->h_status[0].xchg_timeout) return fail(h, MDKM_ERR_CUDA, "the step kernel's grid barrier timed out");
   return MDKM_OK;
 }
 
