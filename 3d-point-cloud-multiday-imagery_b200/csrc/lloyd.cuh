@@ -431,8 +431,18 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
       const float4 rr = s_fast[ref];
       int ncand = 0;
       if (s_bkt == nullptr) {
-        for (int j = 0; j < k; ++j)
-          ncand += (min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) ? 1 : 0;
+        // few centroids: all of them, with the box as centre + half-widths -- the minimum of the
+        // (linear) gap over the box is its value at the centre minus sum_d |a_d| h_d.  The
+        // rounding of this form is covered by a margin of 6 * thresh instead of 4 * thresh.
+        const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
+        const float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
+        const float lim = fmaf(mx, rr.x, fmaf(my, rr.y, fmaf(mz, rr.z, rr.w))) + 1.5f * margin;
+        for (int j = 0; j < k; ++j) {
+          const float4 r = s_fast[j];
+          const float dj = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
+          const float reach = fmaf(fabsf(r.x - rr.x), hx, fmaf(fabsf(r.y - rr.y), hy, fabsf(r.z - rr.z) * hz));
+          ncand += (dj - reach <= lim) ? 1 : 0;  // j == ref: reach = 0, dj <= lim: counted once
+        }
       } else {
         // Only centroids near the group can win: d_j(x) <= d_ref(x) + margin at some x of the box
         // implies |x - c_j| <= sqrt(r^2 + margin), r = largest distance from c_ref to the box;
