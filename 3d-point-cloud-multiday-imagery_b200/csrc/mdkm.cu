@@ -89,6 +89,7 @@ struct mdkm_handle {
   DevStatus* h_status = nullptr;  // pinned, 2 slots
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
   int last_k = 0;
+  int occ_k = -1, occ_step = 0, occ_final = 0;  // occupancy of the step / final kernels for occ_k clusters
   long long stat_refined = 0, stat_reloc = 0;
   double stat_tol = 0.0;
 
@@ -511,10 +512,18 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   // persistent grids: one full wave of resident CTAs (occupancy queried from the runtime)
   int occ_step = 1, occ_final = 1;
   kb.step_fn = pick_step_kernel(kb.wide, kb.priv, kb.kpad);
-  OK(step_occupancy(h, kb.step_fn, kb.step_smem, &occ_step));
   kb.final_fn = pick_final_kernel(kb.kpad);
-  CU(cudaFuncSetAttribute(kb.final_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb.final_smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, kb.final_fn, kThreads, kb.final_smem));
+  if (h->occ_k == k) {  // same kernels and shared-memory sizes as the last fit on this handle
+    occ_step = h->occ_step;
+    occ_final = h->occ_final;
+  } else {
+    OK(step_occupancy(h, kb.step_fn, kb.step_smem, &occ_step));
+    CU(cudaFuncSetAttribute(kb.final_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb.final_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_final, kb.final_fn, kThreads, kb.final_smem));
+    h->occ_k = k;
+    h->occ_step = occ_step;
+    h->occ_final = occ_final;
+  }
   if (occ_step < 1) return fail(h, MDKM_ERR_INVALID, "k=%d does not fit the shared-memory tables", k);
   kb.step_grid = grid_for(h, tiles, std::max(1, occ_step));
   kb.final_grid = grid_for(h, tiles, std::max(1, occ_final));
@@ -1228,6 +1237,12 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       enq += nb;
     }
     if (inflight == 0) break;
+    if (inflight == 2 && enq >= max_iter) {
+      // nothing more to enqueue: the newer batch's status supersedes the older one (a pause or
+      // an early exit makes every later kernel return at once), so wait only for that
+      head ^= 1;
+      --inflight;
+    }
     CU(cudaEventSynchronize(h->batch_ev[head]));
     const DevStatus s = h->h_status[head];
     head ^= 1;
@@ -1250,7 +1265,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
     }
     if (s.done) break;
   }
-  CU(cudaStreamSynchronize(h->stream));
+  // (no synchronisation here: everything below is ordered behind the loop on the stream)
 
   // final E-step (unless strict) + inertia + int32 labels
   int* labels_dev = nullptr;
