@@ -1402,9 +1402,28 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
   const long long per_warp = (n_groups + n_warps - 1) / n_warps;
   const long long g_first = ((long long)blockIdx.x * (kThreads / 32) + warp) * per_warp;
   const long long g_last = min(n_groups, g_first + per_warp);
+  // few centroids: the next group's block is requested before this one is worked on (one group
+  // of look-ahead in registers) -- a warp walks its run serially, so without it every group pays
+  // a DRAM round trip.  With many centroids the pass is bound by the candidate walk instead and
+  // the registers are better spent there.
+  constexpr bool kAhead = kChunks > 0;
+  float4 nx = make_float4(0.f, 0.f, 0.f, 0.f), ny = nx, nz = nx;
+  if (kAhead && g_first < g_last) {
+    const float* blk = p.pts + g_first * kBlockFloats + lane * 4;
+    nx = ldg_stream_f4(blk); ny = ldg_stream_f4(blk + kGroup); nz = ldg_stream_f4(blk + 2 * kGroup);
+  }
   for (long long g = g_first; g < g_last; ++g) {
-    const float* blk = p.pts + g * kBlockFloats + lane * 4;
-    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
+    float4 vx, vy, vz;
+    if (kAhead) {
+      vx = nx; vy = ny; vz = nz;
+      if (g + 1 < g_last) {
+        const float* blk = p.pts + (g + 1) * kBlockFloats + lane * 4;
+        nx = ldg_stream_f4(blk); ny = ldg_stream_f4(blk + kGroup); nz = ldg_stream_f4(blk + 2 * kGroup);
+      }
+    } else {
+      const float* blk = p.pts + g * kBlockFloats + lane * 4;
+      vx = ldg_stream_f4(blk); vy = ldg_stream_f4(blk + kGroup); vz = ldg_stream_f4(blk + 2 * kGroup);
+    }
     const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
     const long long i0 = g * kGroup + lane * 4;
     int lab[4];

@@ -463,27 +463,26 @@ int build_mirror(mdkm_handle* h, int cell_px) {
   g.n_seg = n_seg;
   g.seg_off = h->d_seg_off.p;
   const long long n_cells = gx * gy;
-  // bands of rows: about 32 groups of every segment per band
+  // bands of rows: kMirrorGpb groups of every segment per band
   long long max_groups = 1;
   for (int sgm = 0; sgm < n_seg; ++sgm)
     max_groups = std::max(max_groups, (seg[sgm + 1] + kGroup - 1) / kGroup - (seg[sgm] + kGroup - 1) / kGroup + 1);
-  g.gpb = 32;
-  const long long n_bands = (max_groups + g.gpb - 1) / g.gpb;
-  g.n_virtual = n_bands * n_seg * g.gpb;
-  OK(ensure(h, h->cell_counts, (size_t)n_cells + 1));
+  const long long n_bands = (max_groups + kMirrorGpb - 1) / kMirrorGpb;
+  g.n_virtual = n_bands * n_seg * kMirrorGpb;
+  const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
+  OK(ensure(h, h->cell_counts, (size_t)n_tiles * kScanTile));  // whole tiles: the scan reads 128-bit words
   OK(ensure(h, h->cell_offsets, (size_t)n_cells + 2));
   CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));
   const int grid = grid_for(h, (h->n + 1023) / 1024, 8);
   mirror_count_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_counts.p);
-  const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
   OK(ensure(h, h->partials, (size_t)std::max(n_tiles, h->sm_count * 8) * 8 + 16));
   long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
   mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
   mirror_scan_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, tile_sums);
   ++h->launches;
-  CU(cudaMemsetAsync(h->cell_counts.p, 0, (size_t)n_cells * 4, h->stream));  // now the arrival cursors
-  mirror_scatter_kernel<<<grid, kThreads, 0, h->stream>>>(h->pts.p, h->n, g, h->cell_offsets.p, h->cell_counts.p,
-                                                          h->tpts.p);
+  // the cells' start offsets become their arrival cursors
+  mirror_scatter_kernel<<<grid, kThreads, 0, h->stream>>>(
+      h->pts.p, h->n, g, reinterpret_cast<unsigned long long*>(h->cell_offsets.p), h->tpts.p);
   h->launches += 3;
   CU(cudaGetLastError());
   return MDKM_OK;

@@ -21,60 +21,58 @@
 namespace mdkm {
 
 constexpr int kMirrorMaxSeg = 1024;  // segment table held in shared memory
+constexpr int kMirrorGpb = 32;       // groups per band and segment
 
 struct MirrorGrid {
   float x0, y0;          // lower corner of the cloud's bounding box
   float inv_cx, inv_cy;  // 1 / cell size
-  int gx, gy;            // cells per dimension and segment
+  int gx, gy;            // cells per dimension
   int n_seg;
   const long long* seg_off;  // [n_seg + 1] point offsets of the segments (device)
-  long long gpb;             // groups per band and segment
-  long long n_virtual;       // n_bands * n_seg * gpb
+  long long n_virtual;       // n_bands * n_seg * kMirrorGpb
 };
 
 // Cell of a point.  Cells are wide in x (a raster row contributes a run of consecutive points
 // to a cell, which keeps the scattered writes sector-sized) and short in y.
-__device__ __forceinline__ int mirror_cell(const MirrorGrid& g, int seg, float x, float y) {
+__device__ __forceinline__ int mirror_cell(const MirrorGrid& g, float x, float y) {
   const int cx = min(g.gx - 1, max(0, (int)((x - g.x0) * g.inv_cx)));
   const int cy = min(g.gy - 1, max(0, (int)((y - g.y0) * g.inv_cy)));
-  (void)seg;
   return cy * g.gx + cx;
-}
-
-// The cell of this lane's four points (-1 beyond n).  `seg` is the segment of the group's
-// first point; a group that straddles a boundary walks on to the next segments.
-__device__ __forceinline__ void mirror_cells4(const MirrorGrid& g, const long long* s_off, int seg, long long i0,
-                                              long long n, const float (&xs)[4], const float (&ys)[4], int (&cell)[4]) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const long long i = i0 + e;
-    while (seg < g.n_seg - 1 && i >= s_off[seg + 1]) ++seg;
-    cell[e] = i < n ? mirror_cell(g, seg, xs[e], ys[e]) : -1;
-  }
 }
 
 // Traversal order of the two passes below: band of rows outermost, segment (day) inside.  The
 // points of a cell come from the same few raster rows of EVERY day; visiting those rows of all
 // days together keeps the partial writes to the cell's range close in time, so they merge in
-// L2 instead of being evicted half-filled.  Days are cut into n_bands runs of `gpb` groups;
-// virtual index v = (band * n_seg + seg) * gpb + j  ->  group seg_first[seg] + band * gpb + j.
-__device__ __forceinline__ long long mirror_group_of(const MirrorGrid& g, const long long* s_off, long long v,
-                                                     int& seg) {
-  const long long per_band = (long long)g.n_seg * g.gpb;
-  const long long band = v / per_band;
-  const long long r = v - band * per_band;
-  seg = (int)(r / g.gpb);
-  const long long j = r - (long long)seg * g.gpb;
+// L2 instead of being evicted half-filled.  Days are cut into n_bands runs of kMirrorGpb groups;
+// virtual index v = (band * n_seg + seg) * kMirrorGpb + j  ->  group seg_first[seg] + band * kMirrorGpb + j.
+// (32-bit arithmetic: v / kMirrorGpb is below 2^32 for any cloud that fits the device.)
+__device__ __forceinline__ long long mirror_group_of(const MirrorGrid& g, const long long* s_off, long long v) {
+  const unsigned int t = (unsigned int)(v / kMirrorGpb);
+  const unsigned int j = (unsigned int)v & (kMirrorGpb - 1);
+  const unsigned int band = t / (unsigned int)g.n_seg;
+  const unsigned int seg = t - band * (unsigned int)g.n_seg;
   // groups that START inside the segment belong to it (a straddling group goes with its first point)
   const long long first = (s_off[seg] + kGroup - 1) / kGroup;
   const long long last = (s_off[seg + 1] + kGroup - 1) / kGroup;  // exclusive
-  const long long grp = first + band * g.gpb + j;
+  const long long grp = first + (long long)band * kMirrorGpb + j;
   return grp < last ? grp : -1;
 }
 
-// counts[cell] += 1 for every point.  A lane's four consecutive points usually share a cell,
-// and so do neighbouring lanes: equal cells are merged first in the lane, then across the
-// warp (match.any), and one atomic is issued per distinct cell.
+// Runs of equal cells among the 32 consecutive points a warp holds in one round (one point per
+// lane).  Consecutive points of a raster row share a cell for cell-width pixels, so a round
+// holds a few runs; the first lane of every run acts for it.  `head_lane`: the first lane of
+// this lane's run; `run_len`: the length of the run (valid in its first lane).
+__device__ __forceinline__ bool mirror_runs(int cell, int lane, int& head_lane, int& run_len) {
+  const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+  const bool head = lane == 0 || cell != prev;
+  const unsigned int heads = __ballot_sync(0xffffffffu, head);
+  head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const unsigned int later = heads & ~((2u << lane) - 1u);  // heads after this lane
+  run_len = (later ? __ffs(later) - 1 : 32) - lane;
+  return head;
+}
+
+// counts[cell] += 1 for every point: one atomic per run of equal cells.
 __global__ void __launch_bounds__(kThreads) mirror_count_kernel(const float* pts, long long n, MirrorGrid g,
                                                                 unsigned int* counts) {
   __shared__ long long s_off[kMirrorMaxSeg + 1];
@@ -83,24 +81,21 @@ __global__ void __launch_bounds__(kThreads) mirror_count_kernel(const float* pts
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long v = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); v < g.n_virtual; v += stride) {
-    int seg;
-    const long long grp = mirror_group_of(g, s_off, v, seg);
+    const long long grp = mirror_group_of(g, s_off, v);
     if (grp < 0) continue;  // warp-uniform
-    const float* blk = pts + grp * kBlockFloats + lane * 4;
-    const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup);
-    const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
-    int cell[4];
-    mirror_cells4(g, s_off, seg, grp * kGroup + lane * 4, n, xs, ys, cell);
-    const bool same = cell[0] == cell[1] && cell[0] == cell[2] && cell[0] == cell[3];
-    if (__all_sync(0xffffffffu, same)) {
-      const unsigned int peers = __match_any_sync(0xffffffffu, cell[0]);
-      if (cell[0] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&counts[cell[0]], 4u * (unsigned int)__popc(peers));
-    } else {
+    const float* blk = pts + grp * kBlockFloats + lane;
+    float xs[4], ys[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned int peers = __match_any_sync(0xffffffffu, cell[e]);
-        if (cell[e] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&counts[cell[e]], (unsigned int)__popc(peers));
-      }
+    for (int r = 0; r < 4; ++r) {
+      xs[r] = __ldg(blk + r * 32);
+      ys[r] = __ldg(blk + kGroup + r * 32);
+    }
+    const bool full = (grp + 1) * kGroup <= n;  // warp-uniform; only the cloud's last group is not
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cell = (full || grp * kGroup + r * 32 + lane < n) ? mirror_cell(g, xs[r], ys[r]) : -1;
+      int head_lane, run_len;
+      if (mirror_runs(cell, lane, head_lane, run_len) && cell >= 0) atomicAdd(&counts[cell], (unsigned int)run_len);
     }
   }
 }
@@ -108,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) mirror_count_kernel(const float* pts
 // Exclusive scan of n 32-bit counts into 64-bit offsets in two launches: per-CTA totals of
 // kScanTile counts, then every CTA adds up the totals before it (a few dozen values) and
 // scans its own tile.
-constexpr int kScanItems = 16;
+constexpr int kScanItems = 4;
 constexpr int kScanTile = 1024 * kScanItems;
 
 __global__ void __launch_bounds__(1024) mirror_tile_sums_kernel(const unsigned int* counts, long long n,
@@ -130,9 +125,10 @@ __global__ void __launch_bounds__(1024) mirror_tile_sums_kernel(const unsigned i
   }
 }
 
+// counts: capacity padded to a whole tile (the 128-bit loads of the last tile stay inside it).
 __global__ void __launch_bounds__(1024) mirror_scan_kernel(const unsigned int* counts, long long n, long long* offsets,
                                                            const long long* tile_sums) {
-  constexpr int kItems = kScanItems;
+  static_assert(kScanItems == 4, "one 128-bit load per thread");
   __shared__ long long s_warp[32];
   __shared__ long long s_carry;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -142,78 +138,78 @@ __global__ void __launch_bounds__(1024) mirror_scan_kernel(const unsigned int* c
     for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     if (tid == 0) s_carry = t;
   }
+  const long long i0 = (long long)blockIdx.x * kScanTile + (long long)tid * kScanItems;
+  const uint4 raw = *reinterpret_cast<const uint4*>(counts + i0);
+  const unsigned int v[4] = {i0 < n ? raw.x : 0u, i0 + 1 < n ? raw.y : 0u, i0 + 2 < n ? raw.z : 0u,
+                             i0 + 3 < n ? raw.w : 0u};
+  const long long mine = (long long)v[0] + v[1] + v[2] + v[3];
+  long long incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
   __syncthreads();
-  {
-    const long long base = (long long)blockIdx.x * kScanTile;
-    const long long i0 = base + (long long)tid * kItems;
-    unsigned int v[kItems];
-    long long mine = 0;
-#pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-      v[e] = (i0 + e < n) ? counts[i0 + e] : 0u;
-      mine += v[e];
-    }
-    long long incl = mine;
+  if (w == 0) {
+    long long ws = s_warp[lane];
     for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const long long t = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += t;
     }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      long long ws = s_warp[lane];
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += t;
-      }
-      s_warp[lane] = ws;
-    }
-    __syncthreads();
-    const long long carry = s_carry;
-    long long run = carry + (w ? s_warp[w - 1] : 0) + (incl - mine);
+    s_warp[lane] = ws;
+  }
+  __syncthreads();
+  long long run = s_carry + (w ? s_warp[w - 1] : 0) + (incl - mine);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-      if (i0 + e < n) offsets[i0 + e] = run;
-      run += v[e];
-    }
+  for (int e = 0; e < kScanItems; ++e) {
+    if (i0 + e < n) offsets[i0 + e] = run;
+    run += v[e];
   }
 }
 
-// dst = offsets[cell] + (arrival rank inside the cell); copies x, y, z into the mirror.
-// One point per lane and round (four rounds per group): the lanes that share a cell hold
-// consecutive points of a raster row and get consecutive slots, so every store instruction
-// writes whole runs instead of 4-byte fragments.
+// dst = (cursor of the cell)++ ; copies x, y, z into the mirror.  `cursors` enters as the
+// cells' start offsets (the scan's output) and is consumed: every run of equal cells takes its
+// slots with ONE 64-bit atomic on the cell's cursor.  One point per lane and round (four rounds
+// per group): the lanes of a run hold consecutive points of a raster row and get consecutive
+// slots, so every store instruction writes whole runs instead of 4-byte fragments.  The four
+// atomics of a group are issued back to back, before the first result is needed: their round
+// trips overlap.
 __global__ void __launch_bounds__(kThreads) mirror_scatter_kernel(const float* pts, long long n, MirrorGrid g,
-                                                                  const long long* offsets, unsigned int* cursor,
-                                                                  float* tpts) {
+                                                                  unsigned long long* cursors, float* tpts) {
   __shared__ long long s_off[kMirrorMaxSeg + 1];
   for (int i = threadIdx.x; i <= g.n_seg; i += kThreads) s_off[i] = g.seg_off[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long v = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); v < g.n_virtual; v += stride) {
-    int seg;
-    const long long grp = mirror_group_of(g, s_off, v, seg);
+    const long long grp = mirror_group_of(g, s_off, v);
     if (grp < 0) continue;  // warp-uniform
-    const float* blk = pts + grp * kBlockFloats;
+    const float* blk = pts + grp * kBlockFloats + lane;
     float xs[4], ys[4], zs[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      xs[r] = __ldg(blk + r * 32 + lane);
-      ys[r] = __ldg(blk + kGroup + r * 32 + lane);
-      zs[r] = __ldg(blk + 2 * kGroup + r * 32 + lane);
+      xs[r] = __ldg(blk + r * 32);
+      ys[r] = __ldg(blk + kGroup + r * 32);
+      zs[r] = __ldg(blk + 2 * kGroup + r * 32);
+    }
+    const bool full = (grp + 1) * kGroup <= n;  // warp-uniform
+    int head_lane[4];
+    bool valid[4];
+    unsigned long long base[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cell = (full || grp * kGroup + r * 32 + lane < n) ? mirror_cell(g, xs[r], ys[r]) : -1;
+      int run_len;
+      const bool head = mirror_runs(cell, lane, head_lane[r], run_len);
+      valid[r] = cell >= 0;
+      base[r] = 0;
+      if (head && valid[r]) base[r] = atomicAdd(&cursors[cell], (unsigned long long)run_len);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const long long i = grp * kGroup + r * 32 + lane;
-      const int cell = i < n ? mirror_cell(g, seg, xs[r], ys[r]) : -1;
-      const unsigned int peers = __match_any_sync(0xffffffffu, cell);
-      const int leader = __ffs(peers) - 1;
-      unsigned int base = 0;
-      if (cell >= 0 && lane == leader) base = atomicAdd(&cursor[cell], (unsigned int)__popc(peers));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (cell >= 0) {
-        float* q = tpts + pt_off(offsets[cell] + base + __popc(peers & ((1u << lane) - 1u)));
+      const unsigned long long b = __shfl_sync(0xffffffffu, base[r], head_lane[r]);
+      if (valid[r]) {
+        float* q = tpts + pt_off((long long)b + (lane - head_lane[r]));
         q[0] = xs[r];
         q[kGroup] = ys[r];
         q[2 * kGroup] = zs[r];
