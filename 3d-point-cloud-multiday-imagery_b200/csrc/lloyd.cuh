@@ -558,6 +558,7 @@ struct FinalParams {
   DevStatus* st;
   FrameF f;
   int k, kpad;
+  int split_rows;             // 1: raster-ordered cloud (row-major runs of pixels)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -572,13 +573,16 @@ struct FinalParams {
 // The true nearest centroid of every point, and every centroid within the FP32 error band of
 // it, beats-or-ties i at that point, so it is a candidate: the result equals brute force.
 // Returns the number of candidates; the labels of this lane's points are in lab[].
+// count_mask: bit e clear = point e of this lane is a stand-in (see lloyd_final_kernel) and is
+// left out of the n_refined statistic.
 // ---------------------------------------------------------------------------------------
 template <int kChunks>
 __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&yc)[4], const float (&zc)[4],
                                             const float* orig_x, const float* orig_y, const float* orig_z,
                                             const FrameF& f, const float4* __restrict__ s_fast,
                                             const double4* __restrict__ c64, int k, int kp32, float thresh,
-                                            int lane, int (&lab)[4], unsigned int& n_refined) {
+                                            int lane, int (&lab)[4], unsigned int& n_refined,
+                                            unsigned int count_mask = 0xfu) {
   // bounding box of the group (FMNMX3 + CREDUX.F32)
   const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
   const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
@@ -736,7 +740,7 @@ __device__ __forceinline__ int assign_group(const float (&xc)[4], const float (&
       }
       if (ambig[e]) {
         lab[e] = bi;
-        ++n_refined;
+        n_refined += (count_mask >> e) & 1u;  // (stand-in points of a split group are not counted)
       }
     }
   }
@@ -761,7 +765,7 @@ __device__ __forceinline__ int assign_group_bucketed(const float (&xc)[4], const
                                                      const double4* __restrict__ c64, const unsigned char* s_bkt,
                                                      int k, int kp32, float thresh, int ref_hint,
                                                      unsigned short* s_cand, int lane, int (&lab)[4],
-                                                     unsigned int& n_refined) {
+                                                     unsigned int& n_refined, unsigned int count_mask = 0xfu) {
   const float bx0 = redux_min_f32(fminf(fminf(xc[0], xc[1]), fminf(xc[2], xc[3])));
   const float bx1 = redux_max_f32(fmaxf(fmaxf(xc[0], xc[1]), fmaxf(xc[2], xc[3])));
   const float by0 = redux_min_f32(fminf(fminf(yc[0], yc[1]), fminf(yc[2], yc[3])));
@@ -863,7 +867,7 @@ __device__ __forceinline__ int assign_group_bucketed(const float (&xc)[4], const
       }
       if (ambig[e]) {
         lab[e] = bi;
-        ++n_refined;
+        n_refined += (count_mask >> e) & 1u;  // (stand-in points of a split group are not counted)
       }
     }
   }
@@ -1355,6 +1359,74 @@ __global__ void read_sums_kernel(const unsigned long long* acc, int k, Frame fr,
 }
 
 // ---------------------------------------------------------------------------------------
+// In raster order a group is a strip of one row -- except the one that runs over the end of a
+// row (one in W/128): its box spans the whole width of the frame, every cluster along the row
+// becomes a candidate and the group costs as much as dozens of others.  Such a group is
+// assigned in two halves (the points of its first row, then the rest), each with its own small
+// box; in each half the points of the other one are replaced by a stand-in from this half,
+// whose result is dropped.  Same labels as the one-box form: both are exact.
+// ---------------------------------------------------------------------------------------
+template <int kChunks>
+__device__ __forceinline__ void assign_split_group(const float (&xo)[4], const float (&yo)[4], const float (&zo)[4],
+                                                   const FrameF& f, const float4* __restrict__ s_fast,
+                                                   const double4* __restrict__ c64, const unsigned char* s_bkt,
+                                                   int k, int kp32, float thresh, unsigned short* s_cand, int lane,
+                                                   int (&lab)[4], unsigned int& n_ref) {
+  const float y_head = __shfl_sync(0xffffffffu, yo[0], 0);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int src_lane = half ? 31 : 0;  // the group's first / last point belongs to this half
+    const float sx = __shfl_sync(0xffffffffu, half ? xo[3] : xo[0], src_lane);
+    const float sy = __shfl_sync(0xffffffffu, half ? yo[3] : yo[0], src_lane);
+    const float sz = __shfl_sync(0xffffffffu, half ? zo[3] : zo[0], src_lane);
+    float hx[4], hy[4], hz[4], hxc[4], hyc[4], hzc[4];
+    unsigned int mine = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool in_half = (yo[e] == y_head) == (half == 0);
+      mine |= in_half ? (1u << e) : 0u;
+      hx[e] = in_half ? xo[e] : sx;
+      hy[e] = in_half ? yo[e] : sy;
+      hz[e] = in_half ? zo[e] : sz;
+      hxc[e] = hx[e] - f.ox; hyc[e] = hy[e] - f.oy; hzc[e] = hz[e] - f.oz;
+    }
+    int hl[4];
+    int ncand = -1;
+    if (kChunks == 0 && s_bkt)
+      ncand = assign_group_bucketed(hxc, hyc, hzc, hx, hy, hz, f, s_fast, c64, s_bkt, k, kp32, thresh, -1, s_cand,
+                                    lane, hl, n_ref, mine);
+    if (ncand < 0) assign_group<kChunks>(hxc, hyc, hzc, hx, hy, hz, f, s_fast, c64, k, kp32, thresh, lane, hl, n_ref, mine);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lab[e] = ((mine >> e) & 1u) ? hl[e] : lab[e];
+  }
+}
+
+// labels and FP64 inertia (direct form) of this lane's four points of a group
+__device__ __forceinline__ void final_emit(const FinalParams& p, const double4* __restrict__ c64, const FrameF& f,
+                                           long long i0, const float (&xo)[4], const float (&yo)[4],
+                                           const float (&zo)[4], const int (&lab)[4], double& inert) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (i0 + e < p.n) {
+      const double4 c = ld_c64(&c64[lab[e]]);
+      const double dx = ((double)xo[e] - (double)f.ox) - c.x;
+      const double dy = ((double)yo[e] - (double)f.oy) - c.y;
+      const double dz = ((double)zo[e] - (double)f.oz) - c.z;
+      inert += dx * dx + dy * dy + dz * dz;
+    }
+  }
+  if (p.labels_out) {
+    if (i0 + 3 < p.n && ((reinterpret_cast<uintptr_t>(p.labels_out) & 15) == 0)) {
+      *reinterpret_cast<int4*>(p.labels_out + i0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i0 + e < p.n) p.labels_out[i0 + e] = lab[e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Final pass over the resident cloud (reference point order): E-step with the final centroids
 // -> int32 labels, and the inertia in FP64 (direct form, fixed-order reduction).
 // ---------------------------------------------------------------------------------------
@@ -1427,6 +1499,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
     const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
     const long long i0 = g * kGroup + lane * 4;
     int lab[4];
+    // a raster-order group that runs over the end of a row is left to the second loop below
+    if (p.split_rows && __shfl_sync(0xffffffffu, yo[0], 0) != __shfl_sync(0xffffffffu, yo[3], 31)) continue;
     const float xc[4] = {xo[0] - f.ox, xo[1] - f.ox, xo[2] - f.ox, xo[3] - f.ox};
     const float yc[4] = {yo[0] - f.oy, yo[1] - f.oy, yo[2] - f.oy, yo[3] - f.oy};
     const float zc[4] = {zo[0] - f.oz, zo[1] - f.oz, zo[2] - f.oz, zo[3] - f.oz};
@@ -1436,23 +1510,27 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalPar
                                     s_cand + warp * kCandCap, lane, lab, n_ref);
     if (ncand < 0) assign_group<kChunks>(xc, yc, zc, xo, yo, zo, f, s_fast, c64, p.k, kp32, thresh, lane, lab, n_ref);
     hint = __shfl_sync(0xffffffffu, lab[0], 0);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (i0 + e < p.n) {
-        const double4 c = ld_c64(&c64[lab[e]]);
-        const double dx = ((double)xo[e] - (double)f.ox) - c.x;
-        const double dy = ((double)yo[e] - (double)f.oy) - c.y;
-        const double dz = ((double)zo[e] - (double)f.oz) - c.z;
-        inert += dx * dx + dy * dy + dz * dz;
+    final_emit(p, c64, f, i0, xo, yo, zo, lab, inert);
+  }
+  // second loop: the groups that run over the end of a raster row (one in W/128), two halves each
+  if (p.split_rows) {
+    for (long long gb = g_first; gb < g_last; gb += 32) {
+      bool sp = false;
+      if (gb + lane < g_last) {
+        const float* ys = p.pts + (gb + lane) * kBlockFloats + kGroup;
+        sp = __ldg(ys) != __ldg(ys + kGroup - 1);
       }
-    }
-    if (p.labels_out) {
-      if (i0 + 3 < p.n && ((reinterpret_cast<uintptr_t>(p.labels_out) & 15) == 0)) {
-        *reinterpret_cast<int4*>(p.labels_out + i0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (i0 + e < p.n) p.labels_out[i0 + e] = lab[e];
+      unsigned int todo = __ballot_sync(0xffffffffu, sp);
+      while (todo) {  // warp-uniform
+        const long long g = gb + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float* blk = p.pts + g * kBlockFloats + lane * 4;
+        const float4 vx = ldg_stream_f4(blk), vy = ldg_stream_f4(blk + kGroup), vz = ldg_stream_f4(blk + 2 * kGroup);
+        const float xo[4] = {vx.x, vx.y, vx.z, vx.w}, yo[4] = {vy.x, vy.y, vy.z, vy.w}, zo[4] = {vz.x, vz.y, vz.z, vz.w};
+        int lab[4] = {0, 0, 0, 0};
+        assign_split_group<kChunks>(xo, yo, zo, f, s_fast, c64, bkt_bytes ? s_bkt : nullptr, p.k, kp32, thresh,
+                                    s_cand + warp * kCandCap, lane, lab, n_ref);
+        final_emit(p, c64, f, g * kGroup + lane * 4, xo, yo, zo, lab, inert);
       }
     }
   }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -691,6 +692,7 @@ int run_final(mdkm_handle* h, const KmBuffers& kb, int* labels_dev) {
   fp.st = h->d_status;
   fp.f = h->ff;
   fp.k = kb.k; fp.kpad = kb.kpad;
+  fp.split_rows = h->raster_w > 0 ? 1 : 0;
   kb.final_fn<<<kb.final_grid, kThreads, kb.final_smem, h->stream>>>(fp);
   ++h->launches;
   CU(cudaGetLastError());
