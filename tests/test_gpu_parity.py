@@ -341,6 +341,32 @@ def test_predict_matches_oracle_e_step(engine):
     np.testing.assert_allclose(inertia, KO.inertia(P, C, ref), rtol=1e-9)
 
 
+@pytest.mark.parametrize("shape,k", [((3, 40, 50), 5), ((2, 90, 127), 40), ((2, 64, 333), 300), ((1, 7, 1000), 70)])
+def test_row_straddling_groups(engine, shape, k):
+    """Groups of 128 raster-ordered points that run over the end of a row (several rows when
+    the raster is narrow) are assigned in halves by the final pass; the mirror numbers its
+    rows of cells in serpentine order.  Labels and inertia must not notice either."""
+    D, H, W = shape
+    hm = synth.make_stack(D, H, W, seed=W + k, n_buildings=6).numpy()
+    P = UO.unproject_stack(hm)
+    n = engine.unproject(hm)
+    assert n == P.shape[0]
+    rs = np.random.RandomState(W)
+    C = P[np.sort(rs.choice(n, k, replace=False))] + rs.normal(0, 0.21, size=(k, 3))
+    labels, inertia = engine.predict(C)
+    mean = P.mean(axis=0)
+    ref = KO.e_step(P - mean, C - mean)
+    check_labels(P, C, ref, labels)
+    if (labels == ref).all():
+        np.testing.assert_allclose(inertia, KO.inertia(P, C, ref), rtol=1e-9)
+    r = engine.fit(C, max_iter=8, tol=0.0)
+    fit_ref = KO.kmeans_fit(P, C, max_iter=8, tol=0.0)
+    assert r["n_iter"] == fit_ref["n_iter"]
+    check_labels(P, fit_ref["centers"], fit_ref["labels"], r["labels"])
+    check_centroids(fit_ref["centers"], r["centers"], P)
+    np.testing.assert_allclose(r["inertia"], fit_ref["inertia"], rtol=1e-6)
+
+
 def test_fit_errors(engine):
     engine.set_points(np.zeros((3, 3), dtype=np.float32))
     with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):
