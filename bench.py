@@ -285,8 +285,11 @@ def run_mine(args):
     step_avg_ms = step_ms / max(n_steps, 1)
     achieved = ALGO_BYTES_PER_POINT_ITER * n_local / (step_avg_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic(args.config)
+    # the DRAM rate the kernel actually sustains: ncu's bytes per launch over the live duration
+    dram_gbs = (traffic / (step_avg_ms * 1e-3) / 1e9) if traffic else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
+                "dram_gbs": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
                 "kernel": "lloyd_step_kernel = one Lloyd iteration (classification pass, grid barrier, per-point pass, fused update)",
                 "avg_launch_ms": step_avg_ms,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT_ITER * n_local, "peak_source": peak_src,
