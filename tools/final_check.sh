@@ -5,10 +5,6 @@
 tag=${1:-x}
 out=gpurun_out
 mkdir -p $out
-for smem in 0 49152 36864; do
-  MDKM_SCATTER_SMEM=$smem python bench.py --no-e2e --no-cpu --steps 10 --warmup 3 > $out/x.json 2> $out/x.err
-  echo "scatter smem throttle $smem"; python tools/bench_brief.py $out/x.json
-done
 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; tail -2 $out/pytest_gpu_$tag.log
 python __graft_entry__.py smoke > $out/smoke_$tag.log 2>&1; tail -1 $out/smoke_$tag.log
 python bench.py > $out/bench_${tag}_c2.json 2> $out/bench_${tag}_c2.err
