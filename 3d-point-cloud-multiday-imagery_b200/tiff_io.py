@@ -28,7 +28,7 @@ _TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: (
 IMAGE_WIDTH, IMAGE_LENGTH, BITS_PER_SAMPLE, COMPRESSION, PHOTOMETRIC = 256, 257, 258, 259, 262
 STRIP_OFFSETS, SAMPLES_PER_PIXEL, ROWS_PER_STRIP, STRIP_BYTE_COUNTS = 273, 277, 278, 279
 PLANAR_CONFIG, TILE_WIDTH, TILE_LENGTH, TILE_OFFSETS, TILE_BYTE_COUNTS = 284, 322, 323, 324, 325
-SAMPLE_FORMAT = 339
+EXTRA_SAMPLES, SAMPLE_FORMAT = 338, 339
 
 
 class TiffError(ValueError):
@@ -192,6 +192,8 @@ def write_tiff(path: str, bands: np.ndarray, planar: bool = False, rows_per_stri
         (COMPRESSION, 3, (1,)), (PHOTOMETRIC, 3, (1,)), (SAMPLES_PER_PIXEL, 3, (S,)),
         (PLANAR_CONFIG, 3, (2 if planar else 1,)), (SAMPLE_FORMAT, 3, (kind,) * S),
     ]
+    if S > 1:  # MINISBLACK has one colour channel: the other bands are "unspecified" extra samples (as GDAL writes)
+        entries.append((EXTRA_SAMPLES, 3, (0,) * (S - 1)))
     if tile:
         entries += [(TILE_WIDTH, 3, (tile,)), (TILE_LENGTH, 3, (tile,)), (TILE_OFFSETS, off_t, tuple(offsets)),
                     (TILE_BYTE_COUNTS, off_t, tuple(len(b) for b in blocks))]

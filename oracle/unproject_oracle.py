@@ -3,10 +3,15 @@
 Restates, in float64 numpy and with the same library calls, the tail of
 ``HeightMapExtractor.run`` in the reference
 (``members/rafael/disparity/plugin.py:147-192``).  ``plugin.py`` itself cannot be
-imported in this image (it needs osgeo / rasterio / skimage / napari), and nothing in
-the reference pins this stage, so this restatement is pinned only
-by the hand-computed cases in ``tests/test_oracle.py`` -- **parity unpinned by the
-reference** for this stage.
+imported in this image (it needs osgeo / rasterio / skimage / napari) and the reference
+holds no test or fixture for this stage.  **Pinned** instead by
+outputs of the reference's own source lines: ``tests/golden/make_unproject_ref.py`` reads
+``plugin.py:148-192`` from the reference checkout, ``exec``s the lines verbatim (with
+``C.MAX_DISP`` and ``normalise_for_display`` executed from ``constants.py`` / ``utils.py``)
+on synthetic int16 disparities and stores every intermediate in
+``tests/golden/unproject_ref.npz``; ``tests/test_oracle.py`` requires this restatement to
+reproduce them bit for bit (valid mask, P, centre, normal, height_rel, h_min, h_max,
+h_norm, points_coords).
 
 The multi-day merge (one cloud for all days, day-major order) has no reference code
 (SURVEY.md F1); it is ``np.concatenate`` over what the reference's ``for pair`` loop
@@ -74,6 +79,8 @@ def unproject_stack(height_maps, validity_masks=None, limit=MAX_DISP / 2, detren
     hm = np.asarray(height_maps)
     if hm.ndim == 2:
         hm = hm[None]
+        if validity_masks is not None and np.asarray(validity_masks).ndim == 2:
+            validity_masks = np.asarray(validity_masks)[None]
     out = []
     for d in range(hm.shape[0]):
         vm = None if validity_masks is None else np.asarray(validity_masks)[d]
@@ -94,6 +101,8 @@ def reference_tail_stack(height_maps, validity_masks=None, limit=MAX_DISP / 2, d
     hm = np.asarray(height_maps)
     if hm.ndim == 2:
         hm = hm[None]
+        if validity_masks is not None and np.asarray(validity_masks).ndim == 2:
+            validity_masks = np.asarray(validity_masks)[None]
     pts, hns, los, his, off = [], [], [], [], [0]
     for d in range(hm.shape[0]):
         vm = None if validity_masks is None else np.asarray(validity_masks)[d]

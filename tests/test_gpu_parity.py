@@ -433,6 +433,33 @@ def test_reference_tail_golden(engine, golden):
     np.testing.assert_allclose(hn, g["tail_height_norm"], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_reference_lines_golden(engine, golden, case):
+    """The CUDA path against outputs of the reference's OWN source lines (plugin.py:148-192,
+    exec'd verbatim by tests/golden/make_unproject_ref.py): int16 disparity + validity mask in,
+    points_coords (napari z,y,x) + the 'height' property out."""
+    g = golden("unproject_ref.npz")
+    disp, vm = g[f"{case}_disparity"], g[f"{case}_validity_mask"]
+    # a1-a3: h = -disp/16, validity, np.where order -- bit-exact
+    n = engine.unproject(disp[None], vm[None], disparity_scale=-1.0 / 16.0)
+    assert n == int(g[f"{case}_valid_mask"].sum())
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), g[f"{case}_P"])
+    # a4: plane detrend (FP64 moments + Jacobi on the device, z stored as FP32)
+    n = engine.unproject(disp[None], vm[None], disparity_scale=-1.0 / 16.0, detrend=True)
+    cloud = engine.get_cloud(False).astype(np.float64)
+    np.testing.assert_array_equal(cloud[:, :2], g[f"{case}_P"][:, :2])
+    np.testing.assert_allclose(cloud[:, 2], g[f"{case}_height_rel"], rtol=0, atol=1e-4)
+    # a5: percentile levelling and the colour property
+    lo, hi, hn = engine.ground_level(True)
+    np.testing.assert_allclose(lo[0], float(g[f"{case}_h_min"]), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(hi[0], float(g[f"{case}_h_max"]), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(hn, g[f"{case}_h_norm"], rtol=0, atol=1e-5)
+    zyx = engine.get_cloud(napari_order=True).astype(np.float64)
+    ref = g[f"{case}_points_coords"]
+    np.testing.assert_array_equal(zyx[:, 1:], ref[:, 1:])
+    np.testing.assert_allclose(zyx[:, 0], ref[:, 0], rtol=0, atol=2e-4)
+
+
 def test_ground_level_needs_whole_days(engine):
     hm = synth.make_stack(2, 16, 16, seed=1, n_buildings=1).numpy().reshape(-1)
     engine.unproject(hm[5:300], stack_shape=(2, 16, 16), pix_begin=5)

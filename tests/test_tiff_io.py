@@ -93,3 +93,76 @@ def test_stacking_pads_with_invalid_pixels(tmp_path):
     with pytest.raises(tio.TiffError):
         tio.write_tiff(pa, a[:2])
         tio.load_height_rasters([pa])
+
+
+# ---- files written by INDEPENDENT TIFF writers (OpenCV's libtiff, Pillow), and our writer read
+# ---- back by them: the container code is not only checked against itself ----
+def test_reads_opencv_written_float32_rasters(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(5)
+    # 3-band Float32, the sample layout of the reference's 5-out-F.tif (disparity.py:213-224)
+    a = rs.uniform(-150, 150, size=(45, 70, 3)).astype(np.float32)
+    a[..., 2] = rs.rand(45, 70) > 0.3
+    a[3, 4, 0] = np.nan
+    p = str(tmp_path / "cv3.tif")
+    assert cv2.imwrite(p, a, [cv2.IMWRITE_TIFF_COMPRESSION, 1])  # 1 = none (GDAL's GTiff default)
+    got = tio.read_tiff(p)
+    assert got.shape == (45, 70, 3) and got.dtype == np.float32
+    # OpenCV keeps channels in BGR order in memory and writes RGB: the file holds them reversed
+    np.testing.assert_array_equal(got, a[..., ::-1])
+    np.testing.assert_array_equal(got[..., ::-1], cv2.imread(p, cv2.IMREAD_UNCHANGED))
+    # strips of a few rows each (libtiff's default strip size), not one block
+    for rows in (1, 7):
+        assert cv2.imwrite(p, a, [cv2.IMWRITE_TIFF_COMPRESSION, 1, cv2.IMWRITE_TIFF_ROWSPERSTRIP, rows])
+        np.testing.assert_array_equal(tio.read_tiff(p), a[..., ::-1])
+    # single band float32 / uint16 / uint8
+    for arr in (a[..., 0].copy(), (rs.rand(33, 21) * 65535).astype(np.uint16), (rs.rand(9, 300) * 255).astype(np.uint8)):
+        assert cv2.imwrite(p, arr, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+        got = tio.read_tiff(p)
+        assert got.dtype == arr.dtype
+        np.testing.assert_array_equal(got, arr)
+    # a compressed file (LZW; OpenCV only compresses integer samples) must be refused, not misread
+    assert cv2.imwrite(p, (rs.rand(64, 64) * 255).astype(np.uint8), [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    with pytest.raises(tio.TiffError, match="compressed"):
+        tio.read_tiff(p)
+
+
+def test_reads_pillow_written_rasters(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    rs = np.random.RandomState(6)
+    p = str(tmp_path / "pil.tif")
+    f32 = rs.uniform(-150, 150, size=(40, 61)).astype(np.float32)
+    Image.fromarray(f32).save(p)  # mode "F": one Float32 band, uncompressed strips
+    got = tio.read_tiff(p)
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, f32)
+    u16 = (rs.rand(25, 33) * 65535).astype(np.uint16)
+    Image.fromarray(u16).save(p)  # mode "I;16"
+    np.testing.assert_array_equal(tio.read_tiff(p), u16)
+    rgb = (rs.rand(19, 27, 3) * 255).astype(np.uint8)
+    Image.fromarray(rgb).save(p)  # chunky 8-bit RGB
+    np.testing.assert_array_equal(tio.read_tiff(p), rgb)
+    Image.fromarray(f32).save(p, tiffinfo={278: 3})  # RowsPerStrip = 3
+    np.testing.assert_array_equal(tio.read_tiff(p), f32)
+    Image.fromarray(f32).save(p, compression="tiff_lzw")
+    with pytest.raises(tio.TiffError, match="compressed"):
+        tio.read_tiff(p)
+
+
+@pytest.mark.parametrize("kw", [{}, {"planar": True}, {"rows_per_strip": 5}, {"tile": 16}, {"big": True},
+                                {"byteorder": ">"}])
+def test_our_writer_is_readable_by_opencv_and_pillow(tmp_path, kw):
+    """The GPU tests feed the device path with files from tio.write_tiff: an independent reader
+    (libtiff through OpenCV; Pillow for single-band files) must see the same pixels."""
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    bands = _raster(37, 53, seed=3)
+    p = str(tmp_path / "w.tif")
+    tio.write_tiff(p, bands, **kw)
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.shape == (37, 53, 3) and back.dtype == np.float32
+    if not kw.get("planar"):  # OpenCV's decoder ignores PlanarConfiguration=2 (reads the planes as chunky pixels)
+        np.testing.assert_array_equal(back[..., ::-1], np.moveaxis(bands, 0, 2))  # OpenCV returns BGR
+    tio.write_tiff(p, bands[0], **kw)
+    np.testing.assert_array_equal(np.asarray(Image.open(p)), bands[0])
+    np.testing.assert_array_equal(cv2.imread(p, cv2.IMREAD_UNCHANGED), bands[0])
