@@ -16,6 +16,7 @@ MDKM_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
 HM_F32, HM_I16, HM_F32_GTIFF3 = 0, 1, 2
 POINTS_AOS, POINTS_SOA = 0, 1
+OPT_SETTLE_GROUPS = 1
 NCCL_UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
@@ -41,6 +42,12 @@ SIGNATURES = {
     "mdkm_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_ubyte)]),
     "mdkm_comm_p2p_handle": (c_int, [c_void_p, POINTER(c_ubyte)]),
     "mdkm_comm_p2p_open": (c_int, [c_void_p, POINTER(c_ubyte)]),
+    "mdkm_comm_p2p_close": (c_int, [c_void_p]),
+    "mdkm_comm_p2p_buffer": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "mdkm_comm_p2p_open_ptrs": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "mdkm_get_stream": (c_void_p, [c_void_p]),
+    "mdkm_set_option": (c_int, [c_void_p, c_int, c_int64]),
+    "mdkm_fit_worklist": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "mdkm_unproject": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int,
                                c_int64, c_int64, c_float, c_int, c_int, POINTER(c_int64)]),
     "mdkm_bind_cloud_output": (c_int, [c_void_p, c_void_p, c_int64, c_int]),

@@ -236,6 +236,7 @@ def to_layers(result: FusionResult, prefix: str = "Multi-day") -> List[Layer]:
     face = "cluster"
     if result.height_norm is not None:
         props["height"] = result.height_norm  # plugin.py:186-188
+        face = "height"                       # plugin.py:231: the reference colours by 'height'
     layers: List[Layer] = [(
         result.fused_cloud,
         {
@@ -270,9 +271,12 @@ class MultiDayFusionPlugin:
 
     requires_image = False  # plugin.py:30
 
-    def __init__(self, n_clusters=8, device=0, **kmeans_kwargs):
+    def __init__(self, n_clusters=8, device=0, log_path=None, **kmeans_kwargs):
+        """``log_path``: where the traceback of a failed run is appended, like the reference's
+        ``data/TEMP/log.txt`` (plugin.py:48, 236-240); None = only printed."""
         self.n_clusters = n_clusters
         self.device = device
+        self.log_path = log_path
         self.kmeans_kwargs = kmeans_kwargs
 
     @property
@@ -290,4 +294,10 @@ class MultiDayFusionPlugin:
             return to_layers(res)
         except Exception as e:  # noqa: BLE001 - reference convention, plugin.py:236-241
             traceback.print_exc()
+            if self.log_path is not None:
+                try:  # plugin.py:238-239: f.writelines(f"Error: {e}\n{traceback}") into TEMP/log.txt
+                    with open(self.log_path, "a") as f:
+                        f.writelines(f"Error: {str(e)}\n{traceback.format_exc()}")
+                except OSError:
+                    pass
             return [(np.ones((100, 100)), {"name": f"Error: {str(e)}"}, "image")]

@@ -46,6 +46,7 @@ struct DevStatus {
   unsigned long long epoch;       // fused steps completed since the communicator was created
   int xchg_timeout;               // 1: a kernel-side wait (peer sums, grid barrier) timed out (fatal)
   unsigned int grid_bar;          // arrival counter of the step kernel's grid barrier
+  unsigned long long work_sum;    // groups handed to the per-point pass, summed over the fused steps of a fit
   // diagnostics (MDKM_TIMING builds only): globaltimer stamps of the last fused step, ns
   unsigned long long t_start, t_first_done, t_last_done, t_update_done, t_classify_start, t_classify_done;
 };

@@ -319,6 +319,8 @@ struct StepParams {
   int ignore_status;          // 1: test hook (run even when done/paused)
   int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
                               //    (NVLink, no host, no NCCL) and runs the centroid update
+  int settle;                 // 0: measurement mode, no group is settled from its summary --
+                              //    every point goes through the per-point pass (MDKM_OPT_SETTLE_GROUPS)
   const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
   int* worklist;              // groups the classification pass could not settle
   int* work_count;            // number of entries; cleared by the tail of the kernel
@@ -398,7 +400,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
                                                 bool first_iter, unsigned long long* s_acc, int* s_list,
-                                                const unsigned char* s_bkt, unsigned int& n_chg) {
+                                                const unsigned char* s_bkt, unsigned int& n_chg, bool settle) {
   const int tid = threadIdx.x, lane = tid & 31;
   int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
   int w_count = 0;                                                         // warp-uniform
@@ -415,7 +417,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
     const bool valid = g < n_groups;
     int label = -1;  // settled label, or -1: needs the per-point pass
     const int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
-    if (valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
+    if (settle && valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
       const float lo0 = a.x, lo1 = a.y, lo2 = a.z, hi0 = a.w, hi1 = b.x, hi2 = b.y;
       int ref = prev;
       if (ref < 0) {  // nearest centroid to the box centre, lowest index on ties
@@ -1055,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
   classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
                                   4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
-                                  bkt_bytes ? s_bkt : nullptr, n_chg);
+                                  bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
@@ -1281,7 +1283,10 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __threadfence();
   if (tid == 0) {
     p.st->ticket = 0u;
-    if (p.work_count) *p.work_count = 0;
+    if (p.work_count) {
+      p.st->work_sum += (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
+      *p.work_count = 0;
+    }
   }
   if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
   lloyd_update_body(p.upd);

@@ -91,8 +91,9 @@ struct mdkm_handle {
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
   int last_k = 0;
   int occ_k = -1, occ_step = 0, occ_final = 0;  // occupancy of the step / final kernels for occ_k clusters
-  long long stat_refined = 0, stat_reloc = 0;
+  long long stat_refined = 0, stat_reloc = 0, stat_work = 0, stat_groups = 0;
   double stat_tol = 0.0;
+  int opt_settle = 1;  // MDKM_OPT_SETTLE_GROUPS
 
   // unprojection scratch
   DevBuf<unsigned int> chunk_counts;
@@ -140,7 +141,7 @@ struct mdkm_handle {
   int n_ranks = 1, rank = 0;
   // NVLink peer exchange of the partial sums (CUDA IPC): own buffer, peers' mappings
   unsigned long long* xchg = nullptr;
-  void* peer_base[kMaxRanks] = {};
+  void* peer_base[kMaxRanks] = {};  // mappings opened with cudaIpcOpenMemHandle (closed by close_p2p)
   PeerXchg px{};
   bool p2p_ok = false;
   unsigned long long epoch_base = 0;  // fused steps completed on this communicator
@@ -580,6 +581,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.k = kb.k; sp.kpad = kb.kpad;
   sp.ignore_status = ignore_status;
   sp.fuse_update = fuse_update;
+  sp.settle = h->opt_settle;
   if (fuse_update) {
     sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
     sp.px = h->px;
@@ -859,6 +861,69 @@ int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles) {
   h->p2p_ok = true;
   h->epoch_base = 0;
   return MDKM_OK;
+}
+
+int mdkm_comm_p2p_close(mdkm_handle* h) {
+  if (!h) return MDKM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  close_p2p(h);
+  return MDKM_OK;
+}
+
+int mdkm_comm_p2p_buffer(mdkm_handle* h, void** out_device_ptr) {
+  if (!h || !out_device_ptr) return MDKM_ERR_INVALID;
+  if (!h->xchg) return fail(h, MDKM_ERR_STATE, "call mdkm_comm_p2p_handle first");
+  *out_device_ptr = h->xchg;
+  return MDKM_OK;
+}
+
+int mdkm_comm_p2p_open_ptrs(mdkm_handle* h, void* const* buffers) {
+  if (!h || !buffers) return MDKM_ERR_INVALID;
+  if (!h->xchg) return fail(h, MDKM_ERR_STATE, "call mdkm_comm_p2p_handle first");
+  CU(cudaSetDevice(h->device));
+  const size_t slot = (size_t)kMaxK * 4 + 8;
+  PeerXchg px{};
+  px.n_ranks = h->n_ranks; px.rank = h->rank; px.slot = (int)slot;
+  for (int q = 0; q < h->n_ranks; ++q) {
+    void* base = buffers[q];
+    if (!base) return fail(h, MDKM_ERR_INVALID, "null exchange buffer for rank %d", q);
+    if (q == h->rank) {
+      if (base != h->xchg) return fail(h, MDKM_ERR_INVALID, "buffers[rank] is not this handle's exchange buffer");
+    } else {
+      cudaPointerAttributes at{};
+      CU(cudaPointerGetAttributes(&at, base));
+      if (at.type != cudaMemoryTypeDevice) return fail(h, MDKM_ERR_INVALID, "buffers[%d] is not device memory", q);
+      if (at.device != h->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, h->device, at.device));
+        if (!can) return fail(h, MDKM_ERR_NCCL, "device %d cannot access device %d -- the NCCL exchange stays in use", h->device, at.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(h, MDKM_ERR_NCCL, "cudaDeviceEnablePeerAccess(%d) failed: %s", at.device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    px.data[q] = static_cast<unsigned long long*>(base);
+    px.flags[q] = px.data[q] + 2 * (size_t)h->n_ranks * slot;
+  }
+  h->px = px;
+  h->p2p_ok = true;
+  h->epoch_base = 0;
+  return MDKM_OK;
+}
+
+void* mdkm_get_stream(const mdkm_handle* h) { return h ? reinterpret_cast<void*>(h->stream) : nullptr; }
+
+int mdkm_set_option(mdkm_handle* h, int option, long long value) {
+  if (!h) return MDKM_ERR_INVALID;
+  switch (option) {
+    case MDKM_OPT_SETTLE_GROUPS:
+      h->opt_settle = value != 0;
+      return MDKM_OK;
+    default:
+      return fail(h, MDKM_ERR_INVALID, "unknown option %d", option);
+  }
 }
 
 int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int mem) {
@@ -1305,7 +1370,16 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   if (inertia_out) *inertia_out = fin.inertia;
   h->stat_refined = (long long)fin.n_refined;
   h->stat_reloc = relocs;
+  h->stat_work = (long long)fin.work_sum;
+  h->stat_groups = kb.n_groups;
   OK(collect_profile(h));
+  return MDKM_OK;
+}
+
+int mdkm_fit_worklist(const mdkm_handle* h, int64_t* worklist_groups, int64_t* groups) {
+  if (!h) return MDKM_ERR_INVALID;
+  if (worklist_groups) *worklist_groups = h->stat_work;
+  if (groups) *groups = h->stat_groups;
   return MDKM_OK;
 }
 

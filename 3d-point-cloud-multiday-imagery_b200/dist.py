@@ -63,20 +63,21 @@ def init_engine_comm(engine, rank: int, world: int, p2p: bool = True):
     import torch
     import torch.distributed as dist
 
-    from .engine import Engine
-
     if world == 1:
         engine.init_comm(1, 0, None)
         return
-    uid = exchange_unique_id(Engine.make_unique_id, rank, world, device=engine.device)
+    uid = exchange_unique_id(engine.make_unique_id, rank, world, device=engine.device)
     engine.init_comm(world, rank, uid)
     if p2p and world <= 8:
         handles = gather_bytes(engine.p2p_handle(), rank, world, device=engine.device)
         ok = engine.p2p_open(handles)
-        # all ranks or none: one rank without peer access sends everybody back to NCCL
+        # all ranks or none: one rank without peer access sends everybody back to NCCL.  The
+        # fallback is itself collective -- EVERY rank (whether its own open worked or not) drops
+        # its peer mappings and keeps the communicator it already has, so no rank is left
+        # waiting in a broadcast / ncclCommInitRank the others never enter.
         backend = dist.get_backend()
         dev = torch.device("cuda", engine.device) if backend == "nccl" else torch.device("cpu")
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0 and ok:
-            engine.init_comm(world, rank, exchange_unique_id(Engine.make_unique_id, rank, world, device=engine.device))
+        if int(flag.item()) == 0:
+            engine.p2p_close()

@@ -41,6 +41,35 @@ def _as_buffer(a, dtype=None):
     return arr.ctypes.data, C.MEM_HOST, arr, arr.shape, arr.dtype
 
 
+def _as_out_buffer(a, dtype, n_elems, what):
+    """-> (pointer:int, mem_kind) of a caller-supplied OUTPUT array.  The library writes through
+    the raw pointer, so anything that would make numpy / torch hand over a temporary copy (wrong
+    dtype, non-contiguous view) is rejected instead of silently losing the result."""
+    dt = np.dtype(dtype)
+    if _is_torch(a):
+        import torch
+
+        want = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[dt]
+        if a.dtype != want:
+            raise ValueError(f"{what} must be {dt.name}, got {a.dtype}")
+        if not a.is_contiguous():
+            raise ValueError(f"{what} must be contiguous")
+        if a.numel() != n_elems:
+            raise ValueError(f"{what} must hold {n_elems} elements, got {a.numel()}")
+        return a.data_ptr(), (C.MEM_DEVICE if a.is_cuda else C.MEM_HOST)
+    if not isinstance(a, np.ndarray):
+        raise ValueError(f"{what} must be a numpy array or a torch tensor")
+    if a.dtype != dt:
+        raise ValueError(f"{what} must be {dt.name}, got {a.dtype}")
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{what} must be C-contiguous")
+    if not a.flags["WRITEABLE"]:
+        raise ValueError(f"{what} must be writeable")
+    if a.size != n_elems:
+        raise ValueError(f"{what} must hold {n_elems} elements, got {a.size}")
+    return a.ctypes.data, C.MEM_HOST
+
+
 class Engine:
     """Owns one ``mdkm_handle``.  Use as a context manager or call ``close()``."""
 
@@ -63,6 +92,35 @@ class Engine:
         self.n_ranks = 1
         self.rank = 0
         self.p2p = False
+        self._stream_ptr = int(self._lib.mdkm_get_stream(self._h) or 0)
+        self._ext_stream = None
+
+    # -- ordering against torch's streams ----------------------------------------------------
+    # The handle enqueues on its own stream.  A CUDA tensor handed to it may still be being
+    # produced on torch's current stream (including the .to() / .contiguous() copies made just
+    # above), and a device-resident output may be consumed there right after the call: the two
+    # streams are ordered with events, and temporaries are kept alive for the handle's stream.
+    def _torch_streams(self):
+        import torch
+
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self._stream_ptr, device=self.device)
+        return self._ext_stream, torch.cuda.current_stream(self.device)
+
+    def _after_torch(self, *tensors):
+        """The handle's stream waits for what torch's current stream has enqueued so far."""
+        ext, cur = self._torch_streams()
+        if cur.cuda_stream != self._stream_ptr:
+            ext.wait_stream(cur)
+            for t in tensors:
+                if t is not None and _is_torch(t) and t.is_cuda:
+                    t.record_stream(ext)
+
+    def _before_torch(self):
+        """torch's current stream waits for what the handle has enqueued so far."""
+        ext, cur = self._torch_streams()
+        if cur.cuda_stream != self._stream_ptr:
+            cur.wait_stream(ext)
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
@@ -124,6 +182,33 @@ class Engine:
         self.p2p = rc == C.MDKM_OK
         return self.p2p
 
+    def p2p_close(self):
+        """Back to the NCCL exchange (the communicator is kept).  No-op when nothing is open."""
+        self._check(self._lib.mdkm_comm_p2p_close(self._h))
+        self.p2p = False
+
+    def p2p_buffer(self) -> int:
+        """Device pointer of this rank's exchange buffer (in-process ranks; after p2p_handle)."""
+        out = c_void_p()
+        self._check(self._lib.mdkm_comm_p2p_buffer(self._h, byref(out)))
+        return int(out.value)
+
+    def p2p_open_ptrs(self, buffers) -> bool:
+        """In-process variant of ``p2p_open``: the ranks' exchange-buffer pointers in rank order."""
+        assert len(buffers) == self.n_ranks
+        arr = (c_void_p * len(buffers))(*[c_void_p(int(b)) for b in buffers])
+        rc = self._lib.mdkm_comm_p2p_open_ptrs(self._h, arr)
+        self.p2p = rc == C.MDKM_OK
+        return self.p2p
+
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.mdkm_set_option(self._h, int(option), int(value)))
+
+    def settle_groups(self, on: bool):
+        """``False``: measurement mode -- every point goes through the per-point pass in every
+        iteration (no group is settled from its cached summary).  Results are identical."""
+        self.set_option(C.OPT_SETTLE_GROUPS, 1 if on else 0)
+
     @staticmethod
     def make_unique_id() -> bytes:
         lib = C.load()
@@ -177,6 +262,8 @@ class Engine:
                 raise ValueError("valid_masks must match height_maps")
             if mmem != mem:
                 raise ValueError("height_maps and valid_masks must live in the same memory space")
+        if mem == C.MEM_DEVICE:
+            self._after_torch(keep, keep_m)
         n = c_int64(0)
         cloud_buf = None
         if stream_cloud is not None:
@@ -206,6 +293,8 @@ class Engine:
                 raise ValueError("SoA points must be [3,N]")
             n = shape[1]
             lay = C.POINTS_SOA
+        if mem == C.MEM_DEVICE:
+            self._after_torch(keep)
         self._check(self._lib.mdkm_set_points(self._h, c_void_p(ptr), int(n), lay, mem))
         del keep
         return int(n)
@@ -238,11 +327,13 @@ class Engine:
         n = self.n_points
         if out is None:
             out = self._result_buffer("cloud", (n, 3), np.float32)
-        ptr, mem, keep, shape, _ = _as_buffer(out)
-        if int(np.prod(shape)) != n * 3:
-            raise ValueError("out must hold N*3 float32")
+        ptr, mem = _as_out_buffer(out, np.float32, n * 3, "out")
+        if mem == C.MEM_DEVICE:
+            self._after_torch(out)  # earlier work on torch's stream may still use the buffer
         fn = self._lib.mdkm_get_cloud if wait else self._lib.mdkm_get_cloud_async
         self._check(fn(self._h, c_void_p(ptr), 1 if napari_order else 0, mem))
+        if mem == C.MEM_DEVICE:
+            self._before_torch()
         return out
 
     def wait(self):
@@ -281,9 +372,10 @@ class Engine:
         n = self.n_points
         lab_ptr, lab_mem, labels = None, C.MEM_HOST, None
         if labels_out is not None:
-            lab_ptr, lab_mem, labels, shape, _ = _as_buffer(labels_out)
-            if int(np.prod(shape)) != n:
-                raise ValueError("labels_out must hold N int32")
+            lab_ptr, lab_mem = _as_out_buffer(labels_out, np.int32, n, "labels_out")
+            labels = labels_out
+            if lab_mem == C.MEM_DEVICE:
+                self._after_torch(labels_out)
         elif want_labels:
             labels = self._result_buffer("labels", (n,), np.int32)
             lab_ptr = labels.ctypes.data
@@ -294,12 +386,17 @@ class Engine:
             self._h, int(k), init.ctypes.data_as(POINTER(c_double)), int(max_iter), float(tol),
             c_void_p(lab_ptr) if lab_ptr else None, lab_mem,
             centers.ctypes.data_as(POINTER(c_double)), byref(n_iter), byref(inertia)))
+        if lab_mem == C.MEM_DEVICE:
+            self._before_torch()
         nref, nrel, tols = c_int64(0), c_int64(0), c_double(0)
         self._lib.mdkm_fit_stats(self._h, byref(nref), byref(nrel), byref(tols))
+        work, groups = c_int64(0), c_int64(0)
+        self._lib.mdkm_fit_worklist(self._h, byref(work), byref(groups))
         return {
             "labels": labels, "centers": centers, "n_iter": int(n_iter.value),
             "inertia": float(inertia.value), "n_refined": int(nref.value),
             "n_relocations": int(nrel.value), "tol_scaled": float(tols.value),
+            "worklist_groups": int(work.value), "groups": int(groups.value),
         }
 
     def lloyd_step(self, centroids, want_labels=True):

@@ -75,6 +75,30 @@ int mdkm_comm_init(mdkm_handle* h, int n_ranks, int rank,
  * returns MDKM_ERR_NCCL and the NCCL path stays in use.  Collective: all ranks or none. */
 int mdkm_comm_p2p_handle(mdkm_handle* h, unsigned char out[MDKM_IPC_HANDLE_BYTES]);
 int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles);
+/* Drops the peer mappings (and this rank's exchange buffer) again and keeps the NCCL
+ * communicator: the Lloyd iteration goes back to step kernel -> ncclAllReduce -> update kernel.
+ * The caller uses it to make the fallback collective: when mdkm_comm_p2p_open failed on ANY
+ * rank, EVERY rank calls this (no-op where nothing is open). */
+int mdkm_comm_p2p_close(mdkm_handle* h);
+
+/* The same exchange for ranks that live in ONE process (one handle per device, each driven by
+ * its own host thread -- the in-process caller of the reference, widget.py:116-147): after
+ * mdkm_comm_p2p_handle on every handle, mdkm_comm_p2p_buffer returns the device pointer of this
+ * rank's exchange buffer, and mdkm_comm_p2p_open_ptrs takes the n_ranks pointers in rank order
+ * (peer access between the devices is enabled by the call; no CUDA IPC involved). */
+int mdkm_comm_p2p_buffer(mdkm_handle* h, void** out_device_ptr);
+int mdkm_comm_p2p_open_ptrs(mdkm_handle* h, void* const* buffers);
+
+/* The CUDA stream (cudaStream_t) the handle enqueues on, so that a caller that produces inputs
+ * or consumes device-resident outputs on another stream can order the two with events. */
+void* mdkm_get_stream(const mdkm_handle* h);
+
+/* Tuning / measurement switches.  MDKM_OPT_SETTLE_GROUPS (default 1): 0 disables the
+ * classification pass's settling of whole 128-point groups from their cached summaries, so
+ * that EVERY point is read and assigned by the per-point pass in every iteration (the
+ * streaming path bench.py reports its HBM fraction for); results are identical either way. */
+enum { MDKM_OPT_SETTLE_GROUPS = 1 };
+int mdkm_set_option(mdkm_handle* h, int option, long long value);
 
 /* ---- K1: unprojection ----------------------------------------------------------------
  * Replaces members/rafael/disparity/plugin.py:148 (h = -disp/16), :151-152 (validity:
@@ -163,6 +187,12 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
  * of a tie and were re-decided in float64; n_relocations = empty-cluster relocations. */
 int mdkm_fit_stats(const mdkm_handle* h, int64_t* n_refined, int64_t* n_relocations,
                    double* tol_scaled);
+
+/* More diagnostics of the last mdkm_fit on this rank: *worklist_groups = 128-point groups that
+ * went through the per-point pass, summed over the iterations of the fit (fused iterations
+ * only); *groups = groups of the cloud.  1 - worklist_groups / (groups * n_iter) is the share
+ * of group-iterations settled from the cached summaries without reading a point. */
+int mdkm_fit_worklist(const mdkm_handle* h, int64_t* worklist_groups, int64_t* groups);
 
 /* One E-step + M-step sums with the given centroids (test hook for single-step parity;
  * mirrors sklearn.cluster._k_means_lloyd.lloyd_iter_chunked_dense up to the sums,

@@ -62,6 +62,79 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _FakeEngine:
+    """Stands in for Engine in init_engine_comm: records the calls; p2p_open fails on `bad_rank`."""
+
+    def __init__(self, rank, bad_rank):
+        self.device, self.rank_, self.bad = None, rank, bad_rank
+        self.p2p = False
+        self.calls = []
+
+    def make_unique_id(self):
+        return bytes(range(128))
+
+    def init_comm(self, world, rank, uid):
+        self.calls.append(("init_comm", world, rank, uid))
+
+    def p2p_handle(self):
+        return bytes([self.rank_]) * 64
+
+    def p2p_open(self, handles):
+        self.calls.append(("p2p_open", len(handles)))
+        self.p2p = self.rank_ != self.bad
+        return self.p2p
+
+    def p2p_close(self):
+        self.calls.append(("p2p_close",))
+        self.p2p = False
+
+
+def _worker_fallback(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = importlib.import_module(PKG + ".dist")
+        # peer access missing on rank 1 only: EVERY rank must take the same (collective) way back
+        # to the NCCL exchange -- one p2p_close each, no second unique-id broadcast / comm init --
+        # and nobody may be left with p2p switched on
+        eng = _FakeEngine(rank, bad_rank=1)
+        d.init_engine_comm(eng, rank, world)
+        names = [c[0] for c in eng.calls]
+        assert names == ["init_comm", "p2p_open", "p2p_close"], names
+        assert eng.p2p is False
+        # the next collective still pairs up on every rank (nothing is left half-entered)
+        t = torch.tensor([rank + 1])
+        dist.all_reduce(t)
+        assert int(t.item()) == world * (world + 1) // 2
+        # all ranks fine: the fused exchange stays on, nothing is closed
+        eng = _FakeEngine(rank, bad_rank=-1)
+        d.init_engine_comm(eng, rank, world)
+        assert [c[0] for c in eng.calls] == ["init_comm", "p2p_open"] and eng.p2p is True
+        q.put((rank, "ok"))
+    except Exception as ex:  # pragma: no cover
+        q.put((rank, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(target, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    return sorted(results)
+
+
+def test_p2p_open_failure_on_one_rank_falls_back_collectively():
+    assert _run(_worker_fallback) == [(0, "ok"), (1, "ok")]
+
+
 def test_two_rank_host_logic():
     world = 2
     ctx = mp.get_context("spawn")

@@ -92,6 +92,56 @@ def test_unproject_device_input_and_sharded_slices(engine):
     np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), ref)
 
 
+def test_cuda_tensor_inputs_are_ordered_after_torch_stream(engine):
+    """A CUDA tensor still being produced on torch's current stream when it is handed over: the
+    handle's own stream must wait for the producer (and for the dtype conversion made on the way)."""
+    import torch
+
+    hm_ref = synth.make_stack(2, 512, 640, seed=5)
+    mask_ref = torch.from_numpy(np.random.RandomState(5).rand(2, 512, 640) > 0.2)
+    P = UO.unproject_stack(hm_ref.numpy(), mask_ref.numpy())
+    hm_dev, mask_dev = hm_ref.cuda(), mask_ref.cuda()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        a = torch.randn(4096, 4096, device="cuda")
+        for _ in range(30):  # keeps `side` busy for several milliseconds
+            a = (a @ a) * 1e-4
+        dep = (a[0, 0] != a[0, 0]).float() * 0.0  # 0.0, available only when the chain is done
+        hm = torch.full_like(hm_dev, float("nan"))
+        hm.copy_(hm_dev + dep)
+        n = engine.unproject(hm, mask_dev)  # bool mask: converted to uint8 on `side`, too
+        labels = torch.empty(n, dtype=torch.int32, device="cuda")
+        init = synth.init_from_points(P.astype(np.float32), 4, 0)
+        r = engine.fit(init, max_iter=3, tol=0.0, labels_out=labels)
+        lab_dev = labels.clone()  # consumer on `side`, right after the call
+    torch.cuda.synchronize()
+    assert n == P.shape[0]
+    np.testing.assert_array_equal(engine.get_cloud(False).astype(np.float64), P)
+    r2 = engine.fit(init, max_iter=3, tol=0.0)
+    np.testing.assert_array_equal(lab_dev.cpu().numpy(), r2["labels"])
+    assert r["labels"] is labels
+    # device-resident cloud output
+    out = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    engine.get_cloud(napari_order=False, out=out)
+    np.testing.assert_array_equal(out.cpu().numpy().astype(np.float64), P)
+
+
+def test_output_buffers_must_be_usable_as_they_are(engine):
+    hm = synth.make_stack(1, 32, 48, seed=1).numpy()
+    n = engine.unproject(hm)
+    with pytest.raises(ValueError, match="contiguous"):
+        engine.get_cloud(out=np.empty((n, 6), dtype=np.float32)[:, ::2])
+    with pytest.raises(ValueError, match="float32"):
+        engine.get_cloud(out=np.empty((n, 3), dtype=np.float64))
+    init = synth.init_from_points(engine.get_cloud(False), 3, 0)
+    with pytest.raises(ValueError, match="int32"):
+        engine.fit(init, max_iter=2, labels_out=np.empty(n, dtype=np.int64))
+    out = np.empty(n, dtype=np.int32)
+    r = engine.fit(init, max_iter=2, tol=0.0, labels_out=out)
+    assert r["labels"] is out and np.array_equal(out, engine.fit(init, max_iter=2, tol=0.0)["labels"])
+
+
 def test_unproject_detrend(engine, golden):
     g = golden("unproject_small.npz")
     n = engine.unproject(g["disparity"], g["mask"], disparity_scale=-1.0 / 16.0, detrend=True)

@@ -118,6 +118,51 @@ def test_to_layers_matches_reference_layer_contract():
     assert res.labels_ is res.labels and res.cluster_centers_ is res.centroids
 
 
+def test_to_layers_colours_by_height_when_levelled():
+    api = importlib.import_module(PKG + ".api")
+    hn = np.array([0.0, 1.0], dtype=np.float32)
+    res = api.FusionResult(labels=np.array([0, 1], dtype=np.int32), centroids=np.zeros((2, 3)),
+                           fused_cloud=np.zeros((2, 3), dtype=np.float32), n_iter=1, inertia=0.0, n_points=2,
+                           height_norm=hn)
+    params = api.to_layers(res)[0][1]
+    assert params["face_color"] == "height" and params["properties"]["height"] is hn  # plugin.py:186-188, 231
+    assert params["properties"]["cluster"] is res.labels
+    res.height_norm = None
+    assert api.to_layers(res)[0][1]["face_color"] == "cluster"
+
+
+def test_output_buffers_are_validated_not_copied():
+    eng = importlib.import_module(PKG + ".engine")
+    ok = np.empty((5, 3), dtype=np.float32)
+    ptr, mem = eng._as_out_buffer(ok, np.float32, 15, "out")
+    assert ptr == ok.ctypes.data and mem == 0
+    for bad, msg in ((np.empty((5, 3), dtype=np.float64), "float32"),
+                     (np.empty((5, 6), dtype=np.float32)[:, ::2], "contiguous"),
+                     (np.empty((4, 3), dtype=np.float32), "15 elements"),
+                     ([0.0] * 15, "numpy array")):
+        with pytest.raises(ValueError, match=msg):
+            eng._as_out_buffer(bad, np.float32, 15, "out")
+    t = __import__("torch").empty(10, dtype=__import__("torch").int32)
+    assert eng._as_out_buffer(t, np.int32, 10, "labels_out")[0] == t.data_ptr()
+    with pytest.raises(ValueError, match="contiguous"):
+        eng._as_out_buffer(t[::2], np.int32, 5, "labels_out")
+    with pytest.raises(ValueError, match="int32"):
+        eng._as_out_buffer(t.float(), np.int32, 10, "labels_out")
+
+
+def test_plugin_error_is_logged_like_the_reference(tmp_path, built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    pkg = importlib.import_module(PKG)
+    log = tmp_path / "log.txt"
+    layers = pkg.MultiDayFusionPlugin(log_path=str(log)).run(np.zeros((1, 4, 4), dtype=np.float32))
+    assert layers[0][1]["name"].startswith("Error:")
+    txt = log.read_text()  # plugin.py:238-239: "Error: <e>\n<traceback>"
+    assert txt.startswith("Error: ") and "Traceback (most recent call last)" in txt
+
+
 def test_synthetic_stack_properties():
     pkg = importlib.import_module(PKG)
     hm = pkg.make_stack(3, 64, 96, seed=1).numpy()
