@@ -146,13 +146,13 @@ struct mdkm_handle {
   bool p2p_ok = false;
   unsigned long long epoch_base = 0;  // fused steps completed on this communicator
 
-  // profiling
+  // profiling: CUDA-event spans around the kernels of a phase (mdkm_profile_*)
   bool prof = false;
-  std::vector<cudaEvent_t> prof_ev;
-  std::vector<int> prof_batch_launches;
-  int prof_used = 0;
-  double prof_ms = 0.0;
-  int prof_steps = 0;
+  std::vector<cudaEvent_t> prof_ev;  // pool, two per span
+  struct ProfSpan { int phase; long long count; };
+  std::vector<ProfSpan> prof_spans;
+  double prof_ms[MDKM_PHASE_COUNT] = {};
+  long long prof_count[MDKM_PHASE_COUNT] = {};
   int launches = 0;
 };
 
@@ -241,6 +241,9 @@ void release(DevBuf<T>& b) {
 }
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+int prof_begin(mdkm_handle* h, int phase, long long count);
+void prof_end(mdkm_handle* h, int idx);
 
 int grid_for(const mdkm_handle* h, long long work_items, int per_sm) {
   long long g = std::min<long long>(work_items, (long long)h->sm_count * per_sm);
@@ -535,11 +538,13 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   OK(ensure(h, h->glabel, (size_t)kb.n_groups));
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
   if (!h->summary_ok) {
+    const int span = prof_begin(h, MDKM_PHASE_BUILD, h->n);
     OK(build_mirror(h, k <= 16 ? 16 : 8));
     group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
         h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
     ++h->launches;
     CU(cudaGetLastError());
+    prof_end(h, span);
     h->summary_ok = true;
   }
   if (!h->d_status) {
@@ -627,16 +632,34 @@ int upload_table(mdkm_handle* h, const KmBuffers& kb, const double* centers_host
   return MDKM_OK;
 }
 
-int collect_profile(mdkm_handle* h) {
-  if (!h->prof) return MDKM_OK;
-  for (int i = 0; i + 1 < h->prof_used; i += 2) {
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
-    h->prof_ms += ms;
-    h->prof_steps += h->prof_batch_launches[i / 2];
+// Profiling spans: prof_begin records an event on the compute stream and returns the span's
+// index (-1 when profiling is off), prof_end records the closing event; collect_profile (after
+// the stream has been synchronised) adds the elapsed times to the phases' totals.
+int prof_begin(mdkm_handle* h, int phase, long long count) {
+  if (!h->prof) return -1;
+  const int idx = (int)h->prof_spans.size();
+  while (h->prof_ev.size() < (size_t)(idx + 1) * 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    h->prof_ev.push_back(e);
   }
-  h->prof_used = 0;
-  h->prof_batch_launches.clear();
+  if (cudaEventRecord(h->prof_ev[2 * idx], h->stream) != cudaSuccess) return -1;
+  h->prof_spans.push_back({phase, count});
+  return idx;
+}
+
+void prof_end(mdkm_handle* h, int idx) {
+  if (idx >= 0) cudaEventRecord(h->prof_ev[2 * idx + 1], h->stream);
+}
+
+int collect_profile(mdkm_handle* h) {
+  for (size_t i = 0; i < h->prof_spans.size(); ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    h->prof_ms[h->prof_spans[i].phase] += ms;
+    h->prof_count[h->prof_spans[i].phase] += h->prof_spans[i].count;
+  }
+  h->prof_spans.clear();
   return MDKM_OK;
 }
 
@@ -1127,11 +1150,13 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
         up.chunk_end = c_end;
         const long long nc = c_end - done_chunks;
         const int g = grid_for(h, (nc + 7) / 8, 8);
+        const int span = prof_begin(h, MDKM_PHASE_UNPROJECT, std::min<long long>(c_end * kChunk, pix_count) - done_chunks * kChunk);
         unproject_count_kernel<<<g, kThreads, 0, h->stream>>>(up);
         scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->chunk_counts.p + done_chunks, nc,
                                                       h->chunk_offsets.p + done_chunks, h->slab_totals.p + s,
                                                       h->slab_totals.p + s + 1);
         unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
+        prof_end(h, span);
         h->launches += 3;
         if (cloud_out) {
           blocked_to_aos_range_kernel<<<g, kThreads, 0, h->stream>>>(h->pts.p, h->slab_totals.p + s, cloud_napari,
@@ -1274,18 +1299,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       const int nb = std::min(kBatch, max_iter - enq);
       // profiling: one event pair around the batch's step kernels (back-to-back launches, so
       // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
-      cudaEvent_t pe1 = nullptr;
-      if (h->prof && can_fuse(h)) {
-        while ((int)h->prof_ev.size() < h->prof_used + 2) {
-          cudaEvent_t e;
-          CU(cudaEventCreate(&e));
-          h->prof_ev.push_back(e);
-        }
-        CU(cudaEventRecord(h->prof_ev[h->prof_used], h->stream));
-        pe1 = h->prof_ev[h->prof_used + 1];
-        h->prof_batch_launches.push_back(nb);
-        h->prof_used += 2;
-      }
+      const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
       for (int b = 0; b < nb; ++b) {
         if (can_fuse(h)) {
           OK(launch_step(h, kb, 0, /*fuse_update=*/1));
@@ -1295,7 +1309,7 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
           OK(launch_update(h, kb, /*allow_pause=*/1, 0));
         }
       }
-      if (pe1) CU(cudaEventRecord(pe1, h->stream));
+      prof_end(h, span);
       OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
       CU(cudaEventRecord(h->batch_ev[tail], h->stream));
       tail ^= 1;
@@ -1346,7 +1360,11 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   // labels in the reference's point order: always recomputed from the final centroids (the
   // stored ones follow the mirror's order).  After a strict exit the table equals the one the
   // last E-step used -- the sums are integers -- so this reproduces that step's labels exactly.
-  OK(run_final(h, kb, labels_dev));
+  {
+    const int span = prof_begin(h, MDKM_PHASE_FINAL, h->n);
+    OK(run_final(h, kb, labels_dev));
+    prof_end(h, span);
+  }
   OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
   read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
   ++h->launches;
@@ -1678,21 +1696,37 @@ int mdkm_drop_caches(mdkm_handle* h) {
 
 int mdkm_profile_enable(mdkm_handle* h, int on) {
   if (!h) return MDKM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
   h->prof = on != 0;
-  h->prof_used = 0;
-  h->prof_ms = 0.0;
-  h->prof_steps = 0;
+  h->prof_spans.clear();
+  for (int i = 0; i < MDKM_PHASE_COUNT; ++i) {
+    h->prof_ms[i] = 0.0;
+    h->prof_count[i] = 0;
+  }
   return MDKM_OK;
 }
 
 int mdkm_profile_read(mdkm_handle* h, double* step_kernel_ms, int* n_step_launches, int* n_kernel_launches_total) {
   if (!h) return MDKM_ERR_INVALID;
-  if (step_kernel_ms) *step_kernel_ms = h->prof_ms;
-  if (n_step_launches) *n_step_launches = h->prof_steps;
+  if (step_kernel_ms) *step_kernel_ms = h->prof_ms[MDKM_PHASE_STEP];
+  if (n_step_launches) *n_step_launches = (int)h->prof_count[MDKM_PHASE_STEP];
   if (n_kernel_launches_total) *n_kernel_launches_total = h->launches;
-  h->prof_ms = 0.0;
-  h->prof_steps = 0;
+  h->prof_ms[MDKM_PHASE_STEP] = 0.0;
+  h->prof_count[MDKM_PHASE_STEP] = 0;
   h->launches = 0;
+  return MDKM_OK;
+}
+
+int mdkm_profile_phase(mdkm_handle* h, int phase, double* ms, int64_t* count) {
+  if (!h || phase < 0 || phase >= MDKM_PHASE_COUNT) return MDKM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  OK(collect_profile(h));
+  if (ms) *ms = h->prof_ms[phase];
+  if (count) *count = h->prof_count[phase];
+  h->prof_ms[phase] = 0.0;
+  h->prof_count[phase] = 0;
   return MDKM_OK;
 }
 

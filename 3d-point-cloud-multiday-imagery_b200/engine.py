@@ -463,6 +463,16 @@ class Engine:
     def profile(self, on: bool):
         self._check(self._lib.mdkm_profile_enable(self._h, 1 if on else 0))
 
+    def profile_phases(self):
+        """{phase: (ms, count)} of the kernel groups since the last read (see mdkm_profile_phase)."""
+        out = {}
+        for name, ph in (("unproject", C.PHASE_UNPROJECT), ("build", C.PHASE_BUILD), ("step", C.PHASE_STEP),
+                         ("final", C.PHASE_FINAL)):
+            ms, cnt = c_double(0), c_int64(0)
+            self._check(self._lib.mdkm_profile_phase(self._h, ph, byref(ms), byref(cnt)))
+            out[name] = (float(ms.value), int(cnt.value))
+        return out
+
     def profile_read(self):
         ms, ns, nl = c_double(0), c_int(0), c_int(0)
         self._check(self._lib.mdkm_profile_read(self._h, byref(ms), byref(ns), byref(nl)))

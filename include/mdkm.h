@@ -236,6 +236,15 @@ int mdkm_profile_enable(mdkm_handle* h, int on);
 int mdkm_profile_read(mdkm_handle* h, double* step_kernel_ms, int* n_step_launches,
                       int* n_kernel_launches_total);
 
+/* The same for the other kernel groups of the path (CUDA events on the handle's stream around
+ * the kernels only -- host work and copies between them are outside): summed duration and work
+ * count since the last read of that phase.  count = pixels (UNPROJECT: count + scan + scatter
+ * kernels of mdkm_unproject), points (BUILD: tile-ordered mirror + group summaries of a cold
+ * fit; FINAL: the final labelling / inertia pass of mdkm_fit), launches (STEP). */
+enum { MDKM_PHASE_UNPROJECT = 0, MDKM_PHASE_BUILD = 1, MDKM_PHASE_STEP = 2, MDKM_PHASE_FINAL = 3,
+       MDKM_PHASE_COUNT = 4 };
+int mdkm_profile_phase(mdkm_handle* h, int phase, double* ms, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -629,11 +629,11 @@ def test_config2_full_size_single_step(engine):
 
 
 def test_config2_full_size_fit(engine):
-    """BASELINE.json configs[1] at full size: a 5-iteration fit (cold mirror / summaries, fused
-    update, final pass) against the C oracle iterated step by step."""
+    """BASELINE.json configs[1] at full size and its full 20 iterations (cold mirror / summaries,
+    fused update, final pass) against the C oracle iterated step by step."""
     import torch
 
-    D, H, W, k, iters = 10, 2048, 2048, 16, 5
+    D, H, W, k, iters = 10, 2048, 2048, 16, 20
     hm = synth.make_stack(D, H, W, seed=1, device="cuda")
     n = engine.unproject(hm)
     del hm
@@ -663,3 +663,127 @@ def test_config2_full_size_fit(engine):
     assert r2["centers"].tobytes() == r["centers"].tobytes() and np.array_equal(r2["labels"], r["labels"])
     d = ((cloud.astype(np.float64) - r["centers"][r["labels"]]) ** 2).sum()
     np.testing.assert_allclose(r["inertia"], d, rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, each on a size the C oracle finishes in seconds
+# ---------------------------------------------------------------------------------------
+def _oracle_iterate(x, y, z, init, iters):
+    """`iters` Lloyd iterations of the C oracle (sklearn/_k_means_lloyd.pyx restated), then the
+    final E-step of _kmeans.py:742-756.  Returns (centres, labels, counts)."""
+    C = init.copy()
+    for _ in range(iters):
+        _, sums, counts, _ = c_oracle.lloyd_step_f32soa(x, y, z, C)
+        assert counts.min() > 0  # no relocation in these runs
+        C = sums / counts[:, None]
+    lab, _, counts, _ = c_oracle.lloyd_step_f32soa(x, y, z, C)
+    return C, lab, counts
+
+
+def _check_fit_vs_oracle(engine, cloud, init, iters, tag):
+    x, y, z = (np.ascontiguousarray(cloud[:, i]) for i in range(3))
+    k = init.shape[0]
+    C, lab_ref, counts_ref = _oracle_iterate(x, y, z, init, iters)
+    r = engine.fit(init, max_iter=iters, tol=0.0)
+    assert r["n_iter"] == iters and r["n_relocations"] == 0
+    std = np.array([cloud[:, i].std(dtype=np.float64) for i in range(3)])
+    err = (np.abs(r["centers"] - C) / np.maximum(np.abs(C), std)).max()
+    bad = np.nonzero(r["labels"] != lab_ref)[0]
+    cmp = KO.compare_labels(cloud[bad].astype(np.float64), C, lab_ref[bad], r["labels"][bad], rel_band=LABEL_BAND)
+    settled = 1.0 - r["worklist_groups"] / max(1, r["groups"] * r["n_iter"])
+    print(f"{tag}: N={cloud.shape[0]} k={k} iters={iters} centroid rel err {err:.2e} label mismatches {bad.size} "
+          f"near-ties {cmp['n_near_tie']} hard {cmp['n_hard']} refined {r['n_refined']} settled group-iterations {settled:.3f}")
+    assert err < CENTROID_TOL
+    assert cmp["n_hard"] == 0, cmp
+    if bad.size == 0:
+        np.testing.assert_array_equal(np.bincount(r["labels"], minlength=k), counts_ref.astype(np.int64))
+    return r, C
+
+
+def test_config4_k1024_step_by_step(engine):
+    """BASELINE.json configs[3] code path (k = 1024: uint16 labels, bucket index, shared-memory
+    atomics) on one 4096 x 4096 day: single steps against the C oracle, then a 3-iteration fit."""
+    import torch
+
+    H = W = 4096
+    k = 1024
+    hm = synth.make_stack(1, H, W, seed=4, device="cuda")
+    n = engine.unproject(hm)
+    del hm
+    torch.cuda.empty_cache()
+    cloud = engine.get_cloud(False)
+    x, y, z = (np.ascontiguousarray(cloud[:, i]) for i in range(3))
+    C = synth.init_from_points(cloud, k, 4)
+    init = C.copy()
+    for step in range(2):  # step 0 from k data points (exact ties possible), step 1 from real centroids
+        labels, sums, counts, n_ref = engine.lloyd_step(C)
+        lab_ref, sums_ref, counts_ref, _ = c_oracle.lloyd_step_f32soa(x, y, z, C)
+        bad = np.nonzero(labels != lab_ref)[0]
+        cmp = KO.compare_labels(cloud[bad].astype(np.float64), C, lab_ref[bad], labels[bad], rel_band=LABEL_BAND)
+        print(f"k=1024 step {step}: mismatches {bad.size} near-ties {cmp['n_near_tie']} hard {cmp['n_hard']} "
+              f"refined {n_ref} of {n}")
+        assert cmp["n_hard"] == 0, cmp
+        assert counts.sum() == n
+        if bad.size == 0:
+            np.testing.assert_array_equal(counts, counts_ref.astype(np.int64))
+            np.testing.assert_allclose(sums, sums_ref, rtol=1e-6, atol=1e-2)
+        C = sums_ref / np.maximum(counts_ref, 1)[:, None]
+    _check_fit_vs_oracle(engine, cloud, init, 3, "c4-path fit")
+    # settling disabled (every point through the per-point pass): bit-identical results
+    r1 = engine.fit(init, max_iter=3, tol=0.0)
+    engine.settle_groups(False)
+    try:
+        r2 = engine.fit(init, max_iter=3, tol=0.0)
+    finally:
+        engine.settle_groups(True)
+    assert r2["centers"].tobytes() == r1["centers"].tobytes() and np.array_equal(r2["labels"], r1["labels"])
+    assert r2["worklist_groups"] == r2["groups"] * 3 and r1["worklist_groups"] < r2["worklist_groups"]
+
+
+def test_config5_tol_run_matches_sklearn_n_iter(engine):
+    """BASELINE.json configs[4] style: tol = 1e-4, max_iter = 300, k = 32 on a mid-size stack,
+    against LIVE scikit-learn (the reference's implementation): same n_iter, labels, centroids."""
+    from oracle import sklearn_ref
+
+    if not sklearn_ref.available():
+        pytest.skip("scikit-learn not importable")
+    hm = synth.make_stack(4, 1024, 1024, seed=6).numpy()
+    n = engine.unproject(hm)
+    cloud = engine.get_cloud(False)
+    X = cloud.astype(np.float64)
+    init = synth.init_from_points(cloud, 32, 6)
+    ref = sklearn_ref.fit(X, init, max_iter=300, tol=1e-4)
+    r = engine.fit(init, max_iter=300, tol=1e-4)
+    print(f"c5-style: N={n} sklearn n_iter {ref['n_iter']} ours {r['n_iter']} refined {r['n_refined']} "
+          f"tol_scaled {r['tol_scaled']:.6e}")
+    assert r["n_iter"] == ref["n_iter"]
+    assert 1 < r["n_iter"] < 300
+    check_labels(X, ref["centers"], ref["labels"], r["labels"])
+    check_centroids(ref["centers"], r["centers"], X)
+    np.testing.assert_allclose(r["inertia"], ref["inertia"], rtol=1e-9)
+
+
+def test_config3_row_band_shard(engine):
+    """BASELINE.json configs[2] geometry: one rank's row band of an 8192-wide frame, starting in
+    the middle of a day (pix_begin > 0) and running into the next one; k = 64, 20 iterations."""
+    import torch
+
+    D, H, W, k, iters = 2, 8192, 8192, 64, 20
+    rows = 1024
+    pix_begin = (H - rows // 2) * W              # the last 512 rows of day 0 ...
+    count = rows * W                             # ... and the first 512 rows of day 1
+    hm = synth.make_stack(1, rows, W, seed=8, device="cuda").reshape(-1)
+    n = engine.unproject(hm, stack_shape=(D, H, W), pix_begin=pix_begin)
+    hm_h = hm.cpu().numpy()
+    del hm
+    torch.cuda.empty_cache()
+    idx = np.flatnonzero(UO.valid_mask(hm_h)) + pix_begin  # np.where order of the global stack
+    rem = idx % (H * W)
+    P = np.stack([(rem % W).astype(np.float64), (rem // W).astype(np.float64), hm_h[idx - pix_begin].astype(np.float64)], axis=1)
+    assert n == P.shape[0]
+    cloud = engine.get_cloud(False)
+    np.testing.assert_array_equal(cloud.astype(np.float64), P)
+    off = engine.segment_offsets
+    assert off.tolist() == [0, int((idx < H * W).sum()), n]
+    init = synth.init_from_points(cloud, k, 8)
+    _check_fit_vs_oracle(engine, cloud, init, iters, "c3 row band")
