@@ -17,6 +17,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 HM_F32, HM_I16, HM_F32_GTIFF3 = 0, 1, 2
 POINTS_AOS, POINTS_SOA = 0, 1
 OPT_SETTLE_GROUPS = 1
+OPT_RASTER_MIRROR = 2
 PHASE_UNPROJECT, PHASE_BUILD, PHASE_STEP, PHASE_FINAL = 0, 1, 2, 3
 NCCL_UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64

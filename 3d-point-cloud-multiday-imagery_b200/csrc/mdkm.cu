@@ -85,6 +85,15 @@ struct mdkm_handle {
   int raster_w = 0;  // width of the raster the cloud was unprojected from (0: generic cloud)
   DevBuf<unsigned int> cell_counts;
   DevBuf<long long> cell_offsets;
+  // raster clouds (mdkm_unproject of whole rows): run table written by the unprojection, and the
+  // run list / group index the raster mirror build derives from it (mirror.cuh)
+  DevBuf<unsigned int> run_src;
+  bool runs_ok = false;
+  long long run_row0 = 0, run_rows = 0;  // first global row (day * H + y) and number of rows of the range
+  int run_H = 0;
+  DevBuf<unsigned char> druns;
+  DevBuf<unsigned int> gfirst;
+  int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -493,6 +502,62 @@ int build_mirror(mdkm_handle* h, int cell_px) {
   return MDKM_OK;
 }
 
+// The same for a raster cloud that came with a run table: cell sizes and the place of every run
+// follow from the table (two kernels over the cells), the copy is a gather by destination that
+// also writes the group summaries.  No histogram pass over the points, no atomics.
+int build_mirror_raster(mdkm_handle* h, int cell_px) {
+  const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
+  OK(ensure(h, h->tpts, (size_t)cap * 3));
+  const long long n_groups = cap / kGroup;
+  OK(ensure(h, h->gsum, (size_t)n_groups * sizeof(GroupSummary)));
+  RasterGeom g{};
+  g.run_src = h->run_src.p;
+  g.row0 = h->run_row0; g.n_rows = h->run_rows;
+  g.W = h->raster_w; g.H = h->run_H;
+  g.nb8 = g.W / 8;
+  g.cb = cell_px / 8;
+  g.gx = (g.nb8 + g.cb - 1) / g.cb;
+  g.d0 = (int)(g.row0 / g.H);
+  g.nd = (int)((g.row0 + g.n_rows - 1) / g.H) - g.d0 + 1;
+  // rows of y the range covers: all of them once it holds a whole day, else its n_rows rows
+  // counted (cyclically) from the first one
+  g.yshift = g.n_rows >= g.H ? 0 : (int)(g.row0 % g.H);
+  g.yext = (int)std::min<long long>(g.n_rows, g.H);
+  // rows per cell: about 256 points per cell, counting every day that covers a row
+  const double per_row = (double)h->n / (double)g.yext / (double)g.gx;  // points per cell and row of y
+  g.rpc = (int)std::max(1.0, std::min(64.0, nearbyint(256.0 / std::max(per_row, 1e-9))));
+  g.gy = (g.yext + g.rpc - 1) / g.rpc;
+  const long long n_cells = (long long)g.gx * g.gy;
+  const long long n_entries = n_cells * g.nd * g.rpc;
+  if (n_cells >= (1ll << 31) || n_entries >= (1ll << 32)) return fail(h, MDKM_ERR_INVALID, "raster too large for the run list");
+  const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
+  OK(ensure(h, h->cell_counts, (size_t)n_tiles * kScanTile));
+  OK(ensure(h, h->cell_offsets, (size_t)n_cells + 2));
+  OK(ensure(h, h->druns, ((size_t)n_entries + 1) * sizeof(uint2)));
+  OK(ensure(h, h->gfirst, (size_t)n_groups));
+  OK(ensure(h, h->partials, (size_t)std::max(n_tiles, h->sm_count * 8) * 8 + 16));
+  if (h->n == 0) {
+    CU(cudaMemsetAsync(h->tpts.p, 0, kBlockFloats * 4, h->stream));
+    group_summary_kernel<<<1, kThreads, 0, h->stream>>>(h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
+    ++h->launches;
+    CU(cudaGetLastError());
+    return MDKM_OK;
+  }
+  const int cgrid = grid_for(h, (n_cells + kThreads - 1) / kThreads, 16);
+  raster_cell_count_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_counts.p);
+  long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
+  mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
+  mirror_scan_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, tile_sums);
+  raster_runs_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_offsets.p, h->n, reinterpret_cast<uint2*>(h->druns.p),
+                                                        h->gfirst.p);
+  raster_gather_kernel<<<grid_for(h, (n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
+      h->pts.p, h->n, reinterpret_cast<const uint2*>(h->druns.p), n_entries, h->gfirst.p, h->ff, h->tpts.p,
+      reinterpret_cast<float4*>(h->gsum.p));
+  h->launches += 5;
+  CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
 int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   if (!h->have_points) return fail(h, MDKM_ERR_STATE, "no points resident: call mdkm_unproject or mdkm_set_points first");
   if (k < 1 || k > kMaxK) return fail(h, MDKM_ERR_INVALID, "k must be in [1, %d]", kMaxK);
@@ -539,11 +604,15 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
   if (!h->summary_ok) {
     const int span = prof_begin(h, MDKM_PHASE_BUILD, h->n);
-    OK(build_mirror(h, k <= 16 ? 16 : 8));
-    group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
-        h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
-    ++h->launches;
-    CU(cudaGetLastError());
+    if (h->runs_ok && h->raster_w > 0 && h->opt_raster_mirror) {
+      OK(build_mirror_raster(h, k <= 16 && h->raster_w % 16 == 0 ? 16 : 8));
+    } else {
+      OK(build_mirror(h, k <= 16 ? 16 : 8));
+      group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
+          h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
+      ++h->launches;
+      CU(cudaGetLastError());
+    }
     prof_end(h, span);
     h->summary_ok = true;
   }
@@ -789,6 +858,7 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
   release(h->gsum); release(h->glabel); release(h->worklist);
   release(h->tpts); release(h->cell_counts); release(h->cell_offsets);
+  release(h->run_src); release(h->druns); release(h->gfirst);
   release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
   release(h->d_seg_off); release(h->sel_hist); release(h->sel_targets);
   release(h->kpp_closest); release(h->kpp_cell); release(h->kpp_blk); release(h->kpp_prefix);
@@ -944,6 +1014,10 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
     case MDKM_OPT_SETTLE_GROUPS:
       h->opt_settle = value != 0;
       return MDKM_OK;
+    case MDKM_OPT_RASTER_MIRROR:
+      h->opt_raster_mirror = value != 0;
+      h->summary_ok = false;
+      return MDKM_OK;
     default:
       return fail(h, MDKM_ERR_INVALID, "unknown option %d", option);
   }
@@ -971,6 +1045,7 @@ int mdkm_set_points(mdkm_handle* h, const float* xyz, int64_t n, int layout, int
   h->seg_off.assign({0, (long long)n});
   h->seg_whole = true;
   h->raster_w = 0;
+  h->runs_ok = false;
   h->have_points = true;
   h->frame_ok = false;
   OK(compute_frame(h));
@@ -1070,6 +1145,14 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   up.pts = h->pts.p;
   up.planes = nullptr;
   up.day0 = (int)(pix_begin / HW);
+  // run table for the raster mirror build: whole rows of a raster whose width is a multiple of 8
+  h->runs_ok = false;
+  const bool want_runs = pix_count > 0 && (W % 8) == 0 && (pix_begin % W) == 0 && (pix_count % W) == 0 &&
+                         pix_count < (1ll << 32);
+  if (want_runs) {
+    OK(ensure(h, h->run_src, (size_t)(pix_count / 8) + 1));
+    up.run_src = h->run_src.p;
+  }
   long long n_out = 0;
   if (pix_count > 0) {
     const int n_days = detrend ? (int)(pix_count / HW) : 0;
@@ -1205,6 +1288,15 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   }
   h->n = n_out;
   h->raster_w = W;
+  if (want_runs) {
+    const unsigned int n32 = (unsigned int)n_out;  // closes the table
+    CU(cudaMemcpyAsync(h->run_src.p + pix_count / 8, &n32, 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // (n32 lives on this stack frame)
+    h->runs_ok = true;
+    h->run_row0 = pix_begin / W;
+    h->run_rows = pix_count / W;
+    h->run_H = H;
+  }
   OK(zero_tail(h));
   h->have_points = true;
   h->frame_ok = false;

@@ -224,4 +224,192 @@ __global__ void __launch_bounds__(kThreads) mirror_scatter_kernel(const float* p
   }
 }
 
+// =======================================================================================
+// Raster clouds: the mirror without a histogram pass, atomics or scattered writes.
+//
+// A cloud that mdkm_unproject produced from whole raster rows comes with a run table
+// (UnprojParams::run_src): for every 8 pixels of the range, how many points the pixels before
+// them produced.  The points of an 8- or 16-pixel run of one row are consecutive in the cloud,
+// the table says where they start and how many there are -- so the size of every cell, and the
+// place of every run inside its cell, follow from the table alone (two small kernels over the
+// cells, nothing per point), and the copy itself is a GATHER BY DESTINATION: one warp per group
+// of 128 mirror points looks up the handful of runs that make up the group, fetches them
+// (64-byte pieces of the cloud), writes the 1536-byte block in one piece and, having the whole
+// group in registers, also emits the group's summary (box + fixed-point sums) -- what used to
+// be mirror_count + mirror_scatter + group_summary_kernel.  The order inside a cell is fixed
+// (day, row, x), so the mirror is deterministic.
+// =======================================================================================
+struct RasterGeom {
+  const unsigned int* run_src;  // [n_rows * nb8 + 1]
+  long long row0;   // global row (day * H + y) of the first row of the range
+  long long n_rows; // rows in the range
+  int W, H;
+  int nb8;          // 8-pixel bins per row (W / 8)
+  int cb;           // bins per cell: 1 (8 px) or 2 (16 px)
+  int gx;           // cells per row of cells
+  int rpc;          // raster rows per cell
+  int yshift, yext; // the rows of y the range covers: (yshift + i) mod H for i in [0, yext) -- all H of them
+                    // once the range holds a whole day, else the n_rows rows from its first one on
+  int gy;           // rows of cells: ceil(yext / rpc)
+  int d0, nd;       // first day and number of days the range touches
+};
+
+// serpentine numbering of the cells, as above
+__device__ __forceinline__ int raster_cell_index(const RasterGeom& g, int cxi, int cyi) {
+  return cyi * g.gx + ((cyi & 1) ? g.gx - 1 - cxi : cxi);
+}
+
+// points of the run (day d0 + dd, covered row cyi * rpc + ry, bins [cxi * cb, cxi * cb + cb)) and
+// the index of its first point in the cloud; 0 points when the row is outside the range
+__device__ __forceinline__ unsigned int raster_run(const RasterGeom& g, int cxi, int cyi, int dd, int ry,
+                                                   unsigned int& src) {
+  src = 0u;
+  const int yi = cyi * g.rpc + ry;
+  if (yi >= g.yext) return 0u;
+  int y = yi + g.yshift;
+  if (y >= g.H) y -= g.H;
+  const long long lr = (long long)(g.d0 + dd) * g.H + y - g.row0;
+  if (lr < 0 || lr >= g.n_rows) return 0u;
+  const long long j0 = lr * g.nb8 + (long long)cxi * g.cb;
+  const long long j1 = min(j0 + g.cb, (lr + 1) * g.nb8);
+  src = __ldg(g.run_src + j0);
+  return __ldg(g.run_src + j1) - src;
+}
+
+// points per cell (one thread per cell)
+__global__ void __launch_bounds__(kThreads) raster_cell_count_kernel(const RasterGeom g, unsigned int* counts) {
+  const int n_cells = g.gx * g.gy;
+  for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_cells; c += gridDim.x * kThreads) {
+    const int cyi = c / g.gx, cxi = c - cyi * g.gx;  // consecutive threads: consecutive bins of a row
+    unsigned int tot = 0;
+    for (int dd = 0; dd < g.nd; ++dd)
+      for (int ry = 0; ry < g.rpc; ++ry) {
+        unsigned int src;
+        tot += raster_run(g, cxi, cyi, dd, ry, src);
+      }
+    counts[raster_cell_index(g, cxi, cyi)] = tot;
+  }
+}
+
+// The runs in destination order: entry (cell, day, row) = (first mirror slot, first cloud index);
+// an entry's length is the next entry's slot minus its own (entry n_entries closes the list).
+// gfirst[g] = the entry that holds mirror slot 128 g.
+__global__ void __launch_bounds__(kThreads) raster_runs_kernel(const RasterGeom g, const long long* cell_offsets,
+                                                               long long n, uint2* druns, unsigned int* gfirst) {
+  const int n_cells = g.gx * g.gy;
+  const int per_cell = g.nd * g.rpc;
+  for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_cells; c += gridDim.x * kThreads) {
+    const int cyi = c / g.gx, cxi = c - cyi * g.gx;
+    const int lin = raster_cell_index(g, cxi, cyi);
+    unsigned int dst = (unsigned int)cell_offsets[lin];
+    uint2* out = druns + (size_t)lin * per_cell;
+    for (int dd = 0; dd < g.nd; ++dd)
+      for (int ry = 0; ry < g.rpc; ++ry) {
+        unsigned int src;
+        const unsigned int cnt = raster_run(g, cxi, cyi, dd, ry, src);
+        const int e = dd * g.rpc + ry;
+        out[e] = make_uint2(dst, src);
+        if (cnt) {  // a run is shorter than a group: it holds at most one group start
+          const unsigned long long gs = ((unsigned long long)dst + (kGroup - 1)) / kGroup;
+          if (gs * kGroup < (unsigned long long)dst + cnt) gfirst[gs] = (unsigned int)((size_t)lin * per_cell + e);
+        }
+        dst += cnt;
+      }
+    if (c == 0) druns[(size_t)n_cells * per_cell] = make_uint2((unsigned int)n, 0u);
+  }
+}
+
+// One warp per group of 128 mirror points: resolve the group's slots to cloud indices through
+// the run list (32 entries per window, binary search by shuffles), fetch, write the block, emit
+// the summary.  `summaries` is an array of 48-byte GroupSummary records (lloyd.cuh), written as
+// three float4 here to keep this header independent of it.
+__global__ void __launch_bounds__(kThreads) raster_gather_kernel(const float* __restrict__ pts, long long n,
+                                                                 const uint2* __restrict__ druns, long long n_entries,
+                                                                 const unsigned int* __restrict__ gfirst, FrameF f,
+                                                                 float* __restrict__ tpts, float4* __restrict__ summaries) {
+  const int lane = threadIdx.x & 31;
+  const long long n_groups = (n + kGroup - 1) / kGroup;
+  const long long stride = (long long)gridDim.x * (kThreads / 32);
+  for (long long grp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); grp < n_groups; grp += stride) {
+    const unsigned int base = (unsigned int)(grp * kGroup);
+    const unsigned int n32 = (unsigned int)n;
+    unsigned int srcs[4] = {0u, 0u, 0u, 0u};
+    unsigned int todo = 0;  // rounds whose slot still has to be resolved (bit r)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (base + r * 32 + lane < n32) todo |= 1u << r;
+    long long j = __ldg(gfirst + grp);
+    while (__any_sync(0xffffffffu, todo != 0)) {
+      if (j >= n_entries) break;  // (cannot happen with a consistent run list; never read out of bounds)
+      const long long jj = j + lane;
+      const uint2 e = jj < n_entries ? __ldg(druns + jj) : make_uint2(0xffffffffu, 0u);
+      const unsigned int w_end = __ldg(&druns[min(j + 32, n_entries)].x);  // first slot behind this window
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned int s = base + r * 32 + lane;
+        // last entry of the window whose first slot is <= s (empty entries share their successor's slot)
+        int t = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const unsigned int v = __shfl_sync(0xffffffffu, e.x, t + step);
+          if (v <= s) t += step;
+        }
+        const unsigned int d0 = __shfl_sync(0xffffffffu, e.x, t), s0 = __shfl_sync(0xffffffffu, e.y, t);
+        if (((todo >> r) & 1u) && s < w_end) {
+          srcs[r] = s0 + (s - d0);
+          todo &= ~(1u << r);
+        }
+      }
+      j += 32;
+    }
+    float xs[4], ys[4], zs[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const bool live = base + r * 32 + lane < n32;
+      const float* q = pts + pt_off((long long)srcs[r]);
+      xs[r] = live ? __ldg(q) : 0.f;
+      ys[r] = live ? __ldg(q + kGroup) : 0.f;
+      zs[r] = live ? __ldg(q + 2 * kGroup) : 0.f;
+    }
+    float* tb = tpts + grp * kBlockFloats + lane;
+    float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+    int q3[3] = {0, 0, 0};
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      tb[r * 32] = xs[r];
+      tb[kGroup + r * 32] = ys[r];
+      tb[2 * kGroup + r * 32] = zs[r];
+      // summary, exactly as group_summary_kernel computes it (the zero-filled tail belongs to the
+      // box, not to the sums)
+      const float xc = xs[r] - f.ox, yc = ys[r] - f.oy, zc = zs[r] - f.oz;
+      lo[0] = fminf(lo[0], xc); hi[0] = fmaxf(hi[0], xc);
+      lo[1] = fminf(lo[1], yc); hi[1] = fmaxf(hi[1], yc);
+      lo[2] = fminf(lo[2], zc); hi[2] = fmaxf(hi[2], zc);
+      if (base + r * 32 + lane < n32) {
+        q3[0] += (int)(__float_as_uint(fmaf(xc, f.sx, kMagic)) - kMagicBits);
+        q3[1] += (int)(__float_as_uint(fmaf(yc, f.sy, kMagic)) - kMagicBits);
+        q3[2] += (int)(__float_as_uint(fmaf(zc, f.sz, kMagic)) - kMagicBits);
+        ++cnt;
+      }
+    }
+    float blo[3], bhi[3];
+    int bq[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      blo[d] = redux_min_f32(lo[d]);
+      bhi[d] = redux_max_f32(hi[d]);
+      bq[d] = __reduce_add_sync(0xffffffffu, q3[d]);
+    }
+    const int bn = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) {
+      float4* o = summaries + grp * 3;  // GroupSummary: lo[3] hi[3] | q[3] n | pad[2]
+      o[0] = make_float4(blo[0], blo[1], blo[2], bhi[0]);
+      o[1] = make_float4(bhi[1], bhi[2], __int_as_float(bq[0]), __int_as_float(bq[1]));
+      o[2] = make_float4(__int_as_float(bq[2]), __int_as_float(bn), 0.f, 0.f);
+    }
+  }
+}
+
 }  // namespace mdkm

@@ -36,6 +36,8 @@ struct UnprojParams {
   int day0;               // day index of planes[0]
   long long chunk_begin;  // this launch handles chunks [chunk_begin, chunk_end) of the range
   long long chunk_end;
+  unsigned int* run_src;  // optional [pix_count / 8 + 1]: entry i = points produced by the pixels before
+                          // local pixel 8 i (the raster mirror build reads runs of pixels from it, mirror.cuh)
 };
 
 // One pixel: height and validity (plugin.py:151-152).  dtype 2 is the reference's own
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const Unpro
       bool ok = false;
       if (o < left) ok = load_height1(p, c * kChunk + o, hv);
       const unsigned int m = __ballot_sync(0xffffffffu, ok);
+      if (p.run_src && (lane & 7) == 0 && o < left)
+        p.run_src[(c * kChunk + o) >> 3] = (unsigned int)(out + __popc(m & ((1u << lane) - 1u)));
       if (ok) {
         long long rem = rem0 + o;
         int dcur = (int)day0;

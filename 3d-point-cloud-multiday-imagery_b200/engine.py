@@ -204,6 +204,11 @@ class Engine:
     def set_option(self, option: int, value: int):
         self._check(self._lib.mdkm_set_option(self._h, int(option), int(value)))
 
+    def raster_mirror(self, on: bool):
+        """``False``: test hook -- raster clouds use the generic (histogram + scatter) build of the
+        tile-ordered mirror instead of the run-table build.  Results are identical."""
+        self.set_option(C.OPT_RASTER_MIRROR, 1 if on else 0)
+
     def settle_groups(self, on: bool):
         """``False``: measurement mode -- every point goes through the per-point pass in every
         iteration (no group is settled from its cached summary).  Results are identical."""

@@ -97,7 +97,10 @@ void* mdkm_get_stream(const mdkm_handle* h);
  * classification pass's settling of whole 128-point groups from their cached summaries, so
  * that EVERY point is read and assigned by the per-point pass in every iteration (the
  * streaming path bench.py reports its HBM fraction for); results are identical either way. */
-enum { MDKM_OPT_SETTLE_GROUPS = 1 };
+/* MDKM_OPT_RASTER_MIRROR (default 1): 0 makes clouds that came from mdkm_unproject use the generic
+ * (histogram + scatter) build of the tile-ordered mirror instead of the run-table build; a test
+ * hook, the results are identical. */
+enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2 };
 int mdkm_set_option(mdkm_handle* h, int option, long long value);
 
 /* ---- K1: unprojection ----------------------------------------------------------------

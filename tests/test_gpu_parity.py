@@ -417,6 +417,52 @@ def test_row_straddling_groups(engine, shape, k):
     np.testing.assert_allclose(r["inertia"], fit_ref["inertia"], rtol=1e-6)
 
 
+@pytest.mark.parametrize("shape,k,rows,valid", [
+    ((3, 40, 48), 5, None, 1.0), ((2, 90, 128), 40, None, 1.0), ((2, 64, 328), 16, None, 1.0),
+    ((2, 64, 328), 20, None, 0.3), ((1, 7, 1000), 70, None, 1.0), ((4, 60, 64), 9, (30, 170), 1.0),
+    ((4, 60, 64), 9, (50, 75), 1.0), ((3, 33, 8), 3, None, 0.5), ((6, 256, 512), 300, (100, 1400), 0.9),
+])
+def test_raster_mirror_equals_generic_mirror(engine, shape, k, rows, valid):
+    """The run-table build of the tile-ordered mirror (raster clouds, mirror.cuh) against the
+    generic histogram + scatter build and against the oracle: same labels, bitwise-equal centroids."""
+    D, H, W = shape
+    hm = synth.make_stack(D, H, W, seed=D * H + W + k, n_buildings=8).numpy()
+    mask = None
+    if valid < 1.0:
+        mask = np.random.RandomState(k).rand(D, H, W) < valid
+        mask[0, : H // 2] = False  # half a day without a single point
+    r0, r1 = rows if rows else (0, D * H)
+    sl = slice(r0 * W, r1 * W)
+    kw = dict(stack_shape=shape, pix_begin=r0 * W)
+    n = engine.unproject(hm.reshape(-1)[sl], None if mask is None else mask.reshape(-1)[sl], **kw)
+    full = UO.unproject_stack(hm, mask)
+    flat_valid = UO.valid_mask(hm, mask).reshape(-1)
+    a, b = int(flat_valid[: r0 * W].sum()), int(flat_valid[: r1 * W].sum())
+    P = full[a:b]
+    assert n == P.shape[0]
+    init = synth.init_from_points(P.astype(np.float32), k, 1)
+    res = {}
+    for on in (True, False):
+        engine.raster_mirror(on)
+        try:
+            engine.drop_caches()
+            res[on] = engine.fit(init, max_iter=12, tol=0.0)
+            step = engine.lloyd_step(init)
+        finally:
+            engine.raster_mirror(True)
+        if on:
+            step_on = step
+    assert res[True]["centers"].tobytes() == res[False]["centers"].tobytes()
+    assert np.array_equal(res[True]["labels"], res[False]["labels"])
+    assert res[True]["n_iter"] == res[False]["n_iter"] and res[True]["inertia"] == res[False]["inertia"]
+    assert np.array_equal(step_on[0], step[0]) and np.array_equal(step_on[2], step[2])
+    ref = KO.kmeans_fit(P, init, max_iter=12, tol=0.0)
+    assert res[True]["n_iter"] == ref["n_iter"]
+    check_labels(P, ref["centers"], ref["labels"], res[True]["labels"])
+    check_centroids(ref["centers"], res[True]["centers"], P)
+    np.testing.assert_array_equal(step_on[2], np.bincount(KO.lloyd_iter(P - P.mean(0), init - P.mean(0))[0], minlength=k))
+
+
 def test_fit_errors(engine):
     engine.set_points(np.zeros((3, 3), dtype=np.float32))
     with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):
