@@ -57,13 +57,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Peer exchange of the K x 4 partial sums over NVLink (one process per GPU, buffers shared
-// through CUDA IPC).  Every rank owns a buffer  data[2][n_ranks][slot] + flags[2][n_ranks];
-// rank r writes its partials into slot [parity][r] of EVERY rank's buffer, then the flag.
+// Peer exchange of the K x 4 partial sums over NVLink (buffers shared through CUDA IPC, or plain
+// peer pointers inside one process).  Every rank owns a buffer  packets[2][n_ranks][slot][2] of
+// 8-byte (value half, epoch) packets; rank r writes its partials into [parity][r] of EVERY other
+// rank's buffer (lloyd.cuh: peer_exchange_sums).
 constexpr int kMaxRanks = 8;
 struct PeerXchg {
   unsigned long long* data[kMaxRanks];   // data base of rank q's buffer (peer-mapped pointer)
-  unsigned long long* flags[kMaxRanks];  // flags base of rank q's buffer
+  unsigned long long* flags[kMaxRanks];  // (unused by the packet protocol; kept for layout stability)
   int n_ranks, rank;
   int slot;                              // elements per slot (>= kpad*4 + 8)
   int pad;

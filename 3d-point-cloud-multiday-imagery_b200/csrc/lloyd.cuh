@@ -947,41 +947,50 @@ __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long
 // ---------------------------------------------------------------------------------------
 constexpr int kStages = 3;
 
-// All-gather + fixed-order sum of the ranks' partial sums, inside the step kernel: every rank
-// stores its n words into slot [parity][rank] of every rank's buffer (plain stores over
-// NVLink into peer-mapped memory), publishes a flag stamped with the step's epoch, waits for
-// the n_ranks flags in its own buffer and adds the slots in rank order.  Integer sums: every
-// rank ends with bit-identical totals.  Executed by all threads of one CTA.
+// All-gather + sum of the ranks' partial sums, inside the step kernel.  Every 64-bit word travels
+// as two 8-byte packets (32 bits of the value, 32 bits of the step's epoch) written with ONE store
+// each straight into the peers' buffers over NVLink (peer-mapped memory): value and flag arrive
+// together, so there is no separate flag, no fence and no second round trip -- the receiver
+// polls the packet itself until it carries this step's epoch (the "LL" scheme of collective
+// libraries).  Slots are double-buffered by the epoch's parity: a rank can run at most one step
+// ahead of the slowest one.  Integer sums: every rank ends with bit-identical totals.  Executed by
+// all threads of one CTA; thread t owns word t, t + kThreads, ...
 __device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned long long* acc, int n,
                                                    DevStatus* st) {
   const int tid = threadIdx.x, R = px.n_ranks;
   const unsigned long long epoch = st->epoch + 1ull;
   const int par = (int)(epoch & 1ull);
-  for (int q = 0; q < R; ++q) {
-    unsigned long long* dst = px.data[q] + ((size_t)par * R + px.rank) * px.slot;
-    for (int i = tid; i < n; i += kThreads) st_relaxed_sys_u64(dst + i, __ldcg(acc + i));
-  }
-  __syncthreads();
-  if (tid < R) {
-    // release at system scope after the CTA barrier: cumulative over the stores above
-    st_release_sys_u64(px.flags[tid] + par * R + px.rank, epoch);
-    // bounded wait (about 4 s): a missing peer must not hang the GPU
-    const unsigned long long* mine = px.flags[px.rank] + par * R + tid;
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(mine) != epoch) {
-      if (clock64() - t0 > (8ll << 30)) {
-        st->xchg_timeout = 1;
-        break;
-      }
+  const unsigned int tag = (unsigned int)epoch;
+  // packets of (parity, source rank): 2 * slot of them, 8 bytes each
+  const size_t mine = ((size_t)par * R + px.rank) * (size_t)px.slot * 2;
+  for (int i = tid; i < n; i += kThreads) {
+    const unsigned long long v = __ldcg(acc + i);
+    for (int q = 0; q < R; ++q) {
+      if (q == px.rank) continue;
+      unsigned long long* dst = px.data[q] + mine + 2 * (size_t)i;
+      st_relaxed_sys_v2u32(dst, (unsigned int)v, tag);
+      st_relaxed_sys_v2u32(dst + 1, (unsigned int)(v >> 32), tag);
     }
   }
-  __syncthreads();
-  const unsigned long long* base = px.data[px.rank] + (size_t)par * R * px.slot;
+  bool timed_out = false;
+  const long long t0 = clock64();
   for (int i = tid; i < n; i += kThreads) {
-    unsigned long long s = 0ull;
-    for (int q = 0; q < R; ++q) s += ld_relaxed_sys_u64(base + (size_t)q * px.slot + i);
+    unsigned long long s = __ldcg(acc + i);
+    for (int q = 0; q < R; ++q) {
+      if (q == px.rank) continue;
+      const unsigned long long* src = px.data[px.rank] + ((size_t)par * R + q) * (size_t)px.slot * 2 + 2 * (size_t)i;
+      uint2 lo = ld_relaxed_sys_v2u32(src), hi = ld_relaxed_sys_v2u32(src + 1);
+      // bounded wait (about 4 s): a missing peer must not hang the GPU
+      while ((lo.y != tag || hi.y != tag) && !timed_out) {
+        if (clock64() - t0 > (8ll << 30)) timed_out = true;
+        if (lo.y != tag) lo = ld_relaxed_sys_v2u32(src);
+        if (hi.y != tag) hi = ld_relaxed_sys_v2u32(src + 1);
+      }
+      s += (unsigned long long)lo.x | ((unsigned long long)hi.x << 32);
+    }
     acc[i] = s;
   }
+  if (timed_out) st->xchg_timeout = 1;
   if (tid == 0) st->epoch = epoch;
   __threadfence();
   __syncthreads();

@@ -915,7 +915,7 @@ int mdkm_comm_p2p_handle(mdkm_handle* h, unsigned char out[MDKM_IPC_HANDLE_BYTES
   CU(cudaSetDevice(h->device));
   close_p2p(h);
   const size_t slot = (size_t)kMaxK * 4 + 8;
-  const size_t words = 2 * (size_t)h->n_ranks * slot + 2 * (size_t)h->n_ranks;
+  const size_t words = 4 * (size_t)h->n_ranks * slot + 2 * (size_t)h->n_ranks;  // two 8-byte packets per word
   CU(cudaMalloc(&h->xchg, words * 8));
   CU(cudaMemset(h->xchg, 0, words * 8));
   cudaIpcMemHandle_t ih;
@@ -948,7 +948,7 @@ int mdkm_comm_p2p_open(mdkm_handle* h, const unsigned char* handles) {
       h->peer_base[q] = base;
     }
     px.data[q] = static_cast<unsigned long long*>(base);
-    px.flags[q] = px.data[q] + 2 * (size_t)h->n_ranks * slot;
+    px.flags[q] = px.data[q] + 4 * (size_t)h->n_ranks * slot;
   }
   h->px = px;
   h->p2p_ok = true;
@@ -998,7 +998,7 @@ int mdkm_comm_p2p_open_ptrs(mdkm_handle* h, void* const* buffers) {
       }
     }
     px.data[q] = static_cast<unsigned long long*>(base);
-    px.flags[q] = px.data[q] + 2 * (size_t)h->n_ranks * slot;
+    px.flags[q] = px.data[q] + 4 * (size_t)h->n_ranks * slot;
   }
   h->px = px;
   h->p2p_ok = true;

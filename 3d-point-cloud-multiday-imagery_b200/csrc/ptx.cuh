@@ -136,6 +136,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   return v;
 }
 
+// 8-byte (value, flag) packets: one store / one load each, so a reader never sees one without the other
+__device__ __forceinline__ void st_relaxed_sys_v2u32(void* p, unsigned int a, unsigned int b) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_sys_v2u32(const void* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
 // warp-wide float min / max in one instruction (sm_100a: CREDUX.MIN/MAX.F32)
 __device__ __forceinline__ float redux_min_f32(float v) {
   float r;
