@@ -99,7 +99,11 @@ class Engine:
     # The handle enqueues on its own stream.  A CUDA tensor handed to it may still be being
     # produced on torch's current stream (including the .to() / .contiguous() copies made just
     # above), and a device-resident output may be consumed there right after the call: the two
-    # streams are ordered with events, and temporaries are kept alive for the handle's stream.
+    # streams are ordered with events.  Every library call that READS a caller's device buffer
+    # returns only after the handle's stream has consumed it (they all end in a stream
+    # synchronisation), so temporaries may be released as soon as the call is back -- no
+    # record_stream, which would tie a tensor's release to a stream this engine may already have
+    # destroyed.
     def _torch_streams(self):
         import torch
 
@@ -112,9 +116,6 @@ class Engine:
         ext, cur = self._torch_streams()
         if cur.cuda_stream != self._stream_ptr:
             ext.wait_stream(cur)
-            for t in tensors:
-                if t is not None and _is_torch(t) and t.is_cuda:
-                    t.record_stream(ext)
 
     def _before_torch(self):
         """torch's current stream waits for what the handle has enqueued so far."""
@@ -125,6 +126,7 @@ class Engine:
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
+            self._ext_stream = None  # wraps the handle's stream, which dies with the handle
             self._lib.mdkm_destroy(self._h)
             self._h = c_void_p()
 

@@ -127,6 +127,29 @@ def test_cuda_tensor_inputs_are_ordered_after_torch_stream(engine):
     np.testing.assert_array_equal(out.cpu().numpy().astype(np.float64), P)
 
 
+def test_inputs_outlive_a_closed_engine(pkg):
+    """A CUDA tensor that was handed to an engine must be releasable after that engine (and its
+    stream) is gone: nothing may tie the tensor's release to the destroyed stream."""
+    import gc
+
+    import torch
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        hm = synth.make_stack(2, 256, 320, seed=3, device="cuda")
+        with pkg.Engine(0) as solo:
+            n = solo.unproject(hm)
+            init = solo.gather_points(np.arange(4, dtype=np.int64) * (n // 5)).astype(np.float64)
+            labels = torch.empty(n, dtype=torch.int32, device="cuda")
+            solo.fit(init, max_iter=3, tol=0.0, labels_out=labels)
+        del hm, labels
+        gc.collect()
+        torch.cuda.empty_cache()
+        x = torch.ones(1 << 20, device="cuda").sum().item()  # the allocator still works
+    torch.cuda.synchronize()
+    assert x == float(1 << 20)
+
+
 def test_output_buffers_must_be_usable_as_they_are(engine):
     hm = synth.make_stack(1, 32, 48, seed=1).numpy()
     n = engine.unproject(hm)
