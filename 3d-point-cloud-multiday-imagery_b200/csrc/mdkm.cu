@@ -105,8 +105,8 @@ struct mdkm_handle {
   int opt_settle = 1;  // MDKM_OPT_SETTLE_GROUPS
 
   // unprojection scratch
-  DevBuf<unsigned int> chunk_counts;
   DevBuf<long long> chunk_offsets;
+  DevBuf<unsigned long long> tile_status;  // look-back words of the fused unprojection pass (+ its ticket)
   DevBuf<unsigned char> staging;  // host inputs staged here
   DevBuf<double> planes;
   long long* h_total = nullptr;  // pinned
@@ -859,7 +859,7 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->gsum); release(h->glabel); release(h->worklist);
   release(h->tpts); release(h->cell_counts); release(h->cell_offsets);
   release(h->run_src); release(h->druns); release(h->gfirst);
-  release(h->chunk_counts); release(h->chunk_offsets); release(h->staging); release(h->planes);
+  release(h->tile_status); release(h->chunk_offsets); release(h->staging); release(h->planes);
   release(h->d_seg_off); release(h->sel_hist); release(h->sel_targets);
   release(h->kpp_closest); release(h->kpp_cell); release(h->kpp_blk); release(h->kpp_prefix);
   release(h->kpp_partials); release(h->kpp_rand); release(h->kpp_state);
@@ -1132,16 +1132,18 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   }
   OK(alloc_points(h, pix_count));
   const long long n_chunks = (pix_count + kChunk - 1) / kChunk;
-  OK(ensure(h, h->chunk_counts, (size_t)n_chunks + 1));
+  const long long n_tiles = (pix_count + kTile - 1) / kTile;
   OK(ensure(h, h->chunk_offsets, (size_t)n_chunks + 2));
+  OK(ensure(h, h->tile_status, (size_t)n_tiles + 2));  // [n_tiles] status words, then the ticket counter
   UnprojParams up{};
   up.hm = d_hm; up.mask = d_mask;
   up.pix_begin = pix_begin; up.pix_count = pix_count; up.HW = HW; up.W = W; up.H = H;
   up.dtype = hm_dtype;
   up.vec_ok = ((reinterpret_cast<uintptr_t>(d_hm) & 15) == 0) && (!d_mask || (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
   up.scale = hm_scale; up.max_abs = max_abs;
-  up.chunk_counts = h->chunk_counts.p;
   up.chunk_offsets = h->chunk_offsets.p;
+  up.status = h->tile_status.p;
+  up.ticket = reinterpret_cast<unsigned int*>(h->tile_status.p + n_tiles);
   up.pts = h->pts.p;
   up.planes = nullptr;
   up.day0 = (int)(pix_begin / HW);
@@ -1192,6 +1194,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
     }
     if (cloud_out) OK(ensure(h, h->cloud_aos, (size_t)pix_count * 3));
     CU(cudaMemsetAsync(h->slab_totals.p, 0, 8, h->stream));
+    CU(cudaMemsetAsync(h->tile_status.p, 0, ((size_t)n_tiles + 1) * 8, h->stream));  // look-back words + ticket
     // copies of this call must not start before earlier work on the compute stream that still
     // reads the staging buffer has finished
     if (from_host) {
@@ -1231,16 +1234,17 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
       if (c_end > done_chunks) {
         up.chunk_begin = done_chunks;
         up.chunk_end = c_end;
-        const long long nc = c_end - done_chunks;
-        const int g = grid_for(h, (nc + 7) / 8, 8);
+        // the tiles of these chunks, in one fused pass (rank, look-back, write)
+        up.tile_begin = done_chunks * (kChunk / kTile);
+        up.tile_end = std::min<long long>(c_end * (kChunk / kTile), n_tiles);
+        up.total_out = h->slab_totals.p + s + 1;
+        const long long nt = up.tile_end - up.tile_begin;
+        const int g = grid_for(h, (nt + 7) / 8, 4);  // 48 KB of staging per CTA: four CTAs per SM
+        if (s > 0) CU(cudaMemsetAsync(up.ticket, 0, 4, h->stream));
         const int span = prof_begin(h, MDKM_PHASE_UNPROJECT, std::min<long long>(c_end * kChunk, pix_count) - done_chunks * kChunk);
-        unproject_count_kernel<<<g, kThreads, 0, h->stream>>>(up);
-        scan_chunks_kernel<<<1, 1024, 0, h->stream>>>(h->chunk_counts.p + done_chunks, nc,
-                                                      h->chunk_offsets.p + done_chunks, h->slab_totals.p + s,
-                                                      h->slab_totals.p + s + 1);
-        unproject_scatter_kernel<<<g, kThreads, 0, h->stream>>>(up);
+        unproject_fused_kernel<<<g, kThreads, 0, h->stream>>>(up);
         prof_end(h, span);
-        h->launches += 3;
+        ++h->launches;
         if (cloud_out) {
           blocked_to_aos_range_kernel<<<g, kThreads, 0, h->stream>>>(h->pts.p, h->slab_totals.p + s, cloud_napari,
                                                                      h->cloud_aos.p);

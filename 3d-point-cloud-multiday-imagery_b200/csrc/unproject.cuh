@@ -6,10 +6,13 @@
 // eigen-solve) for every day of the stack, and concatenates the days (absent in the
 // reference).
 //
-// Work unit: a warp-chunk of kChunk = 4096 consecutive pixels (32 rounds of 32 lanes x 4 px,
-// 16 B per lane per round).  Pass 1 counts the valid pixels of every chunk, a single-CTA scan
-// turns the counts into offsets, pass 2 re-reads the pixels and writes x, y, z at
-// offset + warp-exclusive-rank, so the output order is exactly np.where's.
+// ONE pass over the rasters (4 B read + 12 B written per pixel, the algorithmic minimum): a warp
+// takes a tile of kTile = 1024 consecutive pixels (8 rounds of 32 lanes x 4 px, 16 B loads),
+// ranks its valid pixels with ballots, parks them in shared memory, obtains the number of
+// points of all earlier tiles by a decoupled look-back over per-tile status words (tiles are
+// handed out by a ticket counter, so every predecessor of a running tile is itself running or
+// done), and writes x, y, z as contiguous runs at offset + rank -- the output order is exactly
+// np.where's.  Offsets at every kChunk = 4096 pixels are kept for the day boundaries.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -17,6 +20,11 @@
 namespace mdkm {
 
 constexpr int kChunk = 4096;
+constexpr int kTile = 1024;  // pixels per warp tile of the fused pass
+// per-tile status word of the decoupled look-back: flag in the two top bits, count below
+constexpr unsigned long long kStAggregate = 1ull << 62;  // value = valid pixels of this tile
+constexpr unsigned long long kStPrefix = 2ull << 62;     // value = valid pixels up to and including this tile
+constexpr unsigned long long kStValue = (1ull << 62) - 1ull;
 
 struct UnprojParams {
   const void* hm;         // points at pixel pix_begin
@@ -29,8 +37,7 @@ struct UnprojParams {
   int vec_ok;             // hm (and mask) aligned for 16 B / 4 B vector loads
   float scale;            // for I16
   float max_abs;
-  unsigned int* chunk_counts;
-  const long long* chunk_offsets;
+  long long* chunk_offsets;  // [n_chunks]: points produced before every kChunk-th pixel of the range
   float* pts;             // blocked cloud (common.cuh)
   const double* planes;   // [n_days][8]: centre xyz, normal xyz, pad -- or nullptr
   int day0;               // day index of planes[0]
@@ -38,6 +45,11 @@ struct UnprojParams {
   long long chunk_end;
   unsigned int* run_src;  // optional [pix_count / 8 + 1]: entry i = points produced by the pixels before
                           // local pixel 8 i (the raster mirror build reads runs of pixels from it, mirror.cuh)
+  // fused pass: this launch handles tiles [tile_begin, tile_end) of the range
+  long long tile_begin, tile_end;
+  unsigned long long* status;  // [n_tiles] look-back words, zeroed once per mdkm_unproject
+  unsigned int* ticket;        // zeroed before every launch
+  long long* total_out;        // points of all tiles up to tile_end - 1 (running total of the range)
 };
 
 // One pixel: height and validity (plugin.py:151-152).  dtype 2 is the reference's own
@@ -124,110 +136,125 @@ __device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i
   }
 }
 
-__global__ void __launch_bounds__(kThreads) unproject_count_kernel(const UnprojParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (kThreads / 32);
-  for (long long c = p.chunk_begin + warp; c < p.chunk_end; c += n_warps) {
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Points of all tiles before tile t (warp-collective).  Flag and value share one 64-bit word, so
+// no fence is involved: a word is either not there yet, an aggregate or a prefix.
+__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* status, long long t, unsigned int cnt,
+                                                            int lane) {
+  if (lane == 0 && t > 0) st_status(status + t, kStAggregate | cnt);
+  unsigned long long excl = 0ull;
+  for (long long j = t - 1;; j -= 32) {
+    const long long jj = j - lane;
+    unsigned long long s;
+    unsigned int first_pre, invalid;
+    do {
+      s = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
+      const unsigned int flag = (unsigned int)(s >> 62);
+      const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
+      first_pre = pre ? (unsigned int)__ffs(pre) - 1u : 32u;
+      // every tile between t and the nearest prefix must have published its aggregate
+      const unsigned int need = first_pre < 32u ? ((2u << first_pre) - 1u) : 0xffffffffu;
+      invalid = __ballot_sync(0xffffffffu, flag == 0u) & need;
+    } while (invalid);
+    const unsigned int agg = __reduce_add_sync(0xffffffffu, (unsigned int)lane < first_pre ? (unsigned int)(s & kStValue) : 0u);
+    excl += agg;
+    if (first_pre < 32u) {
+      excl += __shfl_sync(0xffffffffu, s, first_pre) & kStValue;
+      break;
+    }
+  }
+  if (lane == 0) st_status(status + t, kStPrefix | (excl + cnt));
+  return excl;
+}
+
+__global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojParams p) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ float s_z[kWarps][kTile];
+  __shared__ unsigned short s_ix[kWarps][kTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wz = s_z[warp];
+  unsigned short* wix = s_ix[warp];
+  while (true) {
+    long long t = 0;
+    if (lane == 0) t = p.tile_begin + (long long)atomicAdd(p.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= p.tile_end) break;
+    const long long pix0 = t * kTile;  // local index of the tile's first pixel
+    // 1. the tile's pixels: 8 x 16 B per lane in flight
+    float hv[kTile / 128][4];
+    unsigned int vb[kTile / 128];
+#pragma unroll
+    for (int r = 0; r < kTile / 128; ++r) load_heights4(p, pix0 + r * 128 + lane * 4, hv[r], vb[r]);
+    // 2. rank of every valid pixel inside the tile, in pixel order, and 3. park (z, pixel) there
     unsigned int cnt = 0;
-#pragma unroll 4
-    for (int r = 0; r < kChunk / 128; ++r) {
-      const long long i = c * kChunk + r * 128 + lane * 4;
-      float h[4];
-      unsigned int vb;
-      load_heights4(p, i, h, vb);
-      cnt += __popc(vb);
-    }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) p.chunk_counts[c] = cnt;
-  }
-}
-
-// Exclusive scan of n chunk counts (single CTA of 1024 threads), continuing from *carry_in
-// (points produced by the earlier slabs); writes the running total to *carry_out.
-__global__ void __launch_bounds__(1024) scan_chunks_kernel(const unsigned int* counts, long long n,
-                                                           long long* offsets, const long long* carry_in,
-                                                           long long* carry_out) {
-  __shared__ long long s_warp[32];
-  __shared__ long long s_carry;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) s_carry = carry_in ? *carry_in : 0;
-  __syncthreads();
-  for (long long base = 0; base < n; base += 1024) {
-    const long long i = base + tid;
-    const long long v = (i < n) ? (long long)counts[i] : 0;
-    long long s = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane == 31) s_warp[w] = s;
-    __syncthreads();
-    if (w == 0) {
-      long long ws = s_warp[lane];
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += t;
+    unsigned int head[kTile / 128];  // rank of this lane's first pixel of round r
+#pragma unroll
+    for (int r = 0; r < kTile / 128; ++r) {
+      const unsigned int lt = (1u << lane) - 1u;
+      unsigned int before = 0, total = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned int m = __ballot_sync(0xffffffffu, (vb[r] >> e) & 1u);
+        before += __popc(m & lt);
+        total += __popc(m);
       }
-      s_warp[lane] = ws;
+      head[r] = cnt + before;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((vb[r] >> e) & 1u) {
+          const unsigned int idx = head[r] + __popc(vb[r] & ((1u << e) - 1u));
+          wz[idx] = hv[r][e];
+          wix[idx] = (unsigned short)(r * 128 + lane * 4 + e);
+        }
+      cnt += total;
     }
-    __syncthreads();
-    const long long carry = s_carry;
-    const long long excl = carry + (w ? s_warp[w - 1] : 0) + (s - v);
-    if (i < n) offsets[i] = excl;
-    __syncthreads();
-    if (tid == 1023) s_carry = carry + s_warp[31];
-    __syncthreads();
-  }
-  if (tid == 0) *carry_out = s_carry;
-}
-
-// Pass 2.  One pixel per lane and round (32 consecutive pixels per warp instruction): the
-// valid pixels of a round are ranked with one ballot and land on consecutive output slots, so
-// the stores of x, y and z are contiguous runs instead of 4-byte fragments.  (Pass 1 keeps
-// the float4 loads: it has nothing to write.)
-__global__ void __launch_bounds__(kThreads) unproject_scatter_kernel(const UnprojParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (kThreads / 32);
-  for (long long c = p.chunk_begin + warp; c < p.chunk_end; c += n_warps) {
-    long long out = p.chunk_offsets[c];
-    // position of the chunk's first pixel in the stack: once per chunk in 64 bits
-    const long long gp0 = p.pix_begin + c * kChunk;
+    __syncwarp();
+    // 4. points of all earlier tiles
+    const unsigned long long excl = tile_lookback(p.status, t, cnt, lane);
+    if (lane == 0) {
+      if ((t & (kChunk / kTile - 1)) == 0) p.chunk_offsets[t / (kChunk / kTile)] = (long long)excl;
+      if (t == p.tile_end - 1 && p.total_out) *p.total_out = (long long)(excl + cnt);
+    }
+    if (p.run_src && (lane & 1) == 0) {
+#pragma unroll
+      for (int r = 0; r < kTile / 128; ++r) {
+        const long long o = pix0 + r * 128 + lane * 4;  // a multiple of 8
+        if (o < p.pix_count) p.run_src[o >> 3] = (unsigned int)(excl + head[r]);
+      }
+    }
+    // 5. contiguous runs of x, y, z
+    const long long gp0 = p.pix_begin + pix0;
     const long long day0 = gp0 / p.HW;
     const long long rem0 = gp0 - day0 * p.HW;
-    const long long left = min((long long)kChunk, p.pix_count - c * kChunk);
-#pragma unroll 4
-    for (int r = 0; r < kChunk / 32; ++r) {
-      const int o = r * 32 + lane;
-      float hv = 0.f;
-      bool ok = false;
-      if (o < left) ok = load_height1(p, c * kChunk + o, hv);
-      const unsigned int m = __ballot_sync(0xffffffffu, ok);
-      if (p.run_src && (lane & 7) == 0 && o < left)
-        p.run_src[(c * kChunk + o) >> 3] = (unsigned int)(out + __popc(m & ((1u << lane) - 1u)));
-      if (ok) {
-        long long rem = rem0 + o;
-        int dcur = (int)day0;
-        while (rem >= p.HW) {  // a chunk may run into the next day(s)
-          rem -= p.HW;
-          ++dcur;
-        }
-        const int row = (int)(rem / p.W);
-        const int col = (int)(rem - (long long)row * p.W);
-        float zz = hv;
-        if (p.planes) {
-          // plugin.py:171: height_rel = dot(P - center, normal)
-          const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
-          zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)hv - pl[2]) * pl[5]);
-        }
-        float* dst = p.pts + pt_off(out + __popc(m & ((1u << lane) - 1u)));
-        dst[0] = (float)col;
-        dst[kGroup] = (float)row;
-        dst[2 * kGroup] = zz;
+    for (unsigned int i = lane; i < cnt; i += 32) {
+      long long rem = rem0 + wix[i];
+      int dcur = (int)day0;
+      while (rem >= p.HW) {  // a tile may run into the next day(s)
+        rem -= p.HW;
+        ++dcur;
       }
-      out += __popc(m);
+      const int row = (int)(rem / p.W);
+      const int col = (int)(rem - (long long)row * p.W);
+      float zz = wz[i];
+      if (p.planes) {
+        // plugin.py:171: height_rel = dot(P - center, normal)
+        const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
+        zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)zz - pl[2]) * pl[5]);
+      }
+      float* dst = p.pts + pt_off((long long)excl + i);
+      dst[0] = (float)col;
+      dst[kGroup] = (float)row;
+      dst[2 * kGroup] = zz;
     }
+    __syncwarp();  // the staging arrays are reused by the next tile
   }
 }
 
