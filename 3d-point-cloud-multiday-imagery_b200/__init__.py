@@ -9,10 +9,11 @@ from .api import (FusionResult, Layer, MultiDayFusionPlugin, fuse_height_rasters
 from .build import build_library
 from .dist import init_engine_comm, shard_range
 from .engine import Engine
+from .group import DeviceGroup
 from .synth import init_from_points, make_stack, make_stack_range
 
 __all__ = [
-    "Engine", "FusionResult", "Layer", "MultiDayFusionPlugin", "build_library",
+    "DeviceGroup", "Engine", "FusionResult", "Layer", "MultiDayFusionPlugin", "build_library",
     "fuse_height_rasters", "fuse_multiday_kmeans", "init_engine_comm", "init_from_points", "kmeans_points",
     "make_stack", "make_stack_range", "shard_range", "to_layers",
 ]

@@ -73,13 +73,36 @@ def _check_random_state(seed):
     raise ValueError("random_state must be None, an int or a numpy RandomState")
 
 
-def _is_same_clustering(l1, l2, k) -> bool:
-    """sklearn/cluster/_k_means_common.pyx:314-330 (labels equal up to a permutation)."""
+def _label_mapping(l1, l2, k):
+    """The map label-of-l1 -> label-of-l2 by first occurrence, and whether every point obeys it
+    (the loop of sklearn/cluster/_k_means_common.pyx:314-330 on one shard)."""
     mapping = np.full(k, -1, dtype=np.int64)
-    first = np.unique(l1, return_index=True)
-    for lab, i in zip(*first):
-        mapping[lab] = l2[i]
-    return bool(np.array_equal(mapping[l1], l2))
+    if l1.shape[0]:
+        uniq, first = np.unique(l1, return_index=True)
+        mapping[uniq] = l2[first]
+    return mapping, bool(np.array_equal(mapping[l1], l2))
+
+
+def _merge_label_mappings(mappings, oks) -> bool:
+    """Do the shards' maps describe ONE map?  (labels equal up to a permutation, over all shards)"""
+    merged = np.full(mappings[0].shape[0], -1, dtype=np.int64)
+    for m in mappings:
+        m = np.asarray(m, dtype=np.int64)
+        both = (m >= 0) & (merged >= 0)
+        if np.any(m[both] != merged[both]):
+            return False
+        merged = np.where(m >= 0, m, merged)
+    return bool(all(oks))
+
+
+def _is_same_clustering(l1, l2, k, gather=None) -> bool:
+    """sklearn/cluster/_k_means_common.pyx:314-330 (labels equal up to a permutation).  With
+    sharded labels ``gather(mapping, ok) -> (mappings, oks)`` collects every rank's shard map
+    (a collective: all ranks call it), and the verdict is the same on every rank."""
+    mapping, ok = _label_mapping(l1, l2, k)
+    if gather is None:
+        return ok
+    return _merge_label_mappings(*gather(mapping, ok))
 
 
 def _random_seeds(rs, n: int, k: int) -> np.ndarray:
@@ -100,8 +123,14 @@ def _random_seeds(rs, n: int, k: int) -> np.ndarray:
     return found[:k]
 
 
-def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True):
-    """KMeans.fit driver (sklearn/_kmeans.py:1436-1563): init, n_init restarts, best inertia."""
+def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True,
+                labels_out=None, gather_mappings=None):
+    """KMeans.fit driver (sklearn/_kmeans.py:1436-1563): init, n_init restarts, best inertia.
+
+    ``labels_out``: optional int32 array that receives this rank's labels of the best run.
+    ``gather_mappings``: with a multi-rank engine, the collective that lets the ranks agree on
+    sklearn's "same clustering up to a permutation" test (see ``_is_same_clustering``); when it is
+    missing the test is skipped on multi-rank engines (the inertia comparison alone decides)."""
     n = eng.n_points_global  # with a communicator: every rank draws the same seeds
     k = int(n_clusters)
     if k < 1:
@@ -119,6 +148,11 @@ def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_
         raise ValueError("init must be 'k-means++', 'random' or an array of shape (n_clusters, 3)")
     if n_init == "auto":
         n_init = 1 if init == "k-means++" else 10  # sklearn/_kmeans.py:896-903
+    if eng.n_ranks > 1 and gather_mappings is None:
+        from .dist import torch_gather_mappings
+
+        gather_mappings = torch_gather_mappings(eng)  # None unless torch.distributed spans the ranks
+    single = int(n_init) == 1
     best = None
     for _ in range(int(n_init)):
         if init_is_array:
@@ -127,23 +161,29 @@ def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_
             centers0 = eng.gather_points(_random_seeds(rs, n, k)).astype(np.float64)
         else:
             centers0, _ = eng.kmeans_plusplus(k, rs)
-        r = eng.fit(centers0, max_iter=max_iter, tol=tol, want_labels=want_labels)
-        # sklearn/_kmeans.py:1534-1541.  With a communicator the labels are this rank's shard
-        # only, so the "same clustering up to a permutation" escape is skipped there: the
-        # decision must be identical on every rank, and the (global) inertia is.
-        same = (want_labels and eng.n_ranks == 1 and best is not None
-                and _is_same_clustering(r["labels"], best["labels"], k))
-        if best is None or (r["inertia"] < best["inertia"] and not same):
+        r = eng.fit(centers0, max_iter=max_iter, tol=tol, want_labels=want_labels,
+                    labels_out=labels_out if (single and want_labels) else None)
+        # sklearn/_kmeans.py:1534-1541: a run replaces the best one when its inertia is lower AND it
+        # is not the same clustering up to a permutation.  The inertia is global, so every rank
+        # takes the same branch and the (collective) permutation test pairs up.
+        better = best is not None and r["inertia"] < best["inertia"]
+        same = False
+        if better and want_labels and (eng.n_ranks == 1 or gather_mappings is not None):
+            same = _is_same_clustering(r["labels"], best["labels"], k, gather_mappings if eng.n_ranks > 1 else None)
+        if best is None or (better and not same):
             best = r
-            if int(n_init) > 1 and r["labels"] is not None:
+            if not single and r["labels"] is not None:
                 best = dict(r, labels=r["labels"].copy())  # result buffers are reused by the next run
+    if labels_out is not None and want_labels and not single:
+        labels_out[...] = best["labels"]
+        best = dict(best, labels=labels_out)
     return best
 
 
 def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k-means++", n_init=1,
                          max_iter=300, tol=1e-4, random_state=None, max_abs_height=MAX_ABS_HEIGHT,
                          detrend=False, disparity_scale=None, ground_level=False, return_cloud=True,
-                         device=0, engine: Optional[Engine] = None, stack_shape=None,
+                         device=0, devices=None, engine=None, stack_shape=None,
                          pix_begin=0, raster_layout=None) -> FusionResult:
     """Unproject a multi-day height-map stack into one XYZ cloud and cluster it (Lloyd).
 
@@ -160,8 +200,25 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     engine : reuse an existing ``Engine`` (keeps device buffers, and with
         ``Engine(pinned_results=True)`` page-locked result buffers, across calls); with a
         multi-rank engine pass this rank's flat slice plus ``stack_shape`` / ``pix_begin``.
+        A ``DeviceGroup`` is accepted too (see ``devices``).
+    devices : several CUDA devices used from THIS process (``[0, 1, 2, 3]``): the host stack is
+        sharded over them by row bands, one host thread drives each device, the devices exchange
+        their K x 4 partial sums over NVLink inside the Lloyd kernel, and the results are
+        assembled in the reference's point order -- bit-identical to one device.  This is how the
+        in-process caller of the reference (a napari worker thread, widget.py:116-147) gets more
+        than one GPU without ``torchrun``.
     Returns a FusionResult; ``fused_cloud`` is float32 ``[N,3]`` in napari (z,y,x) order.
     """
+    from .group import DeviceGroup
+
+    if devices is not None or isinstance(engine, DeviceGroup):
+        if stack_shape is not None or pix_begin:
+            raise ValueError("stack_shape / pix_begin describe a pre-sharded stack; a device group shards by itself")
+        return _fuse_on_group(height_maps, valid_masks, group=engine if isinstance(engine, DeviceGroup) else None,
+                              devices=devices, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter,
+                              tol=tol, random_state=random_state, max_abs_height=max_abs_height, detrend=detrend,
+                              disparity_scale=disparity_scale, ground_level=ground_level, return_cloud=return_cloud,
+                              raster_layout=raster_layout)
     own = engine is None
     eng = engine or Engine(device)
     try:
@@ -192,6 +249,47 @@ def fuse_multiday_kmeans(height_maps, valid_masks=None, *, n_clusters=8, init="k
     finally:
         if own:
             eng.close()
+
+
+def _fuse_on_group(height_maps, valid_masks, *, group, devices, n_clusters, init, n_init, max_iter, tol,
+                   random_state, **unproject_kw) -> FusionResult:
+    """``fuse_multiday_kmeans`` on several devices of this process (``group.DeviceGroup``)."""
+    import threading
+
+    from .group import DeviceGroup, clone_random_state
+
+    own = group is None
+    grp = group or DeviceGroup(devices)
+    try:
+        if random_state is None:  # every rank must draw the same numbers
+            random_state = int(np.random.RandomState().randint(0, 2**31 - 1))
+        states = clone_random_state(random_state, grp.world)
+        # thread all-gather of the shards' label maps (see _is_same_clustering)
+        barrier = threading.Barrier(grp.world)
+        slots = [None] * grp.world
+
+        def gather_for(rank):
+            def gather(mapping, ok):
+                slots[rank] = (mapping, ok)
+                barrier.wait()
+                got = list(slots)
+                barrier.wait()  # nobody overwrites a slot before everybody has read it
+                return [g[0] for g in got], [g[1] for g in got]
+            return gather
+
+        def run(eng, labels_out):
+            r = eng.rank
+            return _run_kmeans(eng, n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter, tol=tol,
+                               random_state=states[r], labels_out=labels_out,
+                               gather_mappings=gather_for(r) if grp.world > 1 else None)
+
+        res, labels, cloud, hn, extra = grp.fuse(height_maps, valid_masks, run_kmeans=run, **unproject_kw)
+        return FusionResult(labels=labels, centroids=res["centers"], fused_cloud=cloud, n_iter=res["n_iter"],
+                            inertia=res["inertia"], n_points=int(labels.shape[0]), n_refined=res["n_refined"],
+                            n_relocations=res["n_relocations"], height_norm=hn, extra=extra)
+    finally:
+        if own:
+            grp.close()
 
 
 def fuse_height_rasters(paths, **kwargs) -> FusionResult:
@@ -271,11 +369,13 @@ class MultiDayFusionPlugin:
 
     requires_image = False  # plugin.py:30
 
-    def __init__(self, n_clusters=8, device=0, log_path=None, **kmeans_kwargs):
+    def __init__(self, n_clusters=8, device=0, devices=None, log_path=None, **kmeans_kwargs):
         """``log_path``: where the traceback of a failed run is appended, like the reference's
-        ``data/TEMP/log.txt`` (plugin.py:48, 236-240); None = only printed."""
+        ``data/TEMP/log.txt`` (plugin.py:48, 236-240); None = only printed.
+        ``devices``: several GPUs of this process (see ``fuse_multiday_kmeans``)."""
         self.n_clusters = n_clusters
         self.device = device
+        self.devices = devices
         self.log_path = log_path
         self.kmeans_kwargs = kmeans_kwargs
 
@@ -290,7 +390,7 @@ class MultiDayFusionPlugin:
     def run(self, image, viewer=None, valid_masks=None) -> List[Layer]:
         try:
             res = fuse_multiday_kmeans(image, valid_masks, n_clusters=self.n_clusters, device=self.device,
-                                       **self.kmeans_kwargs)
+                                       devices=self.devices, **self.kmeans_kwargs)
             return to_layers(res)
         except Exception as e:  # noqa: BLE001 - reference convention, plugin.py:236-241
             traceback.print_exc()

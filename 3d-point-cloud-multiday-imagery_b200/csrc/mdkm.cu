@@ -94,6 +94,7 @@ struct mdkm_handle {
   DevBuf<unsigned char> druns;
   DevBuf<unsigned int> gfirst;
   int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
+  int opt_cell_px = 0, opt_cell_rows = 0;  // MDKM_OPT_CELL_PX / MDKM_OPT_CELL_ROWS (0 = automatic)
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -309,12 +310,14 @@ int allreduce(mdkm_handle* h, void* buf, size_t count, int dtype, int op) {
 
 // Frame of the resident cloud: origin / fixed-point scale / half-range from the global
 // per-dimension min and max.
-int compute_frame(mdkm_handle* h) {
+// `minmax_ready`: uscratch[4..9] already holds the ordered min / max of the points (the fused
+// unprojection pass collects them while it writes the cloud).
+int compute_frame(mdkm_handle* h, bool minmax_ready = false) {
   OK(ensure(h, h->uscratch, 16));
   OK(ensure(h, h->dscratch, 64 + (size_t)h->n_ranks));
   unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-  CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  if (h->n > 0) {
+  if (!minmax_ready) CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  if (h->n > 0 && !minmax_ready) {
     minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, 0, h->stream>>>(h->pts.p, h->n,
                                                                                      h->uscratch.p + 4);
     ++h->launches;
@@ -526,6 +529,7 @@ int build_mirror_raster(mdkm_handle* h, int cell_px) {
   // rows per cell: about 256 points per cell, counting every day that covers a row
   const double per_row = (double)h->n / (double)g.yext / (double)g.gx;  // points per cell and row of y
   g.rpc = (int)std::max(1.0, std::min(64.0, nearbyint(256.0 / std::max(per_row, 1e-9))));
+  if (h->opt_cell_rows > 0) g.rpc = std::min(64, h->opt_cell_rows);
   g.gy = (g.yext + g.rpc - 1) / g.rpc;
   const long long n_cells = (long long)g.gx * g.gy;
   const long long n_entries = n_cells * g.nd * g.rpc;
@@ -543,7 +547,7 @@ int build_mirror_raster(mdkm_handle* h, int cell_px) {
     CU(cudaGetLastError());
     return MDKM_OK;
   }
-  const int cgrid = grid_for(h, (n_cells + kThreads - 1) / kThreads, 16);
+  const int cgrid = grid_for(h, (n_cells + 7) / 8, 16);  // one warp per cell
   raster_cell_count_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_counts.p);
   long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
   mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
@@ -605,7 +609,9 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   if (!h->summary_ok) {
     const int span = prof_begin(h, MDKM_PHASE_BUILD, h->n);
     if (h->runs_ok && h->raster_w > 0 && h->opt_raster_mirror) {
-      OK(build_mirror_raster(h, k <= 16 && h->raster_w % 16 == 0 ? 16 : 8));
+      int cell_px = k <= 16 && h->raster_w % 16 == 0 ? 16 : 8;
+      if (h->opt_cell_px == 8 || (h->opt_cell_px == 16 && h->raster_w % 16 == 0)) cell_px = h->opt_cell_px;
+      OK(build_mirror_raster(h, cell_px));
     } else {
       OK(build_mirror(h, k <= 16 ? 16 : 8));
       group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
@@ -1018,6 +1024,16 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
       h->opt_raster_mirror = value != 0;
       h->summary_ok = false;
       return MDKM_OK;
+    case MDKM_OPT_CELL_PX:
+      if (value != 0 && value != 8 && value != 16) return fail(h, MDKM_ERR_INVALID, "cell width must be 0 (automatic), 8 or 16 pixels");
+      h->opt_cell_px = (int)value;
+      h->summary_ok = false;
+      return MDKM_OK;
+    case MDKM_OPT_CELL_ROWS:
+      if (value < 0 || value > 64) return fail(h, MDKM_ERR_INVALID, "rows per cell must be in [0, 64]");
+      h->opt_cell_rows = (int)value;
+      h->summary_ok = false;
+      return MDKM_OK;
     default:
       return fail(h, MDKM_ERR_INVALID, "unknown option %d", option);
   }
@@ -1195,6 +1211,12 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
     if (cloud_out) OK(ensure(h, h->cloud_aos, (size_t)pix_count * 3));
     CU(cudaMemsetAsync(h->slab_totals.p, 0, 8, h->stream));
     CU(cudaMemsetAsync(h->tile_status.p, 0, ((size_t)n_tiles + 1) * 8, h->stream));  // look-back words + ticket
+    {  // bounding box of the cloud, collected by the fused pass
+      OK(ensure(h, h->uscratch, 16));
+      CU(cudaMemsetAsync(h->uscratch.p + 4, 0xff, 12, h->stream));
+      CU(cudaMemsetAsync(h->uscratch.p + 7, 0, 12, h->stream));
+      up.minmax = h->uscratch.p + 4;
+    }
     // copies of this call must not start before earlier work on the compute stream that still
     // reads the staging buffer has finished
     if (from_host) {
@@ -1282,7 +1304,10 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
         h->d2h_pending = true;
       }
     }
+    unsigned int lookback_fault = 0;
+    OK(small_d2h(h, &lookback_fault, up.ticket + 1, 4));
     OK(sync_small(h));
+    if (lookback_fault) return fail(h, MDKM_ERR_CUDA, "unprojection: a tile's look-back timed out");
     n_out = h->h_slab_totals[n_slabs];
     h->seg_off[n_seg] = n_out;
     h->seg_whole = (pix_begin % HW) == 0 && (pix_count % HW) == 0;
@@ -1304,7 +1329,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   OK(zero_tail(h));
   h->have_points = true;
   h->frame_ok = false;
-  OK(compute_frame(h));
+  OK(compute_frame(h, /*minmax_ready=*/pix_count > 0));
   if (n_points_out) *n_points_out = n_out;
   return MDKM_OK;
 }

@@ -276,46 +276,54 @@ __device__ __forceinline__ unsigned int raster_run(const RasterGeom& g, int cxi,
   return __ldg(g.run_src + j1) - src;
 }
 
-// points per cell (one thread per cell)
+// points per cell.  One WARP per cell, one lane per (day, row) run: the loads of a cell's runs
+// are in flight together instead of one after the other.
 __global__ void __launch_bounds__(kThreads) raster_cell_count_kernel(const RasterGeom g, unsigned int* counts) {
-  const int n_cells = g.gx * g.gy;
-  for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_cells; c += gridDim.x * kThreads) {
-    const int cyi = c / g.gx, cxi = c - cyi * g.gx;  // consecutive threads: consecutive bins of a row
+  const int n_cells = g.gx * g.gy, per_cell = g.nd * g.rpc, lane = threadIdx.x & 31;
+  const int stride = gridDim.x * (kThreads / 32);
+  for (int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < n_cells; c += stride) {
+    const int cyi = c / g.gx, cxi = c - cyi * g.gx;
     unsigned int tot = 0;
-    for (int dd = 0; dd < g.nd; ++dd)
-      for (int ry = 0; ry < g.rpc; ++ry) {
-        unsigned int src;
-        tot += raster_run(g, cxi, cyi, dd, ry, src);
-      }
-    counts[raster_cell_index(g, cxi, cyi)] = tot;
+    for (int e = lane; e < per_cell; e += 32) {
+      unsigned int src;
+      tot += raster_run(g, cxi, cyi, e / g.rpc, e % g.rpc, src);
+    }
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    if (lane == 0) counts[raster_cell_index(g, cxi, cyi)] = tot;
   }
 }
 
 // The runs in destination order: entry (cell, day, row) = (first mirror slot, first cloud index);
 // an entry's length is the next entry's slot minus its own (entry n_entries closes the list).
-// gfirst[g] = the entry that holds mirror slot 128 g.
+// gfirst[g] = the entry that holds mirror slot 128 g.  One warp per cell, as above.
 __global__ void __launch_bounds__(kThreads) raster_runs_kernel(const RasterGeom g, const long long* cell_offsets,
                                                                long long n, uint2* druns, unsigned int* gfirst) {
-  const int n_cells = g.gx * g.gy;
-  const int per_cell = g.nd * g.rpc;
-  for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_cells; c += gridDim.x * kThreads) {
+  const int n_cells = g.gx * g.gy, per_cell = g.nd * g.rpc, lane = threadIdx.x & 31;
+  const int stride = gridDim.x * (kThreads / 32);
+  for (int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < n_cells; c += stride) {
     const int cyi = c / g.gx, cxi = c - cyi * g.gx;
     const int lin = raster_cell_index(g, cxi, cyi);
-    unsigned int dst = (unsigned int)cell_offsets[lin];
+    unsigned int carry = (unsigned int)cell_offsets[lin];
     uint2* out = druns + (size_t)lin * per_cell;
-    for (int dd = 0; dd < g.nd; ++dd)
-      for (int ry = 0; ry < g.rpc; ++ry) {
-        unsigned int src;
-        const unsigned int cnt = raster_run(g, cxi, cyi, dd, ry, src);
-        const int e = dd * g.rpc + ry;
-        out[e] = make_uint2(dst, src);
-        if (cnt) {  // a run is shorter than a group: it holds at most one group start
-          const unsigned long long gs = ((unsigned long long)dst + (kGroup - 1)) / kGroup;
-          if (gs * kGroup < (unsigned long long)dst + cnt) gfirst[gs] = (unsigned int)((size_t)lin * per_cell + e);
-        }
-        dst += cnt;
+    for (int e0 = 0; e0 < per_cell; e0 += 32) {  // warp-uniform trip count
+      const int e = e0 + lane;
+      unsigned int src = 0u;
+      const unsigned int cnt = e < per_cell ? raster_run(g, cxi, cyi, e / g.rpc, e % g.rpc, src) : 0u;
+      unsigned int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-    if (c == 0) druns[(size_t)n_cells * per_cell] = make_uint2((unsigned int)n, 0u);
+      const unsigned int dst = carry + incl - cnt;
+      if (e < per_cell) out[e] = make_uint2(dst, src);
+      if (cnt) {  // a run is shorter than a group: it holds at most one group start
+        const unsigned long long gs = ((unsigned long long)dst + (kGroup - 1)) / kGroup;
+        if (gs * kGroup < (unsigned long long)dst + cnt) gfirst[gs] = (unsigned int)((size_t)lin * per_cell + e);
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (c == 0 && lane == 0) druns[(size_t)n_cells * per_cell] = make_uint2((unsigned int)n, 0u);
   }
 }
 

@@ -48,8 +48,10 @@ struct UnprojParams {
   // fused pass: this launch handles tiles [tile_begin, tile_end) of the range
   long long tile_begin, tile_end;
   unsigned long long* status;  // [n_tiles] look-back words, zeroed once per mdkm_unproject
-  unsigned int* ticket;        // zeroed before every launch
+  unsigned int* ticket;        // zeroed before every launch; ticket[1] = fault flag (look-back timed out)
   long long* total_out;        // points of all tiles up to tile_end - 1 (running total of the range)
+  unsigned int* minmax;        // optional [6]: ordered-uint min x,y,z / max x,y,z of the points written
+                               // (pre-filled with 0xffffffff / 0 by the host, as minmax_kernel expects)
 };
 
 // One pixel: height and validity (plugin.py:151-152).  dtype 2 is the reference's own
@@ -136,6 +138,10 @@ __device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i
   }
 }
 
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -148,14 +154,21 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // Points of all tiles before tile t (warp-collective).  Flag and value share one 64-bit word, so
 // no fence is involved: a word is either not there yet, an aggregate or a prefix.
 __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* status, long long t, unsigned int cnt,
-                                                            int lane) {
+                                                            int lane, unsigned int* fault) {
   if (lane == 0 && t > 0) st_status(status + t, kStAggregate | cnt);
   unsigned long long excl = 0ull;
+  const long long t0 = clock64();
   for (long long j = t - 1;; j -= 32) {
     const long long jj = j - lane;
     unsigned long long s;
     unsigned int first_pre, invalid;
     do {
+      // bounded wait (about 4 s): every predecessor holds an earlier ticket, so it is running or done
+      // and this never triggers; if it ever did, a flagged failure beats a hung GPU
+      if (clock64() - t0 > (8ll << 30)) {
+        if (lane == 0) atomicExch(fault, 1u);
+        return 0ull;
+      }
       s = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
       const unsigned int flag = (unsigned int)(s >> 62);
       const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
@@ -182,6 +195,9 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* wz = s_z[warp];
   unsigned short* wix = s_ix[warp];
+  // bounding box of the points this warp writes (the frame of the cloud needs it: no extra pass)
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
   while (true) {
     long long t = 0;
     if (lane == 0) t = p.tile_begin + (long long)atomicAdd(p.ticket, 1u);
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
     }
     __syncwarp();
     // 4. points of all earlier tiles
-    const unsigned long long excl = tile_lookback(p.status, t, cnt, lane);
+    const unsigned long long excl = tile_lookback(p.status, t, cnt, lane, p.ticket + 1);
     if (lane == 0) {
       if ((t & (kChunk / kTile - 1)) == 0) p.chunk_offsets[t / (kChunk / kTile)] = (long long)excl;
       if (t == p.tile_end - 1 && p.total_out) *p.total_out = (long long)(excl + cnt);
@@ -230,19 +246,28 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
         if (o < p.pix_count) p.run_src[o >> 3] = (unsigned int)(excl + head[r]);
       }
     }
-    // 5. contiguous runs of x, y, z
+    // 5. contiguous runs of x, y, z.  Position of the tile's first pixel once per tile (64-bit);
+    // per point only 32-bit arithmetic, and no division at all for rasters at least a tile wide
     const long long gp0 = p.pix_begin + pix0;
     const long long day0 = gp0 / p.HW;
     const long long rem0 = gp0 - day0 * p.HW;
+    const unsigned int row0 = (unsigned int)(rem0 / p.W);
+    const unsigned int col0 = (unsigned int)(rem0 - (long long)row0 * p.W);
+    const unsigned int W = (unsigned int)p.W, H = (unsigned int)p.H;
     for (unsigned int i = lane; i < cnt; i += 32) {
-      long long rem = rem0 + wix[i];
+      unsigned int col = col0 + wix[i], row = row0;
       int dcur = (int)day0;
-      while (rem >= p.HW) {  // a tile may run into the next day(s)
-        rem -= p.HW;
+      if (W >= (unsigned int)kTile) {  // at most one row boundary inside the tile
+        if (col >= W) { col -= W; ++row; }
+      } else {
+        const unsigned int q = col / W;
+        col -= q * W;
+        row += q;
+      }
+      while (row >= H) {  // a tile may run into the next day(s)
+        row -= H;
         ++dcur;
       }
-      const int row = (int)(rem / p.W);
-      const int col = (int)(rem - (long long)row * p.W);
       float zz = wz[i];
       if (p.planes) {
         // plugin.py:171: height_rel = dot(P - center, normal)
@@ -250,11 +275,26 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
         zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)zz - pl[2]) * pl[5]);
       }
       float* dst = p.pts + pt_off((long long)excl + i);
-      dst[0] = (float)col;
-      dst[kGroup] = (float)row;
+      const float fx = (float)col, fy = (float)row;
+      dst[0] = fx;
+      dst[kGroup] = fy;
       dst[2 * kGroup] = zz;
+      mn[0] = fminf(mn[0], fx); mx[0] = fmaxf(mx[0], fx);
+      mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
+      mn[2] = fminf(mn[2], zz); mx[2] = fmaxf(mx[2], zz);
     }
     __syncwarp();  // the staging arrays are reused by the next tile
+  }
+  if (p.minmax) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const unsigned int a = __reduce_min_sync(0xffffffffu, f2ord(mn[d]));
+      const unsigned int b = __reduce_max_sync(0xffffffffu, f2ord(mx[d]));
+      if (lane == 0) {
+        atomicMin(&p.minmax[d], a);
+        atomicMax(&p.minmax[3 + d], b);
+      }
+    }
   }
 }
 
@@ -372,10 +412,6 @@ __global__ void plane_solve_kernel(const double* partials, int n_blocks, int W, 
 // Cloud statistics: per-dimension min / max (frame + error bound) and first/second moments
 // about the frame origin (mean, and var(X) for sklearn's tolerance, _kmeans.py:285-293).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int f2ord(float f) {
-  const unsigned int b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
 __host__ __device__ inline float ord2f(unsigned int u) {
   const unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
 #ifdef __CUDA_ARCH__

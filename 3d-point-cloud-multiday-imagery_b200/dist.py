@@ -81,3 +81,27 @@ def init_engine_comm(engine, rank: int, world: int, p2p: bool = True):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             engine.p2p_close()
+
+
+def torch_gather_mappings(engine):
+    """The collective ``api._is_same_clustering`` needs on a sharded engine, over
+    torch.distributed: all-gather of the ranks' label maps (k int64 + a flag).  None when
+    torch.distributed does not span the engine's ranks (the test is then skipped)."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == engine.n_ranks):
+        return None
+    backend = dist.get_backend()
+    dev = torch.device("cuda", engine.device) if backend == "nccl" else torch.device("cpu")
+
+    def gather(mapping, ok):
+        mine = torch.tensor(list(mapping) + [1 if ok else 0], dtype=torch.int64, device=dev)
+        parts = [torch.zeros_like(mine) for _ in range(engine.n_ranks)]
+        dist.all_gather(parts, mine)
+        parts = [p.cpu().numpy() for p in parts]
+        return [p[:-1] for p in parts], [bool(p[-1]) for p in parts]
+
+    return gather

@@ -247,8 +247,8 @@ class Engine:
         gtiff3 = raster_layout == "gtiff3"
         if gtiff3:
             # the reference's 5-out-F.tif pixels: [..., 3] float32 = height, unused, final_defined
-            if is_i16 or len(shape) < 3 or shape[-1] != 3:
-                raise ValueError("raster_layout='gtiff3' needs float32 [D,H,W,3] (or [H,W,3])")
+            if is_i16 or shape[-1] != 3 or (stack_shape is None and len(shape) < 3):
+                raise ValueError("raster_layout='gtiff3' needs float32 [D,H,W,3] (or [H,W,3]; [n,3] with stack_shape)")
             shape = tuple(shape[:-1])
         elif raster_layout is not None:
             raise ValueError("raster_layout must be None or 'gtiff3'")

@@ -99,8 +99,10 @@ void* mdkm_get_stream(const mdkm_handle* h);
  * streaming path bench.py reports its HBM fraction for); results are identical either way. */
 /* MDKM_OPT_RASTER_MIRROR (default 1): 0 makes clouds that came from mdkm_unproject use the generic
  * (histogram + scatter) build of the tile-ordered mirror instead of the run-table build; a test
- * hook, the results are identical. */
-enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2 };
+ * hook, the results are identical.
+ * MDKM_OPT_CELL_PX (0 = automatic, 8 or 16) / MDKM_OPT_CELL_ROWS (0 = automatic, 1..64): width and
+ * height, in pixels, of the x-y cells the mirror of a raster cloud is ordered by (tuning). */
+enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2, MDKM_OPT_CELL_PX = 3, MDKM_OPT_CELL_ROWS = 4 };
 int mdkm_set_option(mdkm_handle* h, int option, long long value);
 
 /* ---- K1: unprojection ----------------------------------------------------------------

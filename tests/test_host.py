@@ -103,6 +103,114 @@ def test_same_clustering_helper():
     assert not api._is_same_clustering(a, np.array([2, 2, 0, 1, 0, 0]), 3)
 
 
+def test_same_clustering_over_shards():
+    """sklearn's permutation test (_k_means_common.pyx:314-330) decided from per-shard label maps."""
+    api = importlib.import_module(PKG + ".api")
+    rs = np.random.RandomState(0)
+    k = 7
+    l1 = rs.randint(0, k, size=1000)
+    perm = rs.permutation(k)
+    for l2, want in ((perm[l1], True), (np.where(np.arange(1000) == 777, (perm[l1] + 1) % k, perm[l1]), False)):
+        assert api._is_same_clustering(l1, l2, k) is want
+        for cuts in ([0, 1000], [0, 400, 1000], [0, 10, 10, 600, 1000]):  # shards, one of them empty
+            maps, oks = zip(*[api._label_mapping(l1[a:b], l2[a:b], k) for a, b in zip(cuts, cuts[1:])])
+            assert api._merge_label_mappings(list(maps), list(oks)) is want, cuts
+    # consistent inside every shard, but the shards disagree about the image of label 0
+    a = api._label_mapping(np.array([0, 0, 1]), np.array([2, 2, 0]), 3)
+    b = api._label_mapping(np.array([0, 2]), np.array([1, 1]), 3)
+    assert a[1] and b[1] and not api._merge_label_mappings([a[0], b[0]], [True, True])
+
+
+class _FakeRankEngine:
+    """Host-only stand-in for Engine inside a DeviceGroup: numpy unprojection, labels = rank."""
+
+    def __init__(self, device):
+        self.device, self.p2p, self.closed = device, False, False
+        self.rank, self.n_ranks = 0, 1
+
+    def init_comm(self, world, rank, uid):
+        self.n_ranks, self.rank, self.uid = world, rank, uid
+
+    def p2p_handle(self):
+        return b"\0" * 64
+
+    def p2p_buffer(self):
+        return 0x1000 + self.device
+
+    def p2p_open_ptrs(self, ptrs):
+        self.ptrs, self.p2p = list(ptrs), True
+        return True
+
+    def p2p_close(self):
+        self.p2p = False
+
+    def unproject(self, hm, mask, *, stack_shape, pix_begin, **kw):
+        D, H, W = stack_shape
+        ok = np.isfinite(hm) & (np.abs(hm) <= 144)
+        if mask is not None:
+            ok &= mask.astype(bool)
+        idx = np.flatnonzero(ok) + pix_begin
+        self.P = np.stack([idx % W, (idx // W) % H, hm[ok]], axis=1).astype(np.float32)
+        days = idx // (H * W)
+        d0, d1 = pix_begin // (H * W), (pix_begin + hm.shape[0] - 1) // (H * W)
+        self.seg = np.concatenate([[0], np.cumsum([(days == d).sum() for d in range(d0, d1 + 1)])]).astype(np.int64)
+        return self.P.shape[0]
+
+    @property
+    def segment_offsets(self):
+        return self.seg
+
+    def get_cloud(self, napari_order=True, out=None, wait=True):
+        out[...] = self.P[:, ::-1] if napari_order else self.P
+
+    def wait(self):
+        pass
+
+    def close(self):
+        self.closed = True
+
+
+def test_device_group_shards_and_assembles_in_reference_order():
+    grp_mod = importlib.import_module(PKG + ".group")
+    pkg = importlib.import_module(PKG)
+    from oracle import unproject_oracle as UO
+
+    D, H, W = 3, 20, 16
+    hm = pkg.make_stack(D, H, W, seed=2, n_buildings=3).numpy()
+    P = UO.unproject_stack(hm)
+    fakes = []
+
+    def factory(dev):
+        fakes.append(_FakeRankEngine(dev))
+        return fakes[-1]
+
+    with grp_mod.DeviceGroup([5, 6, 7, 8], engine_factory=factory, make_unique_id=lambda: b"u" * 128) as grp:
+        assert grp.world == 4 and grp.p2p
+        engs = sorted(fakes, key=lambda f: f.rank)
+        assert [f.rank for f in engs] == [0, 1, 2, 3] and all(f.uid == b"u" * 128 and f.n_ranks == 4 for f in engs)
+        assert all(f.ptrs == [0x1005, 0x1006, 0x1007, 0x1008] for f in engs)
+
+        def run(eng, labels_out):
+            labels_out[...] = eng.rank
+            return {"rank": eng.rank}
+
+        res, labels, cloud, hn, extra = grp.fuse(hm, run_kmeans=run)
+        assert res == {"rank": 0} and hn is None
+        np.testing.assert_array_equal(cloud.astype(np.float64), UO.to_napari_points(P))  # np.where order, days merged
+        assert sum(extra["shard_points"]) == P.shape[0] and labels.shape == (P.shape[0],)
+        assert np.all(np.diff(labels) >= 0) and set(labels.tolist()) == {0, 1, 2, 3}      # rank order == point order
+        per_day = [UO.unproject_stack(hm[d:d + 1]).shape[0] for d in range(D)]
+        np.testing.assert_array_equal(extra["segment_offsets"], np.concatenate([[0], np.cumsum(per_day)]))
+        # row-band shards: 60 rows over 4 ranks = 15 rows each, cut on row boundaries
+        assert [len(np.unique(f.P[:, 1])) <= 16 for f in engs]
+        # an error on one rank surfaces, the other ranks still finish their call
+        with pytest.raises(RuntimeError, match="boom"):
+            grp.map(lambda r: (_ for _ in ()).throw(RuntimeError("boom")) if r == 2 else r)
+    assert all(f.closed for f in fakes)
+    with pytest.raises(ValueError):
+        grp_mod.DeviceGroup([0, 0], engine_factory=factory, make_unique_id=lambda: b"")
+
+
 def test_to_layers_matches_reference_layer_contract():
     api = importlib.import_module(PKG + ".api")
     res = api.FusionResult(labels=np.array([0, 1], dtype=np.int32), centroids=np.array([[1.0, 2, 3], [4, 5, 6]]),
