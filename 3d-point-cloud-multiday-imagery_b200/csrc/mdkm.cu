@@ -526,9 +526,10 @@ int build_mirror_raster(mdkm_handle* h, int cell_px) {
   // counted (cyclically) from the first one
   g.yshift = g.n_rows >= g.H ? 0 : (int)(g.row0 % g.H);
   g.yext = (int)std::min<long long>(g.n_rows, g.H);
-  // rows per cell: about 256 points per cell, counting every day that covers a row
+  // rows per cell: about 400 points per cell (measured optimum of fit time over cell shapes, configs 2-4),
+  // counting every day that covers a row
   const double per_row = (double)h->n / (double)g.yext / (double)g.gx;  // points per cell and row of y
-  g.rpc = (int)std::max(1.0, std::min(64.0, nearbyint(256.0 / std::max(per_row, 1e-9))));
+  g.rpc = (int)std::max(1.0, std::min(64.0, nearbyint(400.0 / std::max(per_row, 1e-9))));
   if (h->opt_cell_rows > 0) g.rpc = std::min(64, h->opt_cell_rows);
   g.gy = (g.yext + g.rpc - 1) / g.rpc;
   const long long n_cells = (long long)g.gx * g.gy;
@@ -1149,8 +1150,10 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   OK(alloc_points(h, pix_count));
   const long long n_chunks = (pix_count + kChunk - 1) / kChunk;
   const long long n_tiles = (pix_count + kTile - 1) / kTile;
+  constexpr int kSuper = kThreads / 32;  // warp tiles per super-tile (one CTA, one look-back)
+  const long long n_super = (n_tiles + kSuper - 1) / kSuper;
   OK(ensure(h, h->chunk_offsets, (size_t)n_chunks + 2));
-  OK(ensure(h, h->tile_status, (size_t)n_tiles + 2));  // [n_tiles] status words, then the ticket counter
+  OK(ensure(h, h->tile_status, (size_t)n_super + 2));  // [n_super] status words, then the ticket counter
   UnprojParams up{};
   up.hm = d_hm; up.mask = d_mask;
   up.pix_begin = pix_begin; up.pix_count = pix_count; up.HW = HW; up.W = W; up.H = H;
@@ -1159,7 +1162,8 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   up.scale = hm_scale; up.max_abs = max_abs;
   up.chunk_offsets = h->chunk_offsets.p;
   up.status = h->tile_status.p;
-  up.ticket = reinterpret_cast<unsigned int*>(h->tile_status.p + n_tiles);
+  up.ticket = reinterpret_cast<unsigned int*>(h->tile_status.p + n_super);
+  CU(cudaFuncSetAttribute(unproject_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
   up.pts = h->pts.p;
   up.planes = nullptr;
   up.day0 = (int)(pix_begin / HW);
@@ -1210,7 +1214,7 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
     }
     if (cloud_out) OK(ensure(h, h->cloud_aos, (size_t)pix_count * 3));
     CU(cudaMemsetAsync(h->slab_totals.p, 0, 8, h->stream));
-    CU(cudaMemsetAsync(h->tile_status.p, 0, ((size_t)n_tiles + 1) * 8, h->stream));  // look-back words + ticket
+    CU(cudaMemsetAsync(h->tile_status.p, 0, ((size_t)n_super + 1) * 8, h->stream));  // look-back words + ticket
     {  // bounding box of the cloud, collected by the fused pass
       OK(ensure(h, h->uscratch, 16));
       CU(cudaMemsetAsync(h->uscratch.p + 4, 0xff, 12, h->stream));
@@ -1252,7 +1256,8 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
         ready = days_solved * HW;
         up.planes = h->planes.p;
       }
-      const long long c_end = (s == n_slabs - 1) ? n_chunks : ready / kChunk;
+      // (whole super-tiles = an even number of chunks, except at the very end of the range)
+      const long long c_end = (s == n_slabs - 1) ? n_chunks : (ready / kChunk) / (kSuper * kTile / kChunk) * (kSuper * kTile / kChunk);
       if (c_end > done_chunks) {
         up.chunk_begin = done_chunks;
         up.chunk_end = c_end;
@@ -1261,10 +1266,10 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
         up.tile_end = std::min<long long>(c_end * (kChunk / kTile), n_tiles);
         up.total_out = h->slab_totals.p + s + 1;
         const long long nt = up.tile_end - up.tile_begin;
-        const int g = grid_for(h, (nt + 7) / 8, 4);  // 48 KB of staging per CTA: four CTAs per SM
+        const int g = grid_for(h, (nt + kSuper - 1) / kSuper, 4);  // 48 KB of staging per CTA
         if (s > 0) CU(cudaMemsetAsync(up.ticket, 0, 4, h->stream));
         const int span = prof_begin(h, MDKM_PHASE_UNPROJECT, std::min<long long>(c_end * kChunk, pix_count) - done_chunks * kChunk);
-        unproject_fused_kernel<<<g, kThreads, 0, h->stream>>>(up);
+        unproject_fused_kernel<<<g, kThreads, kFusedSmem, h->stream>>>(up);
         prof_end(h, span);
         ++h->launches;
         if (cloud_out) {

@@ -12,7 +12,8 @@
 // points of all earlier tiles by a decoupled look-back over per-tile status words (tiles are
 // handed out by a ticket counter, so every predecessor of a running tile is itself running or
 // done), and writes x, y, z as contiguous runs at offset + rank -- the output order is exactly
-// np.where's.  Offsets at every kChunk = 4096 pixels are kept for the day boundaries.
+// np.where's.  Offsets at every kChunk = 4096 pixels are kept for the day boundaries.  (The
+// look-back works on super-tiles of eight warp tiles -- one CTA -- see unproject_fused_kernel.)
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -21,6 +22,7 @@ namespace mdkm {
 
 constexpr int kChunk = 4096;
 constexpr int kTile = 1024;  // pixels per warp tile of the fused pass
+constexpr int kFusedSmem = (kThreads / 32) * kTile * 6;  // dynamic shared memory of unproject_fused_kernel
 // per-tile status word of the decoupled look-back: flag in the two top bits, count below
 constexpr unsigned long long kStAggregate = 1ull << 62;  // value = valid pixels of this tile
 constexpr unsigned long long kStPrefix = 2ull << 62;     // value = valid pixels up to and including this tile
@@ -47,7 +49,7 @@ struct UnprojParams {
                           // local pixel 8 i (the raster mirror build reads runs of pixels from it, mirror.cuh)
   // fused pass: this launch handles tiles [tile_begin, tile_end) of the range
   long long tile_begin, tile_end;
-  unsigned long long* status;  // [n_tiles] look-back words, zeroed once per mdkm_unproject
+  unsigned long long* status;  // [n_tiles / 8] look-back words (one per super-tile), zeroed once per mdkm_unproject
   unsigned int* ticket;        // zeroed before every launch; ticket[1] = fault flag (look-back timed out)
   long long* total_out;        // points of all tiles up to tile_end - 1 (running total of the range)
   unsigned int* minmax;        // optional [6]: ordered-uint min x,y,z / max x,y,z of the points written
@@ -188,30 +190,40 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* 
   return excl;
 }
 
+// One CTA takes a super-tile of kThreads / 32 = 8 consecutive warp tiles per ticket: the warps rank
+// their tiles independently, ONE look-back per super-tile (by warp 0) yields the CTA's offset, and
+// the warps' own offsets follow from the eight counts in shared memory.  The look-back depth is
+// bounded by the number of resident CTAs (a few hundred), not by the number of resident warps.
 __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojParams p) {
   constexpr int kWarps = kThreads / 32;
-  __shared__ float s_z[kWarps][kTile];
-  __shared__ unsigned short s_ix[kWarps][kTile];
+  extern __shared__ __align__(16) unsigned char s_stage[];  // kFusedSmem bytes: z [8][1024] f32, pixel [8][1024] u16
+  __shared__ unsigned int s_cnt[kWarps];
+  __shared__ unsigned long long s_base;
+  __shared__ long long s_super;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* wz = s_z[warp];
-  unsigned short* wix = s_ix[warp];
+  float* wz = reinterpret_cast<float*>(s_stage) + warp * kTile;
+  unsigned short* wix = reinterpret_cast<unsigned short*>(s_stage + kWarps * kTile * 4) + warp * kTile;
   // bounding box of the points this warp writes (the frame of the cloud needs it: no extra pass)
   float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
   float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  const long long super_begin = p.tile_begin / kWarps;  // (launch boundaries are whole super-tiles)
   while (true) {
-    long long t = 0;
-    if (lane == 0) t = p.tile_begin + (long long)atomicAdd(p.ticket, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= p.tile_end) break;
+    if (threadIdx.x == 0) s_super = super_begin + (long long)atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const long long sup = s_super;
+    if (sup * kWarps >= p.tile_end) break;  // CTA-uniform
+    const long long t = sup * kWarps + warp;
+    const bool active = t < p.tile_end;     // warp-uniform
     const long long pix0 = t * kTile;  // local index of the tile's first pixel
+    unsigned int cnt = 0;
+    unsigned int head[kTile / 128];  // rank of this lane's first pixel of round r
+    if (active) {
     // 1. the tile's pixels: 8 x 16 B per lane in flight
     float hv[kTile / 128][4];
     unsigned int vb[kTile / 128];
 #pragma unroll
     for (int r = 0; r < kTile / 128; ++r) load_heights4(p, pix0 + r * 128 + lane * 4, hv[r], vb[r]);
     // 2. rank of every valid pixel inside the tile, in pixel order, and 3. park (z, pixel) there
-    unsigned int cnt = 0;
-    unsigned int head[kTile / 128];  // rank of this lane's first pixel of round r
 #pragma unroll
     for (int r = 0; r < kTile / 128; ++r) {
       const unsigned int lt = (1u << lane) - 1u;
@@ -232,9 +244,19 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
         }
       cnt += total;
     }
-    __syncwarp();
-    // 4. points of all earlier tiles
-    const unsigned long long excl = tile_lookback(p.status, t, cnt, lane, p.ticket + 1);
+    }  // active
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    // 4. points of all earlier super-tiles (one look-back per CTA), then of the earlier warps
+    if (warp == 0) {
+      const unsigned int agg = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_cnt[lane] : 0u);
+      const unsigned long long base = tile_lookback(p.status, sup, agg, lane, p.ticket + 1);
+      if (lane == 0) s_base = base;
+    }
+    __syncthreads();
+    if (!active) continue;
+    unsigned long long excl = s_base;
+    for (int w = 0; w < warp; ++w) excl += s_cnt[w];
     if (lane == 0) {
       if ((t & (kChunk / kTile - 1)) == 0) p.chunk_offsets[t / (kChunk / kTile)] = (long long)excl;
       if (t == p.tile_end - 1 && p.total_out) *p.total_out = (long long)(excl + cnt);
@@ -283,7 +305,6 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
       mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
       mn[2] = fminf(mn[2], zz); mx[2] = fmaxf(mx[2], zz);
     }
-    __syncwarp();  // the staging arrays are reused by the next tile
   }
   if (p.minmax) {
 #pragma unroll
