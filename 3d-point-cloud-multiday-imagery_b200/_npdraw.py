@@ -12,9 +12,9 @@ of adding the double ``1.0 / n`` to zero ``i + 1`` times, one IEEE addition afte
 billion points that array does not fit the host (and would take seconds to build), but the
 sequence has a closed form: while the running sum stays inside one binade its unit in the last
 place is fixed, so every addition advances it by the SAME amount (after at most one step that
-settles a round-half-to-even tie).  The sum is therefore piecewise linear in the index with one
-piece per binade -- about thirty pieces between ``1/n`` and ``1`` -- found here with exact integer
-arithmetic; a binary search over the index then reproduces ``searchsorted`` bit for bit.
+settles a round-half-to-even tie).  The sum is therefore piecewise linear in the index with a
+few pieces per binade -- under a hundred between ``1/n`` and ``1`` -- found here with exact
+rational arithmetic; a binary search over the index then reproduces ``searchsorted`` bit for bit.
 
 Host-side arithmetic only (no device work): this is the random-number bookkeeping scikit-learn
 does on the host as well.  Checked against numpy itself in ``tests/test_host.py``.
@@ -50,38 +50,38 @@ class UniformCdf:
         self.last = self.at(self.n - 1)
 
     def _build(self):
-        p = self.p
-        n = self.n
-        i, s = 0, p  # cdf[0] = 0.0 + p = p
-        while i < n:
-            # one plain IEEE step at a time until the increment has settled inside this binade
+        p, n = self.p, self.n
+        i, s = 0, p  # cdf[0] = 0.0 + p
+        while True:
+            self._add_piece(i, Fraction(s), Fraction(0))  # the element itself
+            if i >= n - 1:
+                return
+            # Two plain IEEE steps first: a step that enters a binade, and the one after it, may
+            # differ from the steady increment (change of ulp; round-half-to-even settling).
             s1 = s + p
-            d = Fraction(s1) - Fraction(s)
-            self._add_piece(i, Fraction(s), d)
-            if i + 1 >= n:
-                break
-            m, e = np.frexp(s1)  # s1 = m * 2**e, 0.5 <= m < 1: the binade of s1 ends at 2**e
+            self._add_piece(i + 1, Fraction(s1), Fraction(0))
+            if i + 1 >= n - 1:
+                return
             s2 = s1 + p
-            d2 = Fraction(s2) - Fraction(s1)
-            top = Fraction(2) ** int(e)
-            if Fraction(s2) >= top or d2 <= 0:
-                # the next step leaves the binade (or the sum has stopped moving): keep stepping singly
-                i, s = i + 1, s1
-                if d2 <= 0:  # p is below half an ulp of the sum: every later element equals s1
-                    self._add_piece(i, Fraction(s1), Fraction(0))
-                    break
+            s3 = s2 + p
+            d = Fraction(s3) - Fraction(s2)
+            e2, e3 = np.frexp(s2)[1], np.frexp(s3)[1]
+            if d == 0:
+                # 1/n has dropped below half an ulp of the sum: it no longer moves
+                self._add_piece(i + 2, Fraction(s2), Fraction(0))
+                return
+            if e3 != e2:
+                i, s = i + 2, s2  # s3 is already in the next binade: keep stepping singly
                 continue
-            # inside the binade of s1 the increment is d2 from s1 on (a tie, if any, settled in the step s -> s1)
-            k = int((top - Fraction(s1)) / d2)  # largest k with s1 + k * d2 <= top ...
-            while Fraction(s1) + k * d2 >= top:  # ... strictly below the top of the binade
-                k -= 1
-            k = max(1, min(k, n - 1 - (i + 1)))
-            if n - 1 - (i + 1) <= 0:
-                i, s = i + 1, s1
-                continue
-            self._add_piece(i + 1, Fraction(s1), d2)
-            i = i + 1 + k
-            s = _float_exact(Fraction(s1) + k * d2)
+            # From s2 on, inside its binade (fixed ulp), every addition advances the sum by d:
+            # largest k with s2 + k * d strictly below the top of the binade
+            top = Fraction(2) ** int(e2)
+            k = -((Fraction(s2) - top) // d)  # ceil((top - s2) / d)
+            k = int(k) - 1
+            k = max(1, min(k, n - 1 - (i + 2)))
+            self._add_piece(i + 2, Fraction(s2), d)
+            i = i + 2 + k
+            s = _float_exact(Fraction(s2) + k * d)
 
     def _add_piece(self, i0: int, s0: Fraction, d: Fraction):
         if self._i0 and self._i0[-1] == i0:

@@ -107,20 +107,11 @@ def _is_same_clustering(l1, l2, k, gather=None) -> bool:
 
 def _random_seeds(rs, n: int, k: int) -> np.ndarray:
     """``random_state.choice(n, size=k, replace=False, p=w / w.sum())`` with unit weights
-    (sklearn/_kmeans.py:1014-1021).  numpy draws differently when ``p`` is given, so the very
-    call is made while the probability vector fits comfortably in host memory; beyond that
-    the same rejection scheme is run on ``floor(u * n)`` (identical up to FP rounding of the
-    cdf)."""
-    if n <= (1 << 27):
-        return rs.choice(n, size=k, replace=False, p=np.full(n, 1.0 / n))
-    found = np.empty(0, dtype=np.int64)
-    while found.size < k:
-        x = rs.random_sample(k - found.size)
-        new = np.minimum((x * n).astype(np.int64), n - 1)
-        new = new[np.sort(np.unique(new, return_index=True)[1])]
-        new = new[~np.isin(new, found)]
-        found = np.concatenate([found, new])
-    return found[:k]
+    (sklearn/_kmeans.py:1014-1021), reproduced bit for bit for any ``n`` without the n-sized
+    probability vector (``_npdraw.py``)."""
+    from ._npdraw import choice_uniform_without_replacement
+
+    return choice_uniform_without_replacement(rs, n, k)
 
 
 def _run_kmeans(eng: Engine, *, n_clusters, init, n_init, max_iter, tol, random_state, want_labels=True,

@@ -441,16 +441,11 @@ class Engine:
         n = self.n_points_global
         n_local_trials = 2 + int(np.log(k))
         # RandomState.choice(n, p=w/w.sum()) (sklearn/_kmeans.py:228): one uniform draw inverted
-        # through cdf = cumsum(p)/cdf[-1] with searchsorted(side="right") -- reproduced exactly
-        # while the cdf fits in host memory, floor(u*n) beyond that.
-        u = float(random_state.random_sample())
-        if n <= (1 << 26):
-            cdf = np.cumsum(np.full(n, 1.0 / n))
-            cdf /= cdf[-1]
-            first = int(min(np.searchsorted(cdf, u, side="right"), n - 1))
-            del cdf
-        else:
-            first = min(int(u * n), n - 1)
+        # through cdf = cumsum(p)/cdf[-1] with searchsorted(side="right") -- reproduced bit for bit
+        # for any n from the closed form of that running sum (_npdraw.py), without an n-sized array.
+        from ._npdraw import choice_uniform
+
+        first = choice_uniform(random_state, n)
         rv = np.ascontiguousarray(
             [random_state.uniform(size=n_local_trials) for _ in range(k - 1)], dtype=np.float64
         ).reshape(max(k - 1, 0), n_local_trials)

@@ -103,6 +103,40 @@ def test_same_clustering_helper():
     assert not api._is_same_clustering(a, np.array([2, 2, 0, 1, 0, 0]), 3)
 
 
+def test_uniform_choice_matches_numpy_bit_for_bit():
+    """scikit-learn's first k-means++ index and its init="random" seeds are numpy
+    RandomState.choice(n, p=uniform) draws (sklearn/_kmeans.py:228, 1014-1021); _npdraw.py
+    reproduces them from a closed form of np.cumsum(np.full(n, 1/n)), for any n."""
+    nd = importlib.import_module(PKG + "._npdraw")
+    rs = np.random.RandomState(0)
+    ns = list(range(1, 130)) + [int(v) for v in rs.randint(130, 2_000_000, size=25)] + [2 ** 20, 2 ** 20 + 1, 3 * 2 ** 19, 10 ** 6]
+    for n in ns:
+        c = nd.UniformCdf(n)
+        ref = np.cumsum(np.full(n, 1.0 / n))
+        idx = np.unique(np.concatenate([np.arange(min(n, 40)), rs.randint(0, n, size=120), [n - 1]]))
+        np.testing.assert_array_equal(np.array([c.at(int(i)) for i in idx]), ref[idx], err_msg=str(n))
+        refn = ref / ref[-1]
+        us = np.concatenate([rs.random_sample(30), refn[idx[:15]], np.nextafter(refn[idx[:15]], 0), np.nextafter(refn[idx[:15]], 2)])
+        us = us[us < 1.0]
+        np.testing.assert_array_equal(np.array([c.search(float(u)) for u in us]), refn.searchsorted(us, side="right"),
+                                      err_msg=str(n))
+    for n, k, seed in [(1000, 17, 0), (50, 50, 1), (12345, 300, 2), (7, 3, 3), (10, 10, 4), (300000, 1024, 5)]:
+        want = np.random.RandomState(seed).choice(n, size=k, replace=False, p=np.full(n, 1.0 / n))
+        got = nd.choice_uniform_without_replacement(np.random.RandomState(seed), n, k)
+        np.testing.assert_array_equal(got, want)
+        assert nd.choice_uniform(np.random.RandomState(seed), n) == np.random.RandomState(seed).choice(n, p=np.full(n, 1.0 / n))
+    # BASELINE config sizes (no n-sized array anywhere): sane and monotone
+    for n in (1342177280, 503316480):
+        c = nd.UniformCdf(n)
+        assert len(c._i0) < 200 and abs(c.last - 1.0) < 1e-6
+        probe = [0, 1, 2, n // 3, n // 2, n - 2, n - 1]
+        vals = [c.at(i) for i in probe]
+        assert vals == sorted(vals) and vals[0] == 1.0 / n
+        for u in (0.0, 0.25, 0.5, 0.999999):
+            j = c.search(u)
+            assert abs(j - u * n) <= 1e-6 * n + 2 and (j == 0 or c.at(j - 1) / c.last <= u < c.at(j) / c.last)
+
+
 def test_same_clustering_over_shards():
     """sklearn's permutation test (_k_means_common.pyx:314-330) decided from per-shard label maps."""
     api = importlib.import_module(PKG + ".api")
