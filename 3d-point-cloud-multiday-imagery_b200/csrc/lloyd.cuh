@@ -1,6 +1,6 @@
 // Lloyd k-means kernels for d = 3 on sm_100a.
 //
-//   lloyd_step_kernel   ONE kernel per Lloyd iteration (cooperative launch):
+//   lloyd_step_kernel   ONE kernel per BATCH of Lloyd iterations (cooperative launch); per iteration:
 //                         pass 1  classification: whole 128-point groups settled from their
 //                                 cached summaries (box + fixed-point sums), no point read;
 //                         --      grid barrier;
@@ -12,7 +12,8 @@
 //                         tail    the last CTA completes the sums (peer exchange over NVLink
 //                                 when there are several ranks) and runs the centroid update,
 //                                 centre shift, convergence test and next centroid table
-//                                 (_k_means_common.pyx:274-311, _kmeans.py:721-738).
+//                                 (_k_means_common.pyx:274-311, _kmeans.py:721-738);
+//                         --      grid barrier, next iteration (same launch).
 //   lloyd_update_kernel the update alone (NCCL exchange path, and after a relocation)
 //   lloyd_final_kernel  labels in the reference's point order from the final centroids +
 //                       inertia + int32 labels (_kmeans.py:742-756, _k_means_common.pyx:94-124)
@@ -130,6 +131,15 @@ __device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int
 // It sits on the critical path of every iteration, so global round trips are kept to one: a
 // thread fetches the accumulator row and the old centroid of its cluster together, and the
 // five block-wide reductions share one pair of barriers.
+// 32 bytes of a table row / 4 or 8 bytes of the status block through L2: inside a multi-iteration
+// launch they were written by other SMs in an earlier iteration, and this SM's L1 may still hold
+// what it read before that.
+__device__ __forceinline__ double4 ldcg_d4(const double4* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   DevStatus* st = u.st;
   __shared__ double s_red[5][kThreads / 32];
@@ -150,7 +160,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   if (have0) {
     a0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4));
     b0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4 + 2));
-    old0 = exact[tid];
+    old0 = ldcg_d4(&exact[tid]);
   }
   // empty clusters and the heaviest cluster (np.argmax: first maximum)
   int my_empty = 0;
@@ -188,7 +198,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   for (int j = tid; j < u.kpad; j += kThreads) {
     if (j < u.k) {
       const bool first = j == tid;
-      const double4 old = first ? old0 : exact[j];
+      const double4 old = first ? old0 : ldcg_d4(&exact[j]);
       ulonglong2 a = first ? a0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4));
       ulonglong2 b = first ? b0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4 + 2));
       double cx, cy, cz;
@@ -264,15 +274,15 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
     st->n_changed = n_changed;
     st->n_empty = n_empty;
     st->paused = 0;
-    const int it = st->iter + 1;
+    const int it = __ldcg(&st->iter) + 1;
     st->iter = it;
-    if (!st->first && n_changed == 0ull) {  // _kmeans.py:721-726
+    if (!__ldcg(&st->first) && n_changed == 0ull) {  // _kmeans.py:721-726
       st->strict = 1;
       st->done = 1;
-    } else if (shift2 <= st->tol) {         // _kmeans.py:729-738
+    } else if (shift2 <= __ldcg(&st->tol)) {         // _kmeans.py:729-738
       st->done = 1;
     }
-    if (it >= st->max_iter) st->done = 1;
+    if (it >= __ldcg(&st->max_iter)) st->done = 1;
     st->first = 0;
   }
 }
@@ -284,12 +294,9 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
 
 
 
-// exact centroid row through the read-only path (two 16 B loads)
-__device__ __forceinline__ double4 ld_c64(const double4* p) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
+// exact centroid row (two 16 B loads through L2: the table is rewritten between the iterations of
+// one launch, so neither L1 nor the non-coherent path may serve it)
+__device__ __forceinline__ double4 ld_c64(const double4* p) { return ldcg_d4(p); }
 
 // Can centroid `row` beat the reference centroid `ref` anywhere in the box?  Both rows are in
 // the expanded form (-2c', ||c'||^2), so d_row(x) - d_ref(x) = a.w + a.xyz . x is LINEAR in x
@@ -319,6 +326,7 @@ struct StepParams {
   int ignore_status;          // 1: test hook (run even when done/paused)
   int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
                               //    (NVLink, no host, no NCCL) and runs the centroid update
+  int n_iters;                // Lloyd iterations this launch runs (fuse_update only; 1 otherwise)
   int settle;                 // 0: measurement mode, no group is settled from its summary --
                               //    every point goes through the per-point pass (MDKM_OPT_SETTLE_GROUPS)
   const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
@@ -411,7 +419,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
   if (g < n_groups) {
     const float4* src = reinterpret_cast<const float4*>(gsum + g);
     a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-    prev = first_iter ? -1 : glabel[g];
+    prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
   }
   for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // CTA-uniform trip count
     const bool valid = g < n_groups;
@@ -488,7 +496,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
     if (g < n_groups) {
       const float4* src = reinterpret_cast<const float4*>(gsum + g);
       a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-      prev = first_iter ? -1 : glabel[g];
+      prev = first_iter ? -1 : __ldcg(glabel + g);
     }
     // cached sums, one round per distinct label in the warp (usually one)
     unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
@@ -958,7 +966,7 @@ constexpr int kStages = 3;
 __device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned long long* acc, int n,
                                                    DevStatus* st) {
   const int tid = threadIdx.x, R = px.n_ranks;
-  const unsigned long long epoch = st->epoch + 1ull;
+  const unsigned long long epoch = __ldcg(&st->epoch) + 1ull;
   const int par = (int)(epoch & 1ull);
   const unsigned int tag = (unsigned int)epoch;
   // packets of (parity, source rank): 2 * slot of them, 8 bytes each
@@ -1001,7 +1009,6 @@ __host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGro
 
 template <typename LabT, bool kPrivate, int kChunks>
 __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParams p) {
-  if (!p.ignore_status && (p.st->done | p.st->paused)) return;
   constexpr int kWarps = kThreads / 32;
   constexpr int kStageB = stage_bytes<LabT>();
   constexpr int kLabB = kGroup * (int)sizeof(LabT);
@@ -1016,18 +1023,32 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __shared__ unsigned int s_changed;
   __shared__ unsigned int s_refined;
   __shared__ unsigned short s_cand[kWarps * kCandCap];
+  __shared__ bool s_is_last;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  const int n_slices = kPrivate ? kWarps : 1;
+  unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
+  // bucket index of the centroids (k >= kBucketMinK), behind the accumulator slices
+  const uint32_t bkt_bytes = (uint32_t)bucket_bytes(p.k, p.kpad);
+  unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_acc_all + (size_t)(kPrivate ? kWarps : 1) * p.kpad * 4);
+  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
+  const FrameF f = p.f;
+  const int n_launch_iters = p.fuse_update ? max(1, p.n_iters) : 1;
+
+  // ONE launch runs a whole batch of Lloyd iterations: between two of them the grid only waits
+  // (grid barrier) for the CTA that completes the sums and writes the next centroid table -- no
+  // kernel boundary, no launch gap.  Everything another SM may have written in an earlier
+  // iteration of this launch is read through L2 (TMA, ld.cg, volatile), never through L1.
+  for (int launch_it = 0; launch_it < n_launch_iters; ++launch_it) {
+  if (!p.ignore_status && (__ldcg(&p.st->done) | __ldcg(&p.st->paused))) return;  // the same for every CTA
 #ifdef MDKM_TIMING
   if (blockIdx.x == 0 && tid == 0) {
     p.st->t_start = globaltimer_ns();
     p.st->t_update_done = 0ull;
   }
 #endif
-  const int n_slices = kPrivate ? kWarps : 1;
-  unsigned long long* s_acc = s_acc_all + (kPrivate ? warp * p.kpad * 4 : 0);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     for (int i = 0; i < kWarps * kStages; ++i) mbar_init(&s_gbar[i], 1);
@@ -1041,19 +1062,14 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
   }
   __syncthreads();
-  // bucket index of the centroids (k >= kBucketMinK), behind the accumulator slices
-  const uint32_t bkt_bytes = (uint32_t)bucket_bytes(p.k, p.kpad);
-  unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_acc_all + (size_t)(kPrivate ? kWarps : 1) * p.kpad * 4);
   if (tid == 0) {
     // centroid rows (and their bucket index): global -> shared through the TMA unit (1-D bulk copies)
     mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
     if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
   }
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
-  const float thresh = p.st->thresh;
-  const bool first_iter = p.st->first != 0;
-  const FrameF f = p.f;
+  const float thresh = __ldcg(&p.st->thresh);
+  const bool first_iter = __ldcg(&p.st->first) != 0;
 
   // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
@@ -1276,7 +1292,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   }
   if (!p.fuse_update) return;
   // ---- fused tail: the last CTA to get here owns the complete local sums ----------------
-  __shared__ bool s_is_last;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -1288,21 +1303,25 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
 #endif
   }
   __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  if (tid == 0) {
-    p.st->ticket = 0u;
-    if (p.work_count) {
-      p.st->work_sum += (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
-      *p.work_count = 0;
+  if (s_is_last) {  // CTA-uniform
+    __threadfence();
+    if (tid == 0) {
+      p.st->ticket = 0u;
+      if (p.work_count) {
+        p.st->work_sum = __ldcg(&p.st->work_sum) + (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
+        *p.work_count = 0;
+      }
     }
-  }
-  if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
-  lloyd_update_body(p.upd);
+    if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
+    lloyd_update_body(p.upd);
 #ifdef MDKM_TIMING
-  __syncthreads();
-  if (tid == 0) p.st->t_classify_start = globaltimer_ns();  // (field reused: end of the update)
+    __syncthreads();
+    if (tid == 0) p.st->t_classify_start = globaltimer_ns();  // (field reused: end of the update)
 #endif
+  }
+  // the next iteration of this launch starts when the new table and status are in place
+  if (launch_it + 1 < n_launch_iters) grid_barrier(p.grid_bar, &p.st->xchg_timeout);
+  }  // iterations of this launch
 }
 
 // Builds the centroid table from K x 3 float64 centroids in ORIGINAL coordinates.

@@ -651,7 +651,7 @@ UpdateParams make_update_params(mdkm_handle* h, const KmBuffers& kb, int allow_p
 // or ranks whose exchange buffers are mapped into each other (NVLink, CUDA IPC).
 bool can_fuse(const mdkm_handle* h) { return h->n_ranks == 1 || h->p2p_ok; }
 
-int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0) {
+int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0, int n_iters = 1) {
   StepParams sp{};
   sp.pts = h->tpts.p; sp.n = h->n;  // the tile-ordered mirror; labels / summaries / worklist follow its order
   sp.labels = h->labels.p;
@@ -662,6 +662,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.k = kb.k; sp.kpad = kb.kpad;
   sp.ignore_status = ignore_status;
   sp.fuse_update = fuse_update;
+  sp.n_iters = fuse_update ? n_iters : 1;
   sp.settle = h->opt_settle;
   if (fuse_update) {
     sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
@@ -1426,10 +1427,11 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       // profiling: one event pair around the batch's step kernels (back-to-back launches, so
       // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
       const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
-      for (int b = 0; b < nb; ++b) {
-        if (can_fuse(h)) {
-          OK(launch_step(h, kb, 0, /*fuse_update=*/1));
-        } else {
+      if (can_fuse(h)) {
+        // the whole batch is ONE launch: the kernel iterates, separated by grid barriers only
+        OK(launch_step(h, kb, 0, /*fuse_update=*/1, nb));
+      } else {
+        for (int b = 0; b < nb; ++b) {
           OK(launch_step(h, kb, 0));
           OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
           OK(launch_update(h, kb, /*allow_pause=*/1, 0));
