@@ -518,6 +518,37 @@ def run_mine(args):
                "d2h_bytes_per_step": int(res.labels.nbytes + res.centroids.nbytes + res.fused_cloud.nbytes),
                "ms_per_step": 1e3 * float(wall.item()) / args.steps,
                "returns": "labels int32[N], centroids f64[K,3], fused cloud f32[N,3]"}
+        # what the host allows: the same byte counts as raw pinned copies, both directions at once,
+        # all ranks together (no kernels at all) -- the end-to-end call cannot be faster than this
+        d2h_n, h2d_n = e2e["d2h_bytes_per_step"], e2e["h2d_bytes_per_step"]
+        fl_src = torch.empty(d2h_n, dtype=torch.uint8, device=dev)
+        fl_dst = torch.empty(d2h_n, dtype=torch.uint8, pin_memory=True)
+        fl_in = torch.empty(hm_host.numel() * 4, dtype=torch.uint8, device=dev)
+        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def raw_copies():
+            with torch.cuda.stream(s_a):
+                fl_dst.copy_(fl_src, non_blocking=True)
+            with torch.cuda.stream(s_b):
+                fl_in.copy_(hm_host.view(torch.uint8).reshape(-1), non_blocking=True)
+            s_a.synchronize()
+            s_b.synchronize()
+
+        raw_copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            raw_copies()
+        barrier()
+        fl = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        e2e["floor_ms_raw_pinned_copies"] = 1e3 * float(fl.item())
+        e2e["floor_note"] = (f"{d2h_n} B device->host + {h2d_n} B host->device per rank as plain pinned cudaMemcpyAsync, "
+                             f"all {world} rank(s) at once, no kernels: the host's PCIe / memory path sets this")
+        e2e["ms_over_floor"] = e2e["ms_per_step"] / e2e["floor_ms_raw_pinned_copies"]
+        del fl_src, fl_dst, fl_in
+        torch.cuda.empty_cache()
 
     # ---- brute force: a cloud on which neither settling nor candidate pruning can help -----------
     # (x, y squeezed to a thousandth of the z range: every x-y tile of the mirror spans all the
