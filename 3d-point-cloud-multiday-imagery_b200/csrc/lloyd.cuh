@@ -155,9 +155,8 @@ __device__ __forceinline__ void build_safe_radii(unsigned char* table, int k, in
 // It sits on the critical path of every iteration, so global round trips are kept to one: a
 // thread fetches the accumulator row and the old centroid of its cluster together, and the
 // five block-wide reductions share one pair of barriers.
-// 32 bytes of a table row / 4 or 8 bytes of the status block through L2: inside a multi-iteration
-// launch they were written by other SMs in an earlier iteration, and this SM's L1 may still hold
-// what it read before that.
+// 32 bytes of a table row through L2 (the update step runs in whichever CTA finishes last; what it
+// reads was written by another SM one iteration earlier).
 __device__ __forceinline__ double4 ldcg_d4(const double4* p) {
   const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
   const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
@@ -319,9 +318,14 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
 
 
 
-// exact centroid row (two 16 B loads through L2: the table is rewritten between the iterations of
-// one launch, so neither L1 nor the non-coherent path may serve it)
-__device__ __forceinline__ double4 ld_c64(const double4* p) { return ldcg_d4(p); }
+// exact centroid row: two plain 16 B loads (L1-cached).  NOT the non-coherent path (__ldg): the
+// table is rewritten between the iterations of one launch; plain loads are made coherent again by
+// the acquire fence of the grid barrier that separates the iterations.
+__device__ __forceinline__ double4 ld_c64(const double4* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
 
 // Can centroid `row` beat the reference centroid `ref` anywhere in the box?  Both rows are in
 // the expanded form (-2c', ||c'||^2), so d_row(x) - d_ref(x) = a.w + a.xyz . x is LINEAR in x
@@ -587,6 +591,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, int* timeout
         *timeout_flag = 1;
         break;
       }
+      __nanosleep(32);  // hundreds of CTAs poll one word while the last one is still working
     }
     __threadfence();
   }

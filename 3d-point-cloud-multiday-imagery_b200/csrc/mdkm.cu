@@ -95,6 +95,7 @@ struct mdkm_handle {
   DevBuf<unsigned int> gfirst;
   int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
   int opt_cell_px = 0, opt_cell_rows = 0;  // MDKM_OPT_CELL_PX / MDKM_OPT_CELL_ROWS (0 = automatic)
+  int opt_iters_per_launch = kBatch;       // MDKM_OPT_ITERS_PER_LAUNCH
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -1027,6 +1028,10 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
       h->opt_raster_mirror = value != 0;
       h->summary_ok = false;
       return MDKM_OK;
+    case MDKM_OPT_ITERS_PER_LAUNCH:
+      if (value < 1 || value > kBatch) return fail(h, MDKM_ERR_INVALID, "iterations per launch must be in [1, %d]", kBatch);
+      h->opt_iters_per_launch = (int)value;
+      return MDKM_OK;
     case MDKM_OPT_CELL_PX:
       if (value != 0 && value != 8 && value != 16) return fail(h, MDKM_ERR_INVALID, "cell width must be 0 (automatic), 8 or 16 pixels");
       h->opt_cell_px = (int)value;
@@ -1429,8 +1434,10 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
       const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
       if (can_fuse(h)) {
-        // the whole batch is ONE launch: the kernel iterates, separated by grid barriers only
-        OK(launch_step(h, kb, 0, /*fuse_update=*/1, nb));
+        // the batch in launches of up to opt_iters_per_launch iterations each: inside a launch
+        // the kernel iterates, separated by grid barriers only
+        for (int b = 0; b < nb; b += h->opt_iters_per_launch)
+          OK(launch_step(h, kb, 0, /*fuse_update=*/1, std::min(h->opt_iters_per_launch, nb - b)));
       } else {
         for (int b = 0; b < nb; ++b) {
           OK(launch_step(h, kb, 0));

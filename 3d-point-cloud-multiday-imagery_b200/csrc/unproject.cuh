@@ -196,7 +196,7 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* 
 // bounded by the number of resident CTAs (a few hundred), not by the number of resident warps.
 __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojParams p) {
   constexpr int kWarps = kThreads / 32;
-  extern __shared__ __align__(16) unsigned char s_stage[];  // kFusedSmem bytes: z [8][1024] f32, pixel [8][1024] u16
+  extern __shared__ __align__(16) unsigned char s_stage[];  // kFusedSmem bytes: heights [8][1024] f32 (pixel order), valid-pixel lists [8][1024] u16
   __shared__ unsigned int s_cnt[kWarps];
   __shared__ unsigned long long s_base;
   __shared__ long long s_super;
@@ -218,30 +218,33 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
     unsigned int cnt = 0;
     unsigned int head[kTile / 128];  // rank of this lane's first pixel of round r
     if (active) {
-    // 1. the tile's pixels: 8 x 16 B per lane in flight
-    float hv[kTile / 128][4];
-    unsigned int vb[kTile / 128];
+    // 1. the tile's pixels: 8 x 16 B per lane in flight; the heights are parked in shared memory
+    // in PIXEL order at once (the registers are free again), only the validity bits stay
+    unsigned int vbits = 0;  // 4 bits per round
 #pragma unroll
-    for (int r = 0; r < kTile / 128; ++r) load_heights4(p, pix0 + r * 128 + lane * 4, hv[r], vb[r]);
-    // 2. rank of every valid pixel inside the tile, in pixel order, and 3. park (z, pixel) there
+    for (int r = 0; r < kTile / 128; ++r) {
+      float hv[4];
+      unsigned int vb;
+      load_heights4(p, pix0 + r * 128 + lane * 4, hv, vb);
+      *reinterpret_cast<float4*>(wz + r * 128 + lane * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      vbits |= vb << (4 * r);
+    }
+    // 2. rank of every valid pixel inside the tile, in pixel order: the list of valid pixels
 #pragma unroll
     for (int r = 0; r < kTile / 128; ++r) {
       const unsigned int lt = (1u << lane) - 1u;
+      const unsigned int vb = (vbits >> (4 * r)) & 0xfu;
       unsigned int before = 0, total = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const unsigned int m = __ballot_sync(0xffffffffu, (vb[r] >> e) & 1u);
+        const unsigned int m = __ballot_sync(0xffffffffu, (vb >> e) & 1u);
         before += __popc(m & lt);
         total += __popc(m);
       }
       head[r] = cnt + before;
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if ((vb[r] >> e) & 1u) {
-          const unsigned int idx = head[r] + __popc(vb[r] & ((1u << e) - 1u));
-          wz[idx] = hv[r][e];
-          wix[idx] = (unsigned short)(r * 128 + lane * 4 + e);
-        }
+        if ((vb >> e) & 1u) wix[head[r] + __popc(vb & ((1u << e) - 1u))] = (unsigned short)(r * 128 + lane * 4 + e);
       cnt += total;
     }
     }  // active
@@ -277,7 +280,8 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
     const unsigned int col0 = (unsigned int)(rem0 - (long long)row0 * p.W);
     const unsigned int W = (unsigned int)p.W, H = (unsigned int)p.H;
     for (unsigned int i = lane; i < cnt; i += 32) {
-      unsigned int col = col0 + wix[i], row = row0;
+      const unsigned int pix = wix[i];
+      unsigned int col = col0 + pix, row = row0;
       int dcur = (int)day0;
       if (W >= (unsigned int)kTile) {  // at most one row boundary inside the tile
         if (col >= W) { col -= W; ++row; }
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
         row -= H;
         ++dcur;
       }
-      float zz = wz[i];
+      float zz = wz[pix];
       if (p.planes) {
         // plugin.py:171: height_rel = dot(P - center, normal)
         const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
