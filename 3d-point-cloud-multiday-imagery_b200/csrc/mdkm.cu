@@ -95,7 +95,6 @@ struct mdkm_handle {
   DevBuf<unsigned int> gfirst;
   int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
   int opt_cell_px = 0, opt_cell_rows = 0;  // MDKM_OPT_CELL_PX / MDKM_OPT_CELL_ROWS (0 = automatic)
-  int opt_iters_per_launch = kBatch;       // MDKM_OPT_ITERS_PER_LAUNCH
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -653,7 +652,7 @@ UpdateParams make_update_params(mdkm_handle* h, const KmBuffers& kb, int allow_p
 // or ranks whose exchange buffers are mapped into each other (NVLink, CUDA IPC).
 bool can_fuse(const mdkm_handle* h) { return h->n_ranks == 1 || h->p2p_ok; }
 
-int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0, int n_iters = 1) {
+int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse_update = 0) {
   StepParams sp{};
   sp.pts = h->tpts.p; sp.n = h->n;  // the tile-ordered mirror; labels / summaries / worklist follow its order
   sp.labels = h->labels.p;
@@ -664,7 +663,6 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.k = kb.k; sp.kpad = kb.kpad;
   sp.ignore_status = ignore_status;
   sp.fuse_update = fuse_update;
-  sp.n_iters = fuse_update ? n_iters : 1;
   sp.settle = h->opt_settle;
   if (fuse_update) {
     sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
@@ -1027,10 +1025,6 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
     case MDKM_OPT_RASTER_MIRROR:
       h->opt_raster_mirror = value != 0;
       h->summary_ok = false;
-      return MDKM_OK;
-    case MDKM_OPT_ITERS_PER_LAUNCH:
-      if (value < 1 || value > kBatch) return fail(h, MDKM_ERR_INVALID, "iterations per launch must be in [1, %d]", kBatch);
-      h->opt_iters_per_launch = (int)value;
       return MDKM_OK;
     case MDKM_OPT_CELL_PX:
       if (value != 0 && value != 8 && value != 16) return fail(h, MDKM_ERR_INVALID, "cell width must be 0 (automatic), 8 or 16 pixels");
@@ -1433,13 +1427,10 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
       // profiling: one event pair around the batch's step kernels (back-to-back launches, so
       // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
       const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
-      if (can_fuse(h)) {
-        // the batch in launches of up to opt_iters_per_launch iterations each: inside a launch
-        // the kernel iterates, separated by grid barriers only
-        for (int b = 0; b < nb; b += h->opt_iters_per_launch)
-          OK(launch_step(h, kb, 0, /*fuse_update=*/1, std::min(h->opt_iters_per_launch, nb - b)));
-      } else {
-        for (int b = 0; b < nb; ++b) {
+      for (int b = 0; b < nb; ++b) {
+        if (can_fuse(h)) {
+          OK(launch_step(h, kb, 0, /*fuse_update=*/1));
+        } else {
           OK(launch_step(h, kb, 0));
           OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
           OK(launch_update(h, kb, /*allow_pause=*/1, 0));

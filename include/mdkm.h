@@ -101,11 +101,8 @@ void* mdkm_get_stream(const mdkm_handle* h);
  * (histogram + scatter) build of the tile-ordered mirror instead of the run-table build; a test
  * hook, the results are identical.
  * MDKM_OPT_CELL_PX (0 = automatic, 8 or 16) / MDKM_OPT_CELL_ROWS (0 = automatic, 1..64): width and
- * height, in pixels, of the x-y cells the mirror of a raster cloud is ordered by (tuning).
- * MDKM_OPT_ITERS_PER_LAUNCH (1..10): Lloyd iterations one launch of the step kernel runs before it
- * returns (the iterations of a launch are separated by grid barriers instead of kernel boundaries). */
-enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2, MDKM_OPT_CELL_PX = 3, MDKM_OPT_CELL_ROWS = 4,
-       MDKM_OPT_ITERS_PER_LAUNCH = 5 };
+ * height, in pixels, of the x-y cells the mirror of a raster cloud is ordered by (tuning). */
+enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2, MDKM_OPT_CELL_PX = 3, MDKM_OPT_CELL_ROWS = 4 };
 int mdkm_set_option(mdkm_handle* h, int option, long long value);
 
 /* ---- K1: unprojection ----------------------------------------------------------------
