@@ -109,12 +109,7 @@ __host__ __device__ inline size_t bucket_bytes(int k, int kpad) {
   const int g = bucket_g(k);
   return (sizeof(BucketHdr) + (size_t)(g * g + 1 + kpad) * 2 + 15) & ~(size_t)15;
 }
-// Fourth section, used by the classification pass for k < kBucketMinK: one float per centroid,
-// a quarter of the squared distance to its nearest other centroid, rounded down ("safe radius":
-// a box that lies inside that ball around c_L cannot hold a point of any other cluster).
-__host__ __device__ inline size_t safe_offset(int k, int kpad) { return (size_t)kpad * 48 + bucket_bytes(k, kpad); }
-__host__ __device__ inline size_t safe_bytes(int kpad) { return ((size_t)kpad * 4 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t table_bytes(int k, int kpad) { return safe_offset(k, kpad) + safe_bytes(kpad); }
+__host__ __device__ inline size_t table_bytes(int k, int kpad) { return (size_t)kpad * 48 + bucket_bytes(k, kpad); }
 __device__ __forceinline__ int bucket_coord(float c, float h, float inv, int g) {
   return min(g - 1, max(0, (int)floorf((c + h) * inv)));
 }

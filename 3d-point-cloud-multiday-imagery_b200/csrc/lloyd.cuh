@@ -125,30 +125,6 @@ __device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int
   for (int j = k + tid; j < kpad; j += blockDim.x) perm[j] = 0;
 }
 
-// Safe radii of the k centroids (common.cuh), for the classification pass with few centroids.
-// Executed by all threads of ONE CTA right after that CTA wrote the exact rows.
-__device__ __forceinline__ void build_safe_radii(unsigned char* table, int k, int kpad) {
-  if (k >= kBucketMinK) return;
-  const double4* exact = reinterpret_cast<const double4*>(table + exact_offset(kpad));
-  float* safe = reinterpret_cast<float*>(table + safe_offset(k, kpad));
-  __syncthreads();  // the exact rows of this CTA's other threads are visible
-  for (int j = threadIdx.x; j < kpad; j += blockDim.x) {
-    double m = 1.0 / 0.0;
-    if (j < k) {
-      const double4 a = exact[j];
-      for (int i = 0; i < k; ++i) {
-        const double4 b = exact[i];
-        const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        m = (i != j && d2 < m) ? d2 : m;
-      }
-    } else {
-      m = 0.0;
-    }
-    safe[j] = __double2float_rd(0.25 * m * (1.0 - 1e-6));
-  }
-}
-
 // Executed by all kThreads threads of ONE CTA: the stand-alone update kernel, or the last CTA
 // of a fused step kernel.  Reads the accumulators through L2 (they were produced by atomics).
 // It sits on the critical path of every iteration, so global round trips are kept to one: a
@@ -264,7 +240,6 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   }
   const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);
   build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
-  build_safe_radii(u.table, u.k, u.kpad);
   // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
   for (int o = 16; o > 0; o >>= 1) {
     shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
@@ -435,8 +410,7 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
                                                 bool first_iter, unsigned long long* s_acc, int* s_list,
-                                                const unsigned char* s_bkt, const float* s_safe, unsigned int& n_chg,
-                                                bool settle) {
+                                                const unsigned char* s_bkt, unsigned int& n_chg, bool settle) {
   const int tid = threadIdx.x, lane = tid & 31;
   int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
   int w_count = 0;                                                         // warp-uniform
@@ -472,19 +446,13 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
         // few centroids: all of them, with the box as centre + half-widths -- the minimum of the
         // (linear) gap over the box is its value at the centre minus sum_d |a_d| h_d.  The
         // rounding of this form is covered by a margin of 6 * thresh instead of 4 * thresh.
-        // Cheap first: if the farthest corner of the box is inside the safe ball of c_ref (half the
-        // way to its nearest rival, with the margin to spare), every point of the box is nearer to
-        // c_ref than to any other centroid by more than the margin -- no loop over the centroids.
-        const float ccx = -0.5f * rr.x, ccy = -0.5f * rr.y, ccz = -0.5f * rr.z;
-        const float ex = fmaxf(fabsf(lo0 - ccx), fabsf(hi0 - ccx)), ey = fmaxf(fabsf(lo1 - ccy), fabsf(hi1 - ccy)),
-                    ez = fmaxf(fabsf(lo2 - ccz), fabsf(hi2 - ccz));
-        const float far2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-        const bool inside = fmaf(far2, 1.00001f, 2.0f * margin) <= s_safe[ref];
-        ncand = inside ? 1 : 0;
         const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
         const float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
         const float lim = fmaf(mx, rr.x, fmaf(my, rr.y, fmaf(mz, rr.z, rr.w))) + 1.5f * margin;
-        for (int j = 0; j < (inside ? 0 : k); ++j) {
+        // (A cheap "box inside the safe ball of c_ref" test in front of this loop was measured: one
+        // thread per group means a warp skips the loop only when all its 32 groups pass, and the
+        // extra test cost more than those warps saved -- not kept.)
+        for (int j = 0; j < k; ++j) {
           const float4 r = s_fast[j];
           const float dj = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
           const float reach = fmaf(fabsf(r.x - rr.x), hx, fmaf(fabsf(r.y - rr.y), hy, fabsf(r.z - rr.z) * hz));
@@ -1091,9 +1059,6 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // bucket index of the centroids (k >= kBucketMinK), behind the accumulator slices
   const uint32_t bkt_bytes = (uint32_t)bucket_bytes(p.k, p.kpad);
   unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_acc_all + (size_t)(kPrivate ? kWarps : 1) * p.kpad * 4);
-  // safe radii of the centroids (k < kBucketMinK), behind the bucket index
-  const uint32_t safe_b = p.k < kBucketMinK ? (uint32_t)safe_bytes(p.kpad) : 0u;
-  float* s_safe = reinterpret_cast<float*>(s_bkt + bkt_bytes);
   const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
   const FrameF f = p.f;
   // (One launch = one Lloyd iteration.  Running a batch of iterations inside one launch, with a
@@ -1121,10 +1086,9 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __syncthreads();
   if (tid == 0) {
     // centroid rows (and their bucket index): global -> shared through the TMA unit (1-D bulk copies)
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes + safe_b);
+    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
     if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
-    if (safe_b) tma_load_1d(s_safe, p.table + safe_offset(p.k, p.kpad), safe_b, &s_bar);
   }
   const float thresh = __ldcg(&p.st->thresh);
   const bool first_iter = __ldcg(&p.st->first) != 0;
@@ -1140,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
   classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
                                   4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
-                                  bkt_bytes ? s_bkt : nullptr, s_safe, n_chg, p.settle != 0);
+                                  bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
@@ -1421,7 +1385,6 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
     u.st->thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
   }
   build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
-  build_safe_radii(u.table, u.k, u.kpad);
 }
 
 // Reads the table back as K x 3 float64 centroids in original coordinates.

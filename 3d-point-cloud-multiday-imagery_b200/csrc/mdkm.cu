@@ -574,8 +574,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   const size_t kp32 = (size_t)((kb.kpad + 31) & ~31);
   kb.priv = !kb.wide && kb.kpad <= 128;
   const size_t ring = (size_t)(kThreads / 32) * kStages * (kb.wide ? stage_bytes<unsigned short>() : stage_bytes<unsigned char>());
-  kb.step_smem = kp32 * 16 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1) + bucket_bytes(k, kb.kpad) +
-                 safe_bytes(kb.kpad);
+  kb.step_smem = kp32 * 16 + ring + (size_t)kb.kpad * 32 * (kb.priv ? (kThreads / 32) : 1) + bucket_bytes(k, kb.kpad);
   kb.final_smem = kp32 * 16 + bucket_bytes(k, kb.kpad);
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
