@@ -332,6 +332,7 @@ struct StepParams {
   int settle;                 // 0: measurement mode, no group is settled from its summary --
                               //    every point goes through the per-point pass (MDKM_OPT_SETTLE_GROUPS)
   const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
+  const void* ssum;           // SuperSummary per kSuper groups (defined with the classification pass)
   int* worklist;              // groups the classification pass could not settle
   int* work_count;            // number of entries; cleared by the tail of the kernel
   int* glabel;                // per group: the label that owns its whole box, else -1
@@ -401,12 +402,119 @@ __global__ void __launch_bounds__(kThreads) group_summary_kernel(const float* pt
 // global worklist (staged per warp in shared memory).
 constexpr int kClassifyList = 2048;  // shared-memory staging of the worklist (entries per CTA)
 
+// The same summaries one level up: kSuper consecutive groups (1024 points) with the union of
+// their boxes and the sum of their sums.  Most of the cloud lies deep inside one cluster, so the
+// classification pass first tests whole super-groups -- one box test settles eight groups -- and
+// only looks at the groups of the super-groups that fail.  Static per cloud and frame, like the
+// group summaries.
+constexpr int kSuper = 8;
+struct __align__(16) SuperSummary {
+  float lo[3], hi[3];  // union of the groups' boxes
+  int n;               // points (kSuper * kGroup unless the cloud ends inside)
+  int pad;
+  long long q[3];      // sum of the fixed-point coordinates
+  long long pad2;
+};
+static_assert(sizeof(SuperSummary) == 64, "SuperSummary is read as four 16-byte words");
+
+__global__ void __launch_bounds__(kThreads) super_summary_kernel(const GroupSummary* __restrict__ gsum, int n_groups,
+                                                                 SuperSummary* __restrict__ out) {
+  const int n_super = (n_groups + kSuper - 1) / kSuper;
+  for (int sg = blockIdx.x * kThreads + threadIdx.x; sg < n_super; sg += gridDim.x * kThreads) {
+    SuperSummary s;
+    for (int d = 0; d < 3; ++d) {
+      s.lo[d] = __int_as_float(0x7f800000);
+      s.hi[d] = __int_as_float(0xff800000);
+      s.q[d] = 0;
+    }
+    s.n = 0; s.pad = 0; s.pad2 = 0;
+    for (int i = 0; i < kSuper; ++i) {
+      const int g = sg * kSuper + i;
+      if (g >= n_groups) break;
+      const GroupSummary gs = gsum[g];
+      for (int d = 0; d < 3; ++d) {
+        s.lo[d] = fminf(s.lo[d], gs.lo[d]);
+        s.hi[d] = fmaxf(s.hi[d], gs.hi[d]);
+        s.q[d] += gs.q[d];
+      }
+      s.n += gs.n;
+    }
+    out[sg] = s;
+  }
+}
+
 template <bool kPrivate>
 __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long long sx, long long sy,
                                         long long sz, unsigned int cnt);
 
+// The centroid nearest to the centre of a box (lowest index on ties).
+__device__ __forceinline__ int nearest_to_box_centre(const float4* __restrict__ s_fast, int k, float lo0, float lo1,
+                                                     float lo2, float hi0, float hi1, float hi2) {
+  const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
+  float dmin = __int_as_float(0x7f800000);
+  int ref = 0;
+  for (int j = 0; j < k; ++j) {
+    const float4 r = s_fast[j];
+    const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
+    if (d < dmin) { dmin = d; ref = j; }
+  }
+  return ref;
+}
+
+// Is centroid `ref` the only one that can be nearest (within the margin) to a point of the box?
+__device__ __forceinline__ bool box_owned_by(const float4* __restrict__ s_fast, int k, const unsigned char* s_bkt,
+                                             int ref, float margin, float lo0, float lo1, float lo2, float hi0,
+                                             float hi1, float hi2) {
+  const float4 rr = s_fast[ref];
+  int ncand = 0;
+  if (s_bkt == nullptr) {
+    // few centroids: all of them, with the box as centre + half-widths -- the minimum of the
+    // (linear) gap over the box is its value at the centre minus sum_d |a_d| h_d.  The
+    // rounding of this form is covered by a margin of 6 * thresh instead of 4 * thresh.
+    // (A cheap "box inside the safe ball of c_ref" test in front of this loop was measured: one
+    // thread per box means a warp skips the loop only when all its 32 boxes pass, and the extra
+    // test cost more than those warps saved -- not kept.)
+    const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
+    const float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
+    const float lim = fmaf(mx, rr.x, fmaf(my, rr.y, fmaf(mz, rr.z, rr.w))) + 1.5f * margin;
+    for (int j = 0; j < k; ++j) {
+      const float4 r = s_fast[j];
+      const float dj = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
+      const float reach = fmaf(fabsf(r.x - rr.x), hx, fmaf(fabsf(r.y - rr.y), hy, fabsf(r.z - rr.z) * hz));
+      ncand += (dj - reach <= lim) ? 1 : 0;  // j == ref: reach = 0, dj <= lim: counted once
+    }
+  } else {
+    // Only centroids near the box can win: d_j(x) <= d_ref(x) + margin at some x of the box
+    // implies |x - c_j| <= sqrt(r^2 + margin), r = largest distance from c_ref to the box;
+    // so c_j lies in the box grown by that reach, and only those buckets are visited.
+    const BucketHdr hdr = *reinterpret_cast<const BucketHdr*>(s_bkt);
+    const int g = bucket_g(k);
+    const unsigned short* start = reinterpret_cast<const unsigned short*>(s_bkt + sizeof(BucketHdr));
+    const unsigned short* perm = start + g * g + 1;
+    const float cx = -0.5f * rr.x, cy = -0.5f * rr.y, cz = -0.5f * rr.z;
+    const float dx = fmaxf(fabsf(lo0 - cx), fabsf(hi0 - cx)), dy = fmaxf(fabsf(lo1 - cy), fabsf(hi1 - cy)),
+                dz = fmaxf(fabsf(lo2 - cz), fabsf(hi2 - cz));
+    const float reach = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)) + 2.0f * margin) * 1.0001f + 1e-3f / hdr.inv_x;
+    const int bx0 = bucket_coord(lo0 - reach, hdr.hx, hdr.inv_x, g), bx1 = bucket_coord(hi0 + reach, hdr.hx, hdr.inv_x, g);
+    const int by0 = bucket_coord(lo1 - reach, hdr.hy, hdr.inv_y, g), by1 = bucket_coord(hi1 + reach, hdr.hy, hdr.inv_y, g);
+    ncand = 1;  // ref itself
+    for (int by = by0; by <= by1 && ncand <= 1; ++by) {
+      const int i1 = start[by * g + bx1 + 1];
+      for (int i = start[by * g + bx0]; i < i1; ++i) {
+        const int j = perm[i];
+        if (j != ref && min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) {
+          ++ncand;
+          break;
+        }
+      }
+    }
+  }
+  return ncand <= 1;  // only ref itself can win anywhere in the box
+}
+
 template <typename LabT, bool kPrivate>
-__device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__ gsum, int n_groups,
+__device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__ gsum,
+                                                const SuperSummary* __restrict__ ssum, int n_groups,
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
                                                 bool first_iter, unsigned long long* s_acc, int* s_list,
@@ -414,94 +522,43 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
   const int tid = threadIdx.x, lane = tid & 31;
   int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
   int w_count = 0;                                                         // warp-uniform
-  const int span = (int)gridDim.x * kThreads;
-  int g = (int)blockIdx.x * kThreads + tid;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
-  int prev = -1;
-  if (g < n_groups) {
-    const float4* src = reinterpret_cast<const float4*>(gsum + g);
-    a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-    prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
-  }
-  for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // CTA-uniform trip count
-    const bool valid = g < n_groups;
+  constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;                    // 16-byte words of a group's labels
+
+  // hands the staged worklist entries of this warp to the global list (one atomic per flush, not
+  // one per round: the round trip of a global atomic would dominate this pass) -- no CTA barrier
+  auto flush = [&]() {
+    __syncwarp();
+    int dst = 0;
+    if (lane == 0 && w_count) dst = atomicAdd(work_count, w_count);
+    dst = __shfl_sync(0xffffffffu, dst, 0);
+    for (int i = lane; i < w_count; i += 32) worklist[dst + i] = w_list[i];
+    __syncwarp();
+    w_count = 0;
+  };
+
+  // One group per lane (warp-synchronous): test it against the label it was settled with, add the
+  // cached sums of the settled ones, stage the others for the per-point pass.
+  auto group_round = [&](int g, bool valid) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    int prev = -1;
+    if (valid) {
+      const float4* src = reinterpret_cast<const float4*>(gsum + g);
+      a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
+      prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
+    }
     int label = -1;  // settled label, or -1: needs the per-point pass
     const int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
     if (settle && valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
-      const float lo0 = a.x, lo1 = a.y, lo2 = a.z, hi0 = a.w, hi1 = b.x, hi2 = b.y;
-      int ref = prev;
-      if (ref < 0) {  // nearest centroid to the box centre, lowest index on ties
-        const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
-        float dmin = __int_as_float(0x7f800000);
-        ref = 0;
-        for (int j = 0; j < k; ++j) {
-          const float4 r = s_fast[j];
-          const float d = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
-          if (d < dmin) { dmin = d; ref = j; }
-        }
-      }
-      const float4 rr = s_fast[ref];
-      int ncand = 0;
-      if (s_bkt == nullptr) {
-        // few centroids: all of them, with the box as centre + half-widths -- the minimum of the
-        // (linear) gap over the box is its value at the centre minus sum_d |a_d| h_d.  The
-        // rounding of this form is covered by a margin of 6 * thresh instead of 4 * thresh.
-        const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
-        const float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
-        const float lim = fmaf(mx, rr.x, fmaf(my, rr.y, fmaf(mz, rr.z, rr.w))) + 1.5f * margin;
-        // (A cheap "box inside the safe ball of c_ref" test in front of this loop was measured: one
-        // thread per group means a warp skips the loop only when all its 32 groups pass, and the
-        // extra test cost more than those warps saved -- not kept.)
-        for (int j = 0; j < k; ++j) {
-          const float4 r = s_fast[j];
-          const float dj = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
-          const float reach = fmaf(fabsf(r.x - rr.x), hx, fmaf(fabsf(r.y - rr.y), hy, fabsf(r.z - rr.z) * hz));
-          ncand += (dj - reach <= lim) ? 1 : 0;  // j == ref: reach = 0, dj <= lim: counted once
-        }
-      } else {
-        // Only centroids near the group can win: d_j(x) <= d_ref(x) + margin at some x of the box
-        // implies |x - c_j| <= sqrt(r^2 + margin), r = largest distance from c_ref to the box;
-        // so c_j lies in the box grown by that reach, and only those buckets are visited.
-        const BucketHdr hdr = *reinterpret_cast<const BucketHdr*>(s_bkt);
-        const int g = bucket_g(k);
-        const unsigned short* start = reinterpret_cast<const unsigned short*>(s_bkt + sizeof(BucketHdr));
-        const unsigned short* perm = start + g * g + 1;
-        const float cx = -0.5f * rr.x, cy = -0.5f * rr.y, cz = -0.5f * rr.z;
-        const float dx = fmaxf(fabsf(lo0 - cx), fabsf(hi0 - cx)), dy = fmaxf(fabsf(lo1 - cy), fabsf(hi1 - cy)),
-                    dz = fmaxf(fabsf(lo2 - cz), fabsf(hi2 - cz));
-        const float reach = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)) + 2.0f * margin) * 1.0001f + 1e-3f / hdr.inv_x;
-        const int bx0 = bucket_coord(lo0 - reach, hdr.hx, hdr.inv_x, g), bx1 = bucket_coord(hi0 + reach, hdr.hx, hdr.inv_x, g);
-        const int by0 = bucket_coord(lo1 - reach, hdr.hy, hdr.inv_y, g), by1 = bucket_coord(hi1 + reach, hdr.hy, hdr.inv_y, g);
-        ncand = 1;  // ref itself
-        for (int by = by0; by <= by1 && ncand <= 1; ++by) {
-          const int i1 = start[by * g + bx1 + 1];
-          for (int i = start[by * g + bx0]; i < i1; ++i) {
-            const int j = perm[i];
-            if (j != ref && min_gap_over_box(s_fast[j], rr, lo0, hi0, lo1, hi1, lo2, hi2) <= margin) {
-              ++ncand;
-              break;
-            }
-          }
-        }
-      }
-      if (ncand <= 1) label = ref;  // only ref itself can win anywhere in the box
+      const int ref = prev >= 0 ? prev : nearest_to_box_centre(s_fast, k, a.x, a.y, a.z, a.w, b.x, b.y);
+      if (box_owned_by(s_fast, k, s_bkt, ref, margin, a.x, a.y, a.z, a.w, b.x, b.y)) label = ref;
     }
     if (label >= 0 && first_iter) {  // later iterations: label == prev, nothing to write
       n_chg += kGroup;
       uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)g * kGroup);
-      constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;
       const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
 #pragma unroll
       for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
       glabel[g] = label;
-    }
-    const int g_now = g;
-    // next group of this thread: its summary loads overlap the bookkeeping below
-    g += span;
-    if (g < n_groups) {
-      const float4* src = reinterpret_cast<const float4*>(gsum + g);
-      a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-      prev = first_iter ? -1 : __ldcg(glabel + g);
     }
     // cached sums, one round per distinct label in the warp (usually one)
     unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
@@ -522,23 +579,84 @@ __device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__
       if (lane == 0) acc_add<kPrivate>(s_acc, L, sum[0], sum[1], sum[2], (unsigned int)__popc(hits) * kGroup);
       todo &= ~hits;
     }
-    // the rest goes to the per-point pass: every warp collects its groups in its own slice of
-    // shared memory and hands them to the global worklist with one atomic per flush (not one
-    // per trip: the round trip of a global atomic would dominate this pass) -- no CTA barrier
     const unsigned int heavy = __ballot_sync(0xffffffffu, valid && label < 0);
-    if (valid && label < 0) w_list[w_count + __popc(heavy & ((1u << lane) - 1u))] = g_now;
+    if (valid && label < 0) w_list[w_count + __popc(heavy & ((1u << lane) - 1u))] = g;
     w_count += __popc(heavy);
-    const bool last_trip = base + span >= n_groups;
-    if (last_trip || w_count + 32 > kClassifyList / (kThreads / 32)) {  // warp-uniform
-      __syncwarp();
-      int dst = 0;
-      if (lane == 0 && w_count) dst = atomicAdd(work_count, w_count);
-      dst = __shfl_sync(0xffffffffu, dst, 0);
-      for (int i = lane; i < w_count; i += 32) worklist[dst + i] = w_list[i];
-      __syncwarp();
-      w_count = 0;
+    if (w_count + 32 > kClassifyList / (kThreads / 32)) flush();  // warp-uniform
+  };
+
+  const int n_super = (n_groups + kSuper - 1) / kSuper;
+  const int span = (int)gridDim.x * kThreads;
+  for (int sbase = (int)blockIdx.x * kThreads; sbase < n_super; sbase += span) {  // CTA-uniform trip count
+    // ---- one SUPER-group per lane ------------------------------------------------------------
+    const int sg = sbase + tid;
+    bool fail = sg < n_super;  // its groups have to be looked at one by one
+    int label = -1;
+    long long sq[3] = {0, 0, 0};
+    if (settle && fail) {
+      const float4* src = reinterpret_cast<const float4*>(ssum + sg);
+      const float4 a = __ldg(src), b = __ldg(src + 1);  // lo[3] hi[0] | hi[1] hi[2] n pad
+      if (__float_as_int(b.z) == kSuper * kGroup) {
+        int ref = -1;
+        if (first_iter) {
+          ref = nearest_to_box_centre(s_fast, k, a.x, a.y, a.z, a.w, b.x, b.y);
+        } else {
+          // settled as a whole only if all its groups were settled with one label
+          const int4* gl = reinterpret_cast<const int4*>(glabel + (size_t)sg * kSuper);
+          const int4 u = __ldcg(gl), v = __ldcg(gl + 1);
+          static_assert(kSuper == 8, "two int4 of group labels per super-group");
+          const bool same = u.x == u.y && u.x == u.z && u.x == u.w && u.x == v.x && u.x == v.y && u.x == v.z && u.x == v.w;
+          ref = same ? u.x : -1;
+        }
+        if (ref >= 0 && box_owned_by(s_fast, k, s_bkt, ref, margin, a.x, a.y, a.z, a.w, b.x, b.y)) {
+          label = ref;
+          fail = false;
+          const longlong2 q01 = *reinterpret_cast<const longlong2*>(src + 2);
+          sq[0] = q01.x; sq[1] = q01.y;
+          sq[2] = *reinterpret_cast<const long long*>(src + 3);
+        }
+      }
+    }
+    if (label >= 0 && first_iter) {
+      n_chg += kSuper * kGroup;
+      uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)sg * kSuper * kGroup);
+      const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
+      for (int v = 0; v < kSuper * kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
+      int4* gl = reinterpret_cast<int4*>(glabel + (size_t)sg * kSuper);
+      gl[0] = make_int4(label, label, label, label);
+      gl[1] = make_int4(label, label, label, label);
+    }
+    // cached sums of the settled super-groups, one round per distinct label in the warp
+    unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
+    while (todo) {
+      const int L = __shfl_sync(0xffffffffu, label, __ffs(todo) - 1);
+      const bool hit = label == L;
+      long long sum[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        // |q| < 2^32 per super-group, 32 of them: the two halves are reduced separately
+        const int hi = __reduce_add_sync(0xffffffffu, hit ? (int)(sq[d] >> 16) : 0);
+        const int lo = __reduce_add_sync(0xffffffffu, hit ? (int)(sq[d] & 0xffff) : 0);
+        sum[d] = ((long long)hi << 16) + (long long)lo;
+      }
+      const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) acc_add<kPrivate>(s_acc, L, sum[0], sum[1], sum[2], (unsigned int)__popc(hits) * (kSuper * kGroup));
+      todo &= ~hits;
+    }
+    // ---- the groups of the super-groups that failed: four super-groups (32 groups) per round ----
+    unsigned int fm = __ballot_sync(0xffffffffu, fail);
+    const int wbase = sbase + (tid & ~31);  // first super-group of this warp
+    while (fm) {                            // warp-uniform
+      unsigned int m = fm;
+      for (int i = 0; i < (lane >> 3); ++i) m &= m - 1u;  // drop the lane / 8 lowest set bits
+      const int sl = m ? __ffs(m) - 1 : -1;
+      const int g = sl >= 0 ? (wbase + sl) * kSuper + (lane & (kSuper - 1)) : n_groups;
+      group_round(g, g < n_groups);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fm &= fm - 1u;  // (x & (x - 1) of 0 is 0)
     }
   }
+  flush();
 }
 
 // Grid-wide barrier of a cooperatively launched (fully resident) grid: a monotonically
@@ -1102,7 +1220,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   mbar_wait(&s_bar, 0);
   // the ring is idle during pass 1: its first bytes stage the worklist entries
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
-  classify_groups<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
+  classify_groups<LabT, kPrivate>(p.gsum, reinterpret_cast<const SuperSummary*>(p.ssum), n_groups, labels, p.glabel,
+                                  p.worklist, p.work_count, s_fast, p.k,
                                   4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
                                   bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
 #ifdef MDKM_TIMING

@@ -77,6 +77,7 @@ struct mdkm_handle {
   DevBuf<unsigned int> uscratch;  // tickets, minmax
   DevBuf<unsigned long long> reloc;  // relocation scratch
   DevBuf<unsigned char> gsum;        // GroupSummary per 128-point group (static per cloud + frame)
+  DevBuf<unsigned char> ssum;        // SuperSummary per kSuper groups
   DevBuf<int> glabel;                // per group: uniform label or -1
   DevBuf<int> worklist;              // [n_groups] + 1 counter at the end
   bool summary_ok = false;
@@ -605,7 +606,9 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   // group summaries for the classification pass
   kb.n_groups = cap / kGroup;
   OK(ensure(h, h->gsum, (size_t)kb.n_groups * sizeof(GroupSummary)));
-  OK(ensure(h, h->glabel, (size_t)kb.n_groups));
+  const long long n_super = (kb.n_groups + kSuper - 1) / kSuper;
+  OK(ensure(h, h->ssum, (size_t)n_super * sizeof(SuperSummary)));
+  OK(ensure(h, h->glabel, (size_t)n_super * kSuper));  // (whole super-groups: read eight at a time)
   OK(ensure(h, h->worklist, (size_t)kb.n_groups + 4));
   if (!h->summary_ok) {
     const int span = prof_begin(h, MDKM_PHASE_BUILD, h->n);
@@ -620,6 +623,10 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
       ++h->launches;
       CU(cudaGetLastError());
     }
+    super_summary_kernel<<<grid_for(h, (n_super + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+        reinterpret_cast<const GroupSummary*>(h->gsum.p), (int)kb.n_groups, reinterpret_cast<SuperSummary*>(h->ssum.p));
+    ++h->launches;
+    CU(cudaGetLastError());
     prof_end(h, span);
     h->summary_ok = true;
   }
@@ -672,6 +679,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   // the worklist that pass 2 streams point by point
   int* work_count = h->worklist.p + kb.n_groups;
   sp.gsum = reinterpret_cast<const GroupSummary*>(h->gsum.p);
+  sp.ssum = h->ssum.p;
   sp.worklist = h->worklist.p;
   sp.work_count = work_count;
   sp.glabel = h->glabel.p;
@@ -863,7 +871,7 @@ void mdkm_destroy(mdkm_handle* h) {
   release(h->pts);
   release(h->labels); release(h->table); release(h->acc); release(h->labels32);
   release(h->dscratch); release(h->partials); release(h->uscratch); release(h->reloc);
-  release(h->gsum); release(h->glabel); release(h->worklist);
+  release(h->gsum); release(h->ssum); release(h->glabel); release(h->worklist);
   release(h->tpts); release(h->cell_counts); release(h->cell_offsets);
   release(h->run_src); release(h->druns); release(h->gfirst);
   release(h->tile_status); release(h->chunk_offsets); release(h->staging); release(h->planes);
