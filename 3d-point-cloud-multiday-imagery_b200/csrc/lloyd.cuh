@@ -155,6 +155,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   const bool have0 = tid < u.k;
   ulonglong2 a0 = make_ulonglong2(0ull, 0ull), b0 = a0;
   double4 old0 = make_double4(0.0, 0.0, 0.0, 0.0);
+  const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);  // (same round trip as the rows below)
   if (have0) {
     a0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4));
     b0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4 + 2));
@@ -238,7 +239,6 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
-  const unsigned long long n_changed = __ldcg(&u.acc[u.kpad * 4 + 0]);
   build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
   // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
   for (int o = 16; o > 0; o >>= 1) {
