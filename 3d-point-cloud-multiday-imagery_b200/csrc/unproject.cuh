@@ -190,6 +190,38 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* 
   return excl;
 }
 
+// Raster position (and detrended height) of the pixel `pix` of a tile whose first pixel sits at
+// (day0, row0, col0): 32-bit arithmetic, no division for rasters at least a tile wide.
+struct TilePos {
+  unsigned int col0, row0, W, H;
+  int day0, plane_day0;
+  const double* planes;
+};
+__device__ __forceinline__ void tile_point(const TilePos& t, unsigned int pix, const float* wz, float& fx, float& fy,
+                                           float& zz) {
+  unsigned int col = t.col0 + pix, row = t.row0;
+  int dcur = t.day0;
+  if (t.W >= (unsigned int)kTile) {  // at most one row boundary inside the tile
+    if (col >= t.W) { col -= t.W; ++row; }
+  } else {
+    const unsigned int q = col / t.W;
+    col -= q * t.W;
+    row += q;
+  }
+  while (row >= t.H) {  // a tile may run into the next day(s)
+    row -= t.H;
+    ++dcur;
+  }
+  zz = wz[pix];
+  if (t.planes) {
+    // plugin.py:171: height_rel = dot(P - center, normal)
+    const double* pl = t.planes + (size_t)(dcur - t.plane_day0) * 8;
+    zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)zz - pl[2]) * pl[5]);
+  }
+  fx = (float)col;
+  fy = (float)row;
+}
+
 // One CTA takes a super-tile of kThreads / 32 = 8 consecutive warp tiles per ticket: the warps rank
 // their tiles independently, ONE look-back per super-tile (by warp 0) yields the CTA's offset, and
 // the warps' own offsets follow from the eight counts in shared memory.  The look-back depth is
@@ -279,35 +311,42 @@ __global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojP
     const unsigned int row0 = (unsigned int)(rem0 / p.W);
     const unsigned int col0 = (unsigned int)(rem0 - (long long)row0 * p.W);
     const unsigned int W = (unsigned int)p.W, H = (unsigned int)p.H;
-    for (unsigned int i = lane; i < cnt; i += 32) {
-      const unsigned int pix = wix[i];
-      unsigned int col = col0 + pix, row = row0;
-      int dcur = (int)day0;
-      if (W >= (unsigned int)kTile) {  // at most one row boundary inside the tile
-        if (col >= W) { col -= W; ++row; }
-      } else {
-        const unsigned int q = col / W;
-        col -= q * W;
-        row += q;
-      }
-      while (row >= H) {  // a tile may run into the next day(s)
-        row -= H;
-        ++dcur;
-      }
-      float zz = wz[pix];
-      if (p.planes) {
-        // plugin.py:171: height_rel = dot(P - center, normal)
-        const double* pl = p.planes + (size_t)(dcur - p.day0) * 8;
-        zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)zz - pl[2]) * pl[5]);
-      }
+    const TilePos tp{col0, row0, W, H, (int)day0, p.day0, p.planes};
+    // outputs [excl, excl + cnt): a few single points up to the next multiple of four, then four
+    // consecutive points per lane and round as three 16-byte stores (a block of the cloud holds
+    // 128 points, so an aligned quad never straddles two blocks), then the rest
+    const unsigned int lead = min(cnt, (4u - (unsigned int)(excl & 3ull)) & 3u);
+    const unsigned int quads = (cnt - lead) >> 2;
+    for (unsigned int j = lane; j < quads; j += 32) {
+      const unsigned int i = lead + 4u * j;
+      float4 vx, vy, vz;
+      tile_point(tp, wix[i + 0], wz, vx.x, vy.x, vz.x);
+      tile_point(tp, wix[i + 1], wz, vx.y, vy.y, vz.y);
+      tile_point(tp, wix[i + 2], wz, vx.z, vy.z, vz.z);
+      tile_point(tp, wix[i + 3], wz, vx.w, vy.w, vz.w);
       float* dst = p.pts + pt_off((long long)excl + i);
-      const float fx = (float)col, fy = (float)row;
-      dst[0] = fx;
-      dst[kGroup] = fy;
-      dst[2 * kGroup] = zz;
-      mn[0] = fminf(mn[0], fx); mx[0] = fmaxf(mx[0], fx);
-      mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
-      mn[2] = fminf(mn[2], zz); mx[2] = fmaxf(mx[2], zz);
+      *reinterpret_cast<float4*>(dst) = vx;
+      *reinterpret_cast<float4*>(dst + kGroup) = vy;
+      *reinterpret_cast<float4*>(dst + 2 * kGroup) = vz;
+      mn[0] = fminf(fminf(mn[0], vx.x), fminf(fminf(vx.y, vx.z), vx.w)); mx[0] = fmaxf(fmaxf(mx[0], vx.x), fmaxf(fmaxf(vx.y, vx.z), vx.w));
+      mn[1] = fminf(fminf(mn[1], vy.x), fminf(fminf(vy.y, vy.z), vy.w)); mx[1] = fmaxf(fmaxf(mx[1], vy.x), fmaxf(fmaxf(vy.y, vy.z), vy.w));
+      mn[2] = fminf(fminf(mn[2], vz.x), fminf(fminf(vz.y, vz.z), vz.w)); mx[2] = fmaxf(fmaxf(mx[2], vz.x), fmaxf(fmaxf(vz.y, vz.z), vz.w));
+    }
+    {  // the (at most 3 + 3) points before and behind the quads: one lane each
+      const unsigned int tail0 = lead + 4u * quads;
+      const unsigned int n_single = lead + (cnt - tail0);
+      if ((unsigned int)lane < n_single) {
+        const unsigned int i = (unsigned int)lane < lead ? (unsigned int)lane : tail0 + ((unsigned int)lane - lead);
+        float fx, fy, zz;
+        tile_point(tp, wix[i], wz, fx, fy, zz);
+        float* dst = p.pts + pt_off((long long)excl + i);
+        dst[0] = fx;
+        dst[kGroup] = fy;
+        dst[2 * kGroup] = zz;
+        mn[0] = fminf(mn[0], fx); mx[0] = fmaxf(mx[0], fx);
+        mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
+        mn[2] = fminf(mn[2], zz); mx[2] = fmaxf(mx[2], zz);
+      }
     }
   }
   if (p.minmax) {
