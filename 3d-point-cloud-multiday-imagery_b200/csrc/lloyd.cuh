@@ -329,6 +329,7 @@ struct StepParams {
   int ignore_status;          // 1: test hook (run even when done/paused)
   int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
                               //    (NVLink, no host, no NCCL) and runs the centroid update
+  int two_level;              // 1: classification pass walks super-groups first (large clouds)
   int settle;                 // 0: measurement mode, no group is settled from its summary --
                               //    every point goes through the per-point pass (MDKM_OPT_SETTLE_GROUPS)
   const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
@@ -477,6 +478,7 @@ __device__ __forceinline__ bool box_owned_by(const float4* __restrict__ s_fast, 
     const float mx = 0.5f * (lo0 + hi0), my = 0.5f * (lo1 + hi1), mz = 0.5f * (lo2 + hi2);
     const float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
     const float lim = fmaf(mx, rr.x, fmaf(my, rr.y, fmaf(mz, rr.z, rr.w))) + 1.5f * margin;
+#pragma unroll 4
     for (int j = 0; j < k; ++j) {
       const float4 r = s_fast[j];
       const float dj = fmaf(mx, r.x, fmaf(my, r.y, fmaf(mz, r.z, r.w)));
@@ -512,8 +514,95 @@ __device__ __forceinline__ bool box_owned_by(const float4* __restrict__ s_fast, 
   return ncand <= 1;  // only ref itself can win anywhere in the box
 }
 
+// One level: one thread per group, the next group's summary requested while the current one is
+// worked on.  The better choice while every thread has only a few groups (the two-level walk
+// below is a chain of dependent rounds: super-group test, then its failed groups).
 template <typename LabT, bool kPrivate>
-__device__ __forceinline__ void classify_groups(const GroupSummary* __restrict__ gsum,
+__device__ __forceinline__ void classify_groups_flat(const GroupSummary* __restrict__ gsum, int n_groups,
+                                                LabT* labels, int* glabel, int* worklist, int* work_count,
+                                                const float4* __restrict__ s_fast, int k, float margin,
+                                                bool first_iter, unsigned long long* s_acc, int* s_list,
+                                                const unsigned char* s_bkt, unsigned int& n_chg, bool settle) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
+  int w_count = 0;                                                         // warp-uniform
+  const int span = (int)gridDim.x * kThreads;
+  int g = (int)blockIdx.x * kThreads + tid;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+  int prev = -1;
+  if (g < n_groups) {
+    const float4* src = reinterpret_cast<const float4*>(gsum + g);
+    a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
+    prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
+  }
+  for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // CTA-uniform trip count
+    const bool valid = g < n_groups;
+    int label = -1;  // settled label, or -1: needs the per-point pass
+    const int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
+    if (settle && valid && __float_as_int(c.y) == kGroup && (first_iter || prev >= 0)) {
+      const float lo0 = a.x, lo1 = a.y, lo2 = a.z, hi0 = a.w, hi1 = b.x, hi2 = b.y;
+      const int ref = prev >= 0 ? prev : nearest_to_box_centre(s_fast, k, lo0, lo1, lo2, hi0, hi1, hi2);
+      if (box_owned_by(s_fast, k, s_bkt, ref, margin, lo0, lo1, lo2, hi0, hi1, hi2)) label = ref;
+    }
+    if (label >= 0 && first_iter) {  // later iterations: label == prev, nothing to write
+      n_chg += kGroup;
+      uint4* lp = reinterpret_cast<uint4*>(labels + (size_t)g * kGroup);
+      constexpr int kVec = kGroup * (int)sizeof(LabT) / 16;
+      const unsigned int fillw = sizeof(LabT) == 1 ? (unsigned int)label * 0x01010101u : (unsigned int)label * 0x00010001u;
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) lp[v] = make_uint4(fillw, fillw, fillw, fillw);
+      glabel[g] = label;
+    }
+    const int g_now = g;
+    // next group of this thread: its summary loads overlap the bookkeeping below
+    g += span;
+    if (g < n_groups) {
+      const float4* src = reinterpret_cast<const float4*>(gsum + g);
+      a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
+      prev = first_iter ? -1 : __ldcg(glabel + g);
+    }
+    // cached sums, one round per distinct label in the warp (usually one)
+    unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
+    while (todo) {
+      const int L = __shfl_sync(0xffffffffu, label, __ffs(todo) - 1);
+      const bool hit = label == L;
+      long long sum[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        // 32 groups x 2^29 overflows 32 bits: reduce the two halves of q separately
+        const int hi = __reduce_add_sync(0xffffffffu, hit ? (q[d] >> 15) : 0);
+        const int lo = __reduce_add_sync(0xffffffffu, hit ? (q[d] & 0x7fff) : 0);
+        sum[d] = ((long long)hi << 15) + (long long)lo;
+      }
+      const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+      // the warp's private slice when there is one (plain read-modify-write): 64-bit
+      // shared-memory atomics are compare-and-swap loops and collapse under contention
+      if (lane == 0) acc_add<kPrivate>(s_acc, L, sum[0], sum[1], sum[2], (unsigned int)__popc(hits) * kGroup);
+      todo &= ~hits;
+    }
+    // the rest goes to the per-point pass: every warp collects its groups in its own slice of
+    // shared memory and hands them to the global worklist with one atomic per flush (not one
+    // per trip: the round trip of a global atomic would dominate this pass) -- no CTA barrier
+    const unsigned int heavy = __ballot_sync(0xffffffffu, valid && label < 0);
+    if (valid && label < 0) w_list[w_count + __popc(heavy & ((1u << lane) - 1u))] = g_now;
+    w_count += __popc(heavy);
+    const bool last_trip = base + span >= n_groups;
+    if (last_trip || w_count + 32 > kClassifyList / (kThreads / 32)) {  // warp-uniform
+      __syncwarp();
+      int dst = 0;
+      if (lane == 0 && w_count) dst = atomicAdd(work_count, w_count);
+      dst = __shfl_sync(0xffffffffu, dst, 0);
+      for (int i = lane; i < w_count; i += 32) worklist[dst + i] = w_list[i];
+      __syncwarp();
+      w_count = 0;
+    }
+  }
+}
+
+// Two levels: super-groups first, groups only where a super-group fails.  Pays once a thread
+// has many groups to look at (large clouds).
+template <typename LabT, bool kPrivate>
+__device__ __forceinline__ void classify_groups_two_level(const GroupSummary* __restrict__ gsum,
                                                 const SuperSummary* __restrict__ ssum, int n_groups,
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
@@ -1220,10 +1309,15 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   mbar_wait(&s_bar, 0);
   // the ring is idle during pass 1: its first bytes stage the worklist entries
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
-  classify_groups<LabT, kPrivate>(p.gsum, reinterpret_cast<const SuperSummary*>(p.ssum), n_groups, labels, p.glabel,
-                                  p.worklist, p.work_count, s_fast, p.k,
-                                  4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
-                                  bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
+  if (p.two_level)
+    classify_groups_two_level<LabT, kPrivate>(p.gsum, reinterpret_cast<const SuperSummary*>(p.ssum), n_groups, labels,
+                                              p.glabel, p.worklist, p.work_count, s_fast, p.k, 4.0f * thresh, first_iter,
+                                              s_acc, reinterpret_cast<int*>(s_ring), bkt_bytes ? s_bkt : nullptr, n_chg,
+                                              p.settle != 0);
+  else
+    classify_groups_flat<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
+                                         4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
+                                         bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif

@@ -96,6 +96,7 @@ struct mdkm_handle {
   DevBuf<unsigned int> gfirst;
   int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
   int opt_cell_px = 0, opt_cell_rows = 0;  // MDKM_OPT_CELL_PX / MDKM_OPT_CELL_ROWS (0 = automatic)
+  int opt_two_level = -1;                  // MDKM_OPT_TWO_LEVEL (-1 = automatic)
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -670,6 +671,10 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.ignore_status = ignore_status;
   sp.fuse_update = fuse_update;
   sp.settle = h->opt_settle;
+  // two-level classification once every thread of the grid has more than a handful of groups
+  // (measured: config 2, 2.8 groups per thread, is 5 us per iteration faster with one level;
+  // config 3 / 5, 11 / 34 groups per thread, are 9 / 35 us faster with two)
+  sp.two_level = h->opt_two_level >= 0 ? h->opt_two_level : (kb.n_groups > 6ll * kb.step_grid * kThreads ? 1 : 0);
   if (fuse_update) {
     sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
     sp.px = h->px;
@@ -1032,6 +1037,9 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
     case MDKM_OPT_RASTER_MIRROR:
       h->opt_raster_mirror = value != 0;
       h->summary_ok = false;
+      return MDKM_OK;
+    case MDKM_OPT_TWO_LEVEL:
+      h->opt_two_level = value < 0 ? -1 : (value != 0);
       return MDKM_OK;
     case MDKM_OPT_CELL_PX:
       if (value != 0 && value != 8 && value != 16) return fail(h, MDKM_ERR_INVALID, "cell width must be 0 (automatic), 8 or 16 pixels");

@@ -486,6 +486,32 @@ def test_raster_mirror_equals_generic_mirror(engine, shape, k, rows, valid):
     np.testing.assert_array_equal(step_on[2], np.bincount(KO.lloyd_iter(P - P.mean(0), init - P.mean(0))[0], minlength=k))
 
 
+@pytest.mark.parametrize("shape,k", [((3, 200, 256), 7), ((2, 300, 520), 40), ((1, 64, 2048), 300)])
+def test_two_level_classification_equals_flat(engine, shape, k):
+    """The classification pass walks super-groups first on large clouds and single groups on small
+    ones (MDKM_OPT_TWO_LEVEL picks automatically): both must give the same fit, bit for bit."""
+    cabi = importlib.import_module("3d-point-cloud-multiday-imagery_b200._cabi")
+    hm = synth.make_stack(*shape, seed=k, n_buildings=10).numpy()
+    n = engine.unproject(hm)
+    init = synth.init_from_points(engine.get_cloud(False), k, 2)
+    res = {}
+    try:
+        for mode in (0, 1):
+            engine.set_option(cabi.OPT_TWO_LEVEL, mode)
+            res[mode] = engine.fit(init, max_iter=15, tol=0.0)
+            res[mode, "step"] = engine.lloyd_step(init)
+    finally:
+        engine.set_option(cabi.OPT_TWO_LEVEL, -1)
+    assert res[0]["centers"].tobytes() == res[1]["centers"].tobytes() and res[0]["n_iter"] == res[1]["n_iter"]
+    assert np.array_equal(res[0]["labels"], res[1]["labels"]) and res[0]["inertia"] == res[1]["inertia"]
+    assert np.array_equal(res[0, "step"][0], res[1, "step"][0]) and np.array_equal(res[0, "step"][2], res[1, "step"][2])
+    assert res[1]["worklist_groups"] == res[0]["worklist_groups"]  # the same groups reach the per-point pass
+    P = UO.unproject_stack(hm)
+    ref = KO.kmeans_fit(P, init, max_iter=15, tol=0.0)
+    assert res[1]["n_iter"] == ref["n_iter"]
+    check_labels(P, ref["centers"], ref["labels"], res[1]["labels"])
+
+
 def test_fit_errors(engine):
     engine.set_points(np.zeros((3, 3), dtype=np.float32))
     with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):
