@@ -522,19 +522,15 @@ __device__ __forceinline__ void classify_groups_flat(const GroupSummary* __restr
                                                 LabT* labels, int* glabel, int* worklist, int* work_count,
                                                 const float4* __restrict__ s_fast, int k, float margin,
                                                 bool first_iter, unsigned long long* s_acc, int* s_list,
-                                                const unsigned char* s_bkt, unsigned int& n_chg, bool settle) {
+                                                const unsigned char* s_bkt, unsigned int& n_chg, bool settle,
+                                                float4 a, float4 b, float4 c, int prev) {
+  // a, b, c, prev: summary and previous label of this thread's FIRST group (block * kThreads + tid),
+  // requested by the caller before it waited for the centroid table
   const int tid = threadIdx.x, lane = tid & 31;
   int* w_list = s_list + (tid >> 5) * (kClassifyList / (kThreads / 32));  // this warp's slice
   int w_count = 0;                                                         // warp-uniform
   const int span = (int)gridDim.x * kThreads;
   int g = (int)blockIdx.x * kThreads + tid;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
-  int prev = -1;
-  if (g < n_groups) {
-    const float4* src = reinterpret_cast<const float4*>(gsum + g);
-    a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-    prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
-  }
   for (int base = (int)blockIdx.x * kThreads; base < n_groups; base += span) {  // CTA-uniform trip count
     const bool valid = g < n_groups;
     int label = -1;  // settled label, or -1: needs the per-point pass
@@ -1306,6 +1302,15 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   LabT* labels = reinterpret_cast<LabT*>(p.labels);
   unsigned int n_chg = 0, n_ref = 0;
   // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
+  // (one-level walk: the first group's summary travels while the centroid table does)
+  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
+  int pprev = -1;
+  if (!p.two_level && (int)blockIdx.x * kThreads + tid < n_groups) {
+    const int g_first = (int)blockIdx.x * kThreads + tid;
+    const float4* src = reinterpret_cast<const float4*>(p.gsum + g_first);
+    pa = __ldg(src); pb = __ldg(src + 1); pc = __ldg(src + 2);
+    pprev = first_iter ? -1 : __ldcg(p.glabel + g_first);  // (written by other SMs in the previous iteration)
+  }
   mbar_wait(&s_bar, 0);
   // the ring is idle during pass 1: its first bytes stage the worklist entries
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
@@ -1317,7 +1322,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   else
     classify_groups_flat<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
                                          4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
-                                         bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0);
+                                         bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0, pa, pb, pc, pprev);
 #ifdef MDKM_TIMING
   if (tid == 0) atomicMax(&p.st->t_first_done, globaltimer_ns());  // latest end of pass 1 (reused field)
 #endif
