@@ -760,7 +760,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, int* timeout
         *timeout_flag = 1;
         break;
       }
-      __nanosleep(32);  // hundreds of CTAs poll one word while the last one is still working
     }
     __threadfence();
   }

@@ -81,6 +81,7 @@ struct mdkm_handle {
   DevBuf<int> glabel;                // per group: uniform label or -1
   DevBuf<int> worklist;              // [n_groups] + 1 counter at the end
   bool summary_ok = false;
+  bool ssum_ok = false;  // super-group summaries built for the current mirror
   // tile-ordered mirror of the cloud (mirror.cuh): what the Lloyd iterations stream
   DevBuf<float> tpts;
   int raster_w = 0;  // width of the raster the cloud was unprojected from (0: generic cloud)
@@ -442,6 +443,7 @@ struct KmBuffers {
   int step_grid, final_grid;
   bool wide;     // uint16 labels
   bool priv;     // per-warp accumulator slices in shared memory
+  bool two_level;  // classification pass walks super-groups first
   StepKernel step_fn;
   FinalKernel final_fn;
   long long n_groups;
@@ -624,12 +626,22 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
       ++h->launches;
       CU(cudaGetLastError());
     }
+    prof_end(h, span);
+    h->summary_ok = true;
+    h->ssum_ok = false;
+  }
+  // two-level classification once every thread of the grid has more than a handful of groups
+  // (measured on one box: config 2, 2.8 groups per thread, is 4 us per iteration faster with one
+  // level; config 3 / 5, 11 / 34 groups per thread, are 3 / 47 us faster with two)
+  kb.two_level = h->opt_two_level >= 0 ? h->opt_two_level != 0 : kb.n_groups > 6ll * kb.step_grid * kThreads;
+  if (kb.two_level && !h->ssum_ok) {  // super-group summaries: only when they will be used
+    const int span = prof_begin(h, MDKM_PHASE_BUILD, 0);
     super_summary_kernel<<<grid_for(h, (n_super + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
         reinterpret_cast<const GroupSummary*>(h->gsum.p), (int)kb.n_groups, reinterpret_cast<SuperSummary*>(h->ssum.p));
     ++h->launches;
     CU(cudaGetLastError());
     prof_end(h, span);
-    h->summary_ok = true;
+    h->ssum_ok = true;
   }
   if (!h->d_status) {
     CU(cudaMalloc(&h->d_status, sizeof(DevStatus)));
@@ -671,10 +683,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.ignore_status = ignore_status;
   sp.fuse_update = fuse_update;
   sp.settle = h->opt_settle;
-  // two-level classification once every thread of the grid has more than a handful of groups
-  // (measured: config 2, 2.8 groups per thread, is 5 us per iteration faster with one level;
-  // config 3 / 5, 11 / 34 groups per thread, are 9 / 35 us faster with two)
-  sp.two_level = h->opt_two_level >= 0 ? h->opt_two_level : (kb.n_groups > 6ll * kb.step_grid * kThreads ? 1 : 0);
+  sp.two_level = kb.two_level ? 1 : 0;
   if (fuse_update) {
     sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
     sp.px = h->px;
