@@ -130,14 +130,6 @@ __device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int
 // It sits on the critical path of every iteration, so global round trips are kept to one: a
 // thread fetches the accumulator row and the old centroid of its cluster together, and the
 // five block-wide reductions share one pair of barriers.
-// 32 bytes of a table row through L2 (the update step runs in whichever CTA finishes last; what it
-// reads was written by another SM one iteration earlier).
-__device__ __forceinline__ double4 ldcg_d4(const double4* p) {
-  const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-  const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
-
 __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   DevStatus* st = u.st;
   __shared__ double s_red[5][kThreads / 32];
@@ -159,7 +151,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   if (have0) {
     a0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4));
     b0 = __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + tid * 4 + 2));
-    old0 = ldcg_d4(&exact[tid]);
+    old0 = exact[tid];
   }
   // empty clusters and the heaviest cluster (np.argmax: first maximum)
   int my_empty = 0;
@@ -197,7 +189,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
   for (int j = tid; j < u.kpad; j += kThreads) {
     if (j < u.k) {
       const bool first = j == tid;
-      const double4 old = first ? old0 : ldcg_d4(&exact[j]);
+      const double4 old = first ? old0 : exact[j];
       ulonglong2 a = first ? a0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4));
       ulonglong2 b = first ? b0 : __ldcg(reinterpret_cast<const ulonglong2*>(u.acc + j * 4 + 2));
       double cx, cy, cz;
@@ -272,15 +264,15 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
     st->n_changed = n_changed;
     st->n_empty = n_empty;
     st->paused = 0;
-    const int it = __ldcg(&st->iter) + 1;
+    const int it = st->iter + 1;
     st->iter = it;
-    if (!__ldcg(&st->first) && n_changed == 0ull) {  // _kmeans.py:721-726
+    if (!st->first && n_changed == 0ull) {  // _kmeans.py:721-726
       st->strict = 1;
       st->done = 1;
-    } else if (shift2 <= __ldcg(&st->tol)) {         // _kmeans.py:729-738
+    } else if (shift2 <= st->tol) {         // _kmeans.py:729-738
       st->done = 1;
     }
-    if (it >= __ldcg(&st->max_iter)) st->done = 1;
+    if (it >= st->max_iter) st->done = 1;
     st->first = 0;
   }
 }
@@ -292,9 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) lloyd_update_kernel(const UpdateP
 
 
 
-// exact centroid row: two plain 16 B loads (L1-cached).  NOT the non-coherent path (__ldg): the
-// table is rewritten between the iterations of one launch; plain loads are made coherent again by
-// the acquire fence of the grid barrier that separates the iterations.
+// exact centroid row: two plain 16 B loads (L1-cached; measured faster than the non-coherent
+// path on the many-centroid configurations)
 __device__ __forceinline__ double4 ld_c64(const double4* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
   const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
@@ -555,7 +546,7 @@ __device__ __forceinline__ void classify_groups_flat(const GroupSummary* __restr
     if (g < n_groups) {
       const float4* src = reinterpret_cast<const float4*>(gsum + g);
       a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-      prev = first_iter ? -1 : __ldcg(glabel + g);
+      prev = first_iter ? -1 : glabel[g];
     }
     // cached sums, one round per distinct label in the warp (usually one)
     unsigned int todo = __ballot_sync(0xffffffffu, label >= 0);
@@ -629,7 +620,7 @@ __device__ __forceinline__ void classify_groups_two_level(const GroupSummary* __
     if (valid) {
       const float4* src = reinterpret_cast<const float4*>(gsum + g);
       a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-      prev = first_iter ? -1 : __ldcg(glabel + g);  // (written by other SMs in the previous iteration)
+      prev = first_iter ? -1 : glabel[g];
     }
     int label = -1;  // settled label, or -1: needs the per-point pass
     const int q[3] = {__float_as_int(b.z), __float_as_int(b.w), __float_as_int(c.x)};
@@ -688,7 +679,7 @@ __device__ __forceinline__ void classify_groups_two_level(const GroupSummary* __
         } else {
           // settled as a whole only if all its groups were settled with one label
           const int4* gl = reinterpret_cast<const int4*>(glabel + (size_t)sg * kSuper);
-          const int4 u = __ldcg(gl), v = __ldcg(gl + 1);
+          const int4 u = gl[0], v = gl[1];
           static_assert(kSuper == 8, "two int4 of group labels per super-group");
           const bool same = u.x == u.y && u.x == u.z && u.x == u.w && u.x == v.x && u.x == v.y && u.x == v.z && u.x == v.w;
           ref = same ? u.x : -1;
@@ -1174,7 +1165,7 @@ constexpr int kStages = 3;
 __device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned long long* acc, int n,
                                                    DevStatus* st) {
   const int tid = threadIdx.x, R = px.n_ranks;
-  const unsigned long long epoch = __ldcg(&st->epoch) + 1ull;
+  const unsigned long long epoch = st->epoch + 1ull;
   const int par = (int)(epoch & 1ull);
   const unsigned int tag = (unsigned int)epoch;
   // packets of (parity, source rank): 2 * slot of them, 8 bytes each
@@ -1266,7 +1257,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // (One launch = one Lloyd iteration.  Running a batch of iterations inside one launch, with a
   // grid barrier instead of the kernel boundary, was measured: 0.9 us per iteration at best, and
   // the loop-carried state pushed the kernel over its register budget -- not kept.)
-  if (!p.ignore_status && (__ldcg(&p.st->done) | __ldcg(&p.st->paused))) return;  // the same for every CTA
+  if (!p.ignore_status && (p.st->done | p.st->paused)) return;  // the same for every CTA
 #ifdef MDKM_TIMING
   if (blockIdx.x == 0 && tid == 0) {
     p.st->t_start = globaltimer_ns();
@@ -1292,8 +1283,8 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
     if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
   }
-  const float thresh = __ldcg(&p.st->thresh);
-  const bool first_iter = __ldcg(&p.st->first) != 0;
+  const float thresh = p.st->thresh;
+  const bool first_iter = p.st->first != 0;
 
   // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
@@ -1308,7 +1299,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const int g_first = (int)blockIdx.x * kThreads + tid;
     const float4* src = reinterpret_cast<const float4*>(p.gsum + g_first);
     pa = __ldg(src); pb = __ldg(src + 1); pc = __ldg(src + 2);
-    pprev = first_iter ? -1 : __ldcg(p.glabel + g_first);  // (written by other SMs in the previous iteration)
+    pprev = first_iter ? -1 : p.glabel[g_first];
   }
   mbar_wait(&s_bar, 0);
   // the ring is idle during pass 1: its first bytes stage the worklist entries
@@ -1547,7 +1538,7 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     if (tid == 0) {
       p.st->ticket = 0u;
       if (p.work_count) {
-        p.st->work_sum = __ldcg(&p.st->work_sum) + (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
+        p.st->work_sum += (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
         *p.work_count = 0;
       }
     }
