@@ -409,29 +409,40 @@ struct __align__(16) SuperSummary {
 };
 static_assert(sizeof(SuperSummary) == 64, "SuperSummary is read as four 16-byte words");
 
+// One lane per group (coalesced 48-byte reads), the eight lanes of a super-group combined by shuffles.
 __global__ void __launch_bounds__(kThreads) super_summary_kernel(const GroupSummary* __restrict__ gsum, int n_groups,
                                                                  SuperSummary* __restrict__ out) {
+  static_assert(kSuper == 8, "eight lanes per super-group");
+  const int n_pad = (n_groups + 31) / 32 * 32;  // whole warps: the shuffles below need all 32 lanes
   const int n_super = (n_groups + kSuper - 1) / kSuper;
-  for (int sg = blockIdx.x * kThreads + threadIdx.x; sg < n_super; sg += gridDim.x * kThreads) {
-    SuperSummary s;
-    for (int d = 0; d < 3; ++d) {
-      s.lo[d] = __int_as_float(0x7f800000);
-      s.hi[d] = __int_as_float(0xff800000);
-      s.q[d] = 0;
+  for (int g = blockIdx.x * kThreads + threadIdx.x; g < n_pad; g += gridDim.x * kThreads) {  // warp-uniform trip count
+    float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+    long long q[3] = {0, 0, 0};
+    int n = 0;
+    if (g < n_groups) {
+      const float4* src = reinterpret_cast<const float4*>(gsum + g);
+      const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+      lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = a.w; hi[1] = b.x; hi[2] = b.y;
+      q[0] = __float_as_int(b.z); q[1] = __float_as_int(b.w); q[2] = __float_as_int(c.x);
+      n = __float_as_int(c.y);
     }
-    s.n = 0; s.pad = 0; s.pad2 = 0;
-    for (int i = 0; i < kSuper; ++i) {
-      const int g = sg * kSuper + i;
-      if (g >= n_groups) break;
-      const GroupSummary gs = gsum[g];
+#pragma unroll
+    for (int o = 1; o < kSuper; o <<= 1) {
+#pragma unroll
       for (int d = 0; d < 3; ++d) {
-        s.lo[d] = fminf(s.lo[d], gs.lo[d]);
-        s.hi[d] = fmaxf(s.hi[d], gs.hi[d]);
-        s.q[d] += gs.q[d];
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        q[d] += __shfl_xor_sync(0xffffffffu, q[d], o);
       }
-      s.n += gs.n;
+      n += __shfl_xor_sync(0xffffffffu, n, o);
     }
-    out[sg] = s;
+    if ((threadIdx.x & (kSuper - 1)) == 0 && g / kSuper < n_super) {
+      SuperSummary s;
+      for (int d = 0; d < 3; ++d) { s.lo[d] = lo[d]; s.hi[d] = hi[d]; s.q[d] = q[d]; }
+      s.n = n; s.pad = 0; s.pad2 = 0;
+      out[g / kSuper] = s;
+    }
   }
 }
 

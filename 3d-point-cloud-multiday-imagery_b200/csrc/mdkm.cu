@@ -636,7 +636,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.two_level = h->opt_two_level >= 0 ? h->opt_two_level != 0 : kb.n_groups > 6ll * kb.step_grid * kThreads;
   if (kb.two_level && !h->ssum_ok) {  // super-group summaries: only when they will be used
     const int span = prof_begin(h, MDKM_PHASE_BUILD, 0);
-    super_summary_kernel<<<grid_for(h, (n_super + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+    super_summary_kernel<<<grid_for(h, (kb.n_groups + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
         reinterpret_cast<const GroupSummary*>(h->gsum.p), (int)kb.n_groups, reinterpret_cast<SuperSummary*>(h->ssum.p));
     ++h->launches;
     CU(cudaGetLastError());
