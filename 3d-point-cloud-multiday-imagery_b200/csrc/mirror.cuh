@@ -270,8 +270,9 @@ __device__ __forceinline__ unsigned int raster_run(const RasterGeom& g, int cxi,
   if (y >= g.H) y -= g.H;
   const long long lr = (long long)(g.d0 + dd) * g.H + y - g.row0;
   if (lr < 0 || lr >= g.n_rows) return 0u;
-  const long long j0 = lr * g.nb8 + (long long)cxi * g.cb;
-  const long long j1 = min(j0 + g.cb, (lr + 1) * g.nb8);
+  // (the table has pix_count / 8 + 1 < 2^29 + 1 entries: 32-bit indices)
+  const unsigned int j0 = (unsigned int)lr * (unsigned int)g.nb8 + (unsigned int)(cxi * g.cb);
+  const unsigned int j1 = min(j0 + (unsigned int)g.cb, ((unsigned int)lr + 1u) * (unsigned int)g.nb8);
   src = __ldg(g.run_src + j0);
   return __ldg(g.run_src + j1) - src;
 }
@@ -284,9 +285,11 @@ __global__ void __launch_bounds__(kThreads) raster_cell_count_kernel(const Raste
   for (int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < n_cells; c += stride) {
     const int cyi = c / g.gx, cxi = c - cyi * g.gx;
     unsigned int tot = 0;
+    const float inv_rpc = 1.0f / (float)g.rpc;  // e / rpc without an integer division
     for (int e = lane; e < per_cell; e += 32) {
       unsigned int src;
-      tot += raster_run(g, cxi, cyi, e / g.rpc, e % g.rpc, src);
+      const int dd = per_cell <= 4096 ? (int)(((float)e + 0.5f) * inv_rpc) : e / g.rpc;  // (checked exact for e < 4096)
+      tot += raster_run(g, cxi, cyi, dd, e - dd * g.rpc, src);
     }
     tot = __reduce_add_sync(0xffffffffu, tot);
     if (lane == 0) counts[raster_cell_index(g, cxi, cyi)] = tot;
@@ -305,10 +308,12 @@ __global__ void __launch_bounds__(kThreads) raster_runs_kernel(const RasterGeom 
     const int lin = raster_cell_index(g, cxi, cyi);
     unsigned int carry = (unsigned int)cell_offsets[lin];
     uint2* out = druns + (size_t)lin * per_cell;
+    const float inv_rpc = 1.0f / (float)g.rpc;
     for (int e0 = 0; e0 < per_cell; e0 += 32) {  // warp-uniform trip count
       const int e = e0 + lane;
       unsigned int src = 0u;
-      const unsigned int cnt = e < per_cell ? raster_run(g, cxi, cyi, e / g.rpc, e % g.rpc, src) : 0u;
+      const int dd = per_cell <= 4096 ? (int)(((float)e + 0.5f) * inv_rpc) : e / g.rpc;  // (checked exact for e < 4096)
+      const unsigned int cnt = e < per_cell ? raster_run(g, cxi, cyi, dd, e - dd * g.rpc, src) : 0u;
       unsigned int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -338,7 +343,18 @@ __global__ void __launch_bounds__(kThreads) raster_gather_kernel(const float* __
   const int lane = threadIdx.x & 31;
   const long long n_groups = (n + kGroup - 1) / kGroup;
   const long long stride = (long long)gridDim.x * (kThreads / 32);
-  for (long long grp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); grp < n_groups; grp += stride) {
+  // the first window of the NEXT group of this warp (its index entry, then 32 run-list entries) is
+  // requested while the current group is worked on: two of the three dependent round trips per
+  // group (index -> run list -> points) are off the critical path
+  long long grp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  long long j_next = grp < n_groups ? (long long)__ldg(gfirst + grp) : 0;
+  uint2 e_next = make_uint2(0xffffffffu, 0u);
+  unsigned int w_end_next = 0;
+  if (grp < n_groups) {
+    if (j_next + lane < n_entries) e_next = __ldg(druns + j_next + lane);
+    w_end_next = __ldg(&druns[min(j_next + 32, n_entries)].x);
+  }
+  for (; grp < n_groups; grp += stride) {
     const unsigned int base = (unsigned int)(grp * kGroup);
     const unsigned int n32 = (unsigned int)n;
     unsigned int srcs[4] = {0u, 0u, 0u, 0u};
@@ -346,12 +362,26 @@ __global__ void __launch_bounds__(kThreads) raster_gather_kernel(const float* __
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       if (base + r * 32 + lane < n32) todo |= 1u << r;
-    long long j = __ldg(gfirst + grp);
+    long long j = j_next;
+    uint2 e = e_next;
+    unsigned int w_end = w_end_next;  // first slot behind the window
+    {  // request the next group's first window
+      const long long gn = grp + stride;
+      if (gn < n_groups) {
+        j_next = (long long)__ldg(gfirst + gn);
+        e_next = j_next + lane < n_entries ? __ldg(druns + j_next + lane) : make_uint2(0xffffffffu, 0u);
+        w_end_next = __ldg(&druns[min(j_next + 32, n_entries)].x);
+      }
+    }
+    bool first_window = true;
     while (__any_sync(0xffffffffu, todo != 0)) {
       if (j >= n_entries) break;  // (cannot happen with a consistent run list; never read out of bounds)
-      const long long jj = j + lane;
-      const uint2 e = jj < n_entries ? __ldg(druns + jj) : make_uint2(0xffffffffu, 0u);
-      const unsigned int w_end = __ldg(&druns[min(j + 32, n_entries)].x);  // first slot behind this window
+      if (!first_window) {
+        const long long jj = j + lane;
+        e = jj < n_entries ? __ldg(druns + jj) : make_uint2(0xffffffffu, 0u);
+        w_end = __ldg(&druns[min(j + 32, n_entries)].x);
+      }
+      first_window = false;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const unsigned int s = base + r * 32 + lane;
