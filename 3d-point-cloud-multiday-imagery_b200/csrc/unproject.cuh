@@ -153,17 +153,21 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Points of all tiles before tile t (warp-collective).  Flag and value share one 64-bit word, so
-// no fence is involved: a word is either not there yet, an aggregate or a prefix.
+// Points of all super-tiles before super-tile t (warp-collective).  Flag and value share one 64-bit
+// word, so no fence is involved: a word is either not there yet, an aggregate or a prefix.  Every
+// lane requests kLookWin status words at once, so ONE round trip covers the 32 * kLookWin
+// predecessors of t -- about as many as there are tickets in flight without a prefix yet; walking
+// back one window of 32 per round trip made the look-back the longest phase of the kernel.
+constexpr int kLookWin = 8;
+
 __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* status, long long t, unsigned int cnt,
                                                             int lane, unsigned int* fault) {
   if (lane == 0 && t > 0) st_status(status + t, kStAggregate | cnt);
   unsigned long long excl = 0ull;
   const long long t0 = clock64();
-  for (long long j = t - 1;; j -= 32) {
-    const long long jj = j - lane;
-    unsigned long long s;
-    unsigned int first_pre, invalid;
+  for (long long base = t - 1;; base -= 32 * kLookWin) {
+    unsigned long long acc;
+    int state;  // 0: no prefix in these windows, 1: reached a prefix, 2: a word is missing, ask again
     do {
       // bounded wait (about 4 s): every predecessor holds an earlier ticket, so it is running or done
       // and this never triggers; if it ever did, a flagged failure beats a hung GPU
@@ -171,20 +175,36 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* 
         if (lane == 0) atomicExch(fault, 1u);
         return 0ull;
       }
-      s = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
-      const unsigned int flag = (unsigned int)(s >> 62);
-      const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
-      first_pre = pre ? (unsigned int)__ffs(pre) - 1u : 32u;
-      // every tile between t and the nearest prefix must have published its aggregate
-      const unsigned int need = first_pre < 32u ? ((2u << first_pre) - 1u) : 0xffffffffu;
-      invalid = __ballot_sync(0xffffffffu, flag == 0u) & need;
-    } while (invalid);
-    const unsigned int agg = __reduce_add_sync(0xffffffffu, (unsigned int)lane < first_pre ? (unsigned int)(s & kStValue) : 0u);
-    excl += agg;
-    if (first_pre < 32u) {
-      excl += __shfl_sync(0xffffffffu, s, first_pre) & kStValue;
-      break;
-    }
+      unsigned long long s[kLookWin];
+#pragma unroll
+      for (int i = 0; i < kLookWin; ++i) {
+        const long long jj = base - (i * 32 + lane);
+        s[i] = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
+      }
+      acc = 0ull;
+      state = 0;
+#pragma unroll
+      for (int i = 0; i < kLookWin; ++i) {
+        if (state == 0) {  // warp-uniform
+          const unsigned int flag = (unsigned int)(s[i] >> 62);
+          const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
+          const unsigned int first_pre = pre ? (unsigned int)__ffs(pre) - 1u : 32u;
+          // every tile between t and the nearest prefix must have published its aggregate
+          const unsigned int need = first_pre < 32u ? ((2u << first_pre) - 1u) : 0xffffffffu;
+          if (__ballot_sync(0xffffffffu, flag == 0u) & need) {
+            state = 2;
+          } else {
+            acc += __reduce_add_sync(0xffffffffu, (unsigned int)lane < first_pre ? (unsigned int)(s[i] & kStValue) : 0u);
+            if (first_pre < 32u) {
+              acc += __shfl_sync(0xffffffffu, s[i], first_pre) & kStValue;
+              state = 1;
+            }
+          }
+        }
+      }
+    } while (state == 2);
+    excl += acc;
+    if (state == 1) break;
   }
   if (lane == 0) st_status(status + t, kStPrefix | (excl + cnt));
   return excl;
