@@ -1183,12 +1183,10 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
   up.hm = d_hm; up.mask = d_mask;
   up.pix_begin = pix_begin; up.pix_count = pix_count; up.HW = HW; up.W = W; up.H = H;
   up.dtype = hm_dtype;
-  up.vec_ok = ((reinterpret_cast<uintptr_t>(d_hm) & 15) == 0) && (!d_mask || (reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
   up.scale = hm_scale; up.max_abs = max_abs;
   up.chunk_offsets = h->chunk_offsets.p;
   up.status = h->tile_status.p;
   up.ticket = reinterpret_cast<unsigned int*>(h->tile_status.p + n_super);
-  CU(cudaFuncSetAttribute(unproject_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
   up.pts = h->pts.p;
   up.planes = nullptr;
   up.day0 = (int)(pix_begin / HW);
@@ -1291,10 +1289,20 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
         up.tile_end = std::min<long long>(c_end * (kChunk / kTile), n_tiles);
         up.total_out = h->slab_totals.p + s + 1;
         const long long nt = up.tile_end - up.tile_begin;
-        const int g = grid_for(h, (nt + kSuper - 1) / kSuper, 4);  // 48 KB of staging per CTA
+        const int g = grid_for(h, (nt + kSuper - 1) / kSuper, MDKM_UNPROJ_CTAS);  // resident CTAs per SM (register budget)
         if (s > 0) CU(cudaMemsetAsync(up.ticket, 0, 4, h->stream));
         const int span = prof_begin(h, MDKM_PHASE_UNPROJECT, std::min<long long>(c_end * kChunk, pix_count) - done_chunks * kChunk);
-        unproject_fused_kernel<<<g, kThreads, kFusedSmem, h->stream>>>(up);
+        // row / day bookkeeping per step when a step of 32 pixels never straddles a raster row
+        const int mode = (W % 32 == 0 && pix_begin % 32 == 0) ? 0 : (W >= 32 ? 1 : 2);
+        if (up.planes) {
+          if (mode == 0) unproject_fused_kernel<0, true><<<g, kThreads, 0, h->stream>>>(up);
+          else if (mode == 1) unproject_fused_kernel<1, true><<<g, kThreads, 0, h->stream>>>(up);
+          else unproject_fused_kernel<2, true><<<g, kThreads, 0, h->stream>>>(up);
+        } else {
+          if (mode == 0) unproject_fused_kernel<0, false><<<g, kThreads, 0, h->stream>>>(up);
+          else if (mode == 1) unproject_fused_kernel<1, false><<<g, kThreads, 0, h->stream>>>(up);
+          else unproject_fused_kernel<2, false><<<g, kThreads, 0, h->stream>>>(up);
+        }
         prof_end(h, span);
         ++h->launches;
         if (cloud_out) {

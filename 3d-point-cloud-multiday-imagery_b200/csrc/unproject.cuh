@@ -7,13 +7,14 @@
 // reference).
 //
 // ONE pass over the rasters (4 B read + 12 B written per pixel, the algorithmic minimum): a warp
-// takes a tile of kTile = 1024 consecutive pixels (8 rounds of 32 lanes x 4 px, 16 B loads),
-// ranks its valid pixels with ballots, parks them in shared memory, obtains the number of
-// points of all earlier tiles by a decoupled look-back over per-tile status words (tiles are
-// handed out by a ticket counter, so every predecessor of a running tile is itself running or
-// done), and writes x, y, z as contiguous runs at offset + rank -- the output order is exactly
-// np.where's.  Offsets at every kChunk = 4096 pixels are kept for the day boundaries.  (The
-// look-back works on super-tiles of eight warp tiles -- one CTA -- see unproject_fused_kernel.)
+// takes a tile of kTile = 1024 consecutive pixels, one pixel per lane and step (heights and validity
+// bits in registers), counts its valid pixels, obtains the number of points of all earlier tiles by
+// a decoupled look-back over status words (tiles are handed out by a ticket counter, so every
+// predecessor of a running tile is itself running or done; the look-back works on super-tiles of
+// eight warp tiles = one CTA), and stores x, y, z at offset + rank, step by step -- dense 128-byte
+// runs in exactly np.where's order.  The loop is software-pipelined (the next super-tile is loaded
+// and announced before the look-back of the current one): the pass is bound by HBM, not by the
+// look-back chain.  Offsets at every kChunk = 4096 pixels are kept for the day boundaries.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -21,8 +22,15 @@
 namespace mdkm {
 
 constexpr int kChunk = 4096;
-constexpr int kTile = 1024;  // pixels per warp tile of the fused pass
-constexpr int kFusedSmem = (kThreads / 32) * kTile * 6;  // dynamic shared memory of unproject_fused_kernel
+// (measured on config 2, 41.9 M pixels: 1024-pixel tiles with two 256-thread CTAs of 127-register
+// threads per SM 0.160 ms; 512-pixel tiles with four CTAs of 64 registers 0.164 ms)
+#ifndef MDKM_TILE
+#define MDKM_TILE 1024
+#endif
+#ifndef MDKM_UNPROJ_CTAS
+#define MDKM_UNPROJ_CTAS 2
+#endif
+constexpr int kTile = MDKM_TILE;  // pixels per warp tile of the fused pass
 // per-tile status word of the decoupled look-back: flag in the two top bits, count below
 constexpr unsigned long long kStAggregate = 1ull << 62;  // value = valid pixels of this tile
 constexpr unsigned long long kStPrefix = 2ull << 62;     // value = valid pixels up to and including this tile
@@ -36,7 +44,6 @@ struct UnprojParams {
   long long HW;
   int W, H;
   int dtype;              // MDKM_HM_F32 / MDKM_HM_I16 / MDKM_HM_F32_GTIFF3
-  int vec_ok;             // hm (and mask) aligned for 16 B / 4 B vector loads
   float scale;            // for I16
   float max_abs;
   long long* chunk_offsets;  // [n_chunks]: points produced before every kChunk-th pixel of the range
@@ -75,71 +82,6 @@ __device__ __forceinline__ bool load_height1(const UnprojParams& p, long long i,
   return ok;
 }
 
-// Loads 4 consecutive pixel heights starting at local index i (i % 4 == 0); invalid -> NaN.
-__device__ __forceinline__ void load_heights4(const UnprojParams& p, long long i, float (&h)[4],
-                                              unsigned int& valid_bits) {
-  valid_bits = 0;
-  const bool full = (i + 3 < p.pix_count);
-  if (p.dtype == 0) {
-    const float* src = reinterpret_cast<const float*>(p.hm);
-    if (full && p.vec_ok) {
-      const float4 v = ldg_stream_f4(src + i);
-      h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = (i + e < p.pix_count) ? __ldg(src + i + e) : __int_as_float(0x7fc00000);
-    }
-  } else if (p.dtype == 1) {
-    const short* src = reinterpret_cast<const short*>(p.hm);
-    if (full && p.vec_ok) {
-      const uint2 v = ldg_stream_u64(src + i);
-      h[0] = p.scale * (float)(short)(v.x & 0xffff);
-      h[1] = p.scale * (float)(short)(v.x >> 16);
-      h[2] = p.scale * (float)(short)(v.y & 0xffff);
-      h[3] = p.scale * (float)(short)(v.y >> 16);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        h[e] = (i + e < p.pix_count) ? p.scale * (float)__ldg(src + i + e) : __int_as_float(0x7fc00000);
-    }
-  } else {
-    // 4 pixels = 12 floats (h a d | h a d | h a d | h a d): three aligned 16 B loads
-    const float* src = reinterpret_cast<const float*>(p.hm) + 3 * i;
-    float d[4];
-    if (full && p.vec_ok) {
-      const float4 v0 = ldg_stream_f4(src), v1 = ldg_stream_f4(src + 4), v2 = ldg_stream_f4(src + 8);
-      h[0] = v0.x; d[0] = v0.z; h[1] = v0.w; d[1] = v1.y; h[2] = v1.z; d[2] = v2.x; h[3] = v2.y; d[3] = v2.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool in = i + e < p.pix_count;
-        h[e] = in ? __ldg(src + 3 * e) : __int_as_float(0x7fc00000);
-        d[e] = in ? __ldg(src + 3 * e + 2) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (d[e] == 0.f) h[e] = __int_as_float(0x7fc00000);  // not `final_defined` -> nodata
-  }
-  unsigned int m4 = 0x01010101u;
-  if (p.mask) {
-    if (full && p.vec_ok) {
-      m4 = ldg_stream_u32(p.mask + i);
-    } else {
-      m4 = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (i + e < p.pix_count && __ldg(p.mask + i + e)) m4 |= (1u << (8 * e));
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    // plugin.py:151-152: isfinite(h) & (|h| <= limit) & validity_mask
-    const bool ok = (i + e < p.pix_count) && (fabsf(h[e]) <= p.max_abs) && ((m4 >> (8 * e)) & 0xff);
-    valid_bits |= ok ? (1u << e) : 0u;  // NaN and inf fail the <= test
-  }
-}
-
 __device__ __forceinline__ unsigned int f2ord(float f) {
   const unsigned int b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -153,21 +95,20 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Points of all super-tiles before super-tile t (warp-collective).  Flag and value share one 64-bit
-// word, so no fence is involved: a word is either not there yet, an aggregate or a prefix.  Every
-// lane requests kLookWin status words at once, so ONE round trip covers the 32 * kLookWin
-// predecessors of t -- about as many as there are tickets in flight without a prefix yet; walking
-// back one window of 32 per round trip made the look-back the longest phase of the kernel.
-constexpr int kLookWin = 8;
-
-__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* status, long long t, unsigned int cnt,
+// Points of all super-tiles before super-tile t (warp-collective; the super-tile's own aggregate has
+// been published by the caller).  Flag and value share one 64-bit status word, so no fence is
+// involved: a word is either not there yet, an aggregate or a prefix.
+__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* status, long long t, unsigned int agg,
                                                             int lane, unsigned int* fault) {
-  if (lane == 0 && t > 0) st_status(status + t, kStAggregate | cnt);
+#ifdef MDKM_NO_LOOKBACK  // timing experiment only (wrong offsets): the pass without its look-back
+  return (unsigned long long)t * ((kThreads / 32) * kTile);
+#endif
   unsigned long long excl = 0ull;
   const long long t0 = clock64();
-  for (long long base = t - 1;; base -= 32 * kLookWin) {
-    unsigned long long acc;
-    int state;  // 0: no prefix in these windows, 1: reached a prefix, 2: a word is missing, ask again
+  for (long long j = t - 1;; j -= 32) {
+    const long long jj = j - lane;
+    unsigned long long s;
+    unsigned int first_pre, invalid;
     do {
       // bounded wait (about 4 s): every predecessor holds an earlier ticket, so it is running or done
       // and this never triggers; if it ever did, a flagged failure beats a hung GPU
@@ -175,199 +116,258 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long* 
         if (lane == 0) atomicExch(fault, 1u);
         return 0ull;
       }
-      unsigned long long s[kLookWin];
-#pragma unroll
-      for (int i = 0; i < kLookWin; ++i) {
-        const long long jj = base - (i * 32 + lane);
-        s[i] = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
-      }
-      acc = 0ull;
-      state = 0;
-#pragma unroll
-      for (int i = 0; i < kLookWin; ++i) {
-        if (state == 0) {  // warp-uniform
-          const unsigned int flag = (unsigned int)(s[i] >> 62);
-          const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
-          const unsigned int first_pre = pre ? (unsigned int)__ffs(pre) - 1u : 32u;
-          // every tile between t and the nearest prefix must have published its aggregate
-          const unsigned int need = first_pre < 32u ? ((2u << first_pre) - 1u) : 0xffffffffu;
-          if (__ballot_sync(0xffffffffu, flag == 0u) & need) {
-            state = 2;
-          } else {
-            acc += __reduce_add_sync(0xffffffffu, (unsigned int)lane < first_pre ? (unsigned int)(s[i] & kStValue) : 0u);
-            if (first_pre < 32u) {
-              acc += __shfl_sync(0xffffffffu, s[i], first_pre) & kStValue;
-              state = 1;
-            }
-          }
-        }
-      }
-    } while (state == 2);
-    excl += acc;
-    if (state == 1) break;
+      s = jj >= 0 ? ld_status(status + jj) : kStPrefix;  // before tile 0: a prefix of zero points
+      const unsigned int flag = (unsigned int)(s >> 62);
+      const unsigned int pre = __ballot_sync(0xffffffffu, flag == 2u);
+      first_pre = pre ? (unsigned int)__ffs(pre) - 1u : 32u;
+      // every tile between t and the nearest prefix must have published its aggregate
+      const unsigned int need = first_pre < 32u ? ((2u << first_pre) - 1u) : 0xffffffffu;
+      invalid = __ballot_sync(0xffffffffu, flag == 0u) & need;
+    } while (invalid);
+    excl += __reduce_add_sync(0xffffffffu, (unsigned int)lane < first_pre ? (unsigned int)(s & kStValue) : 0u);
+    if (first_pre < 32u) {
+      excl += __shfl_sync(0xffffffffu, s, first_pre) & kStValue;
+      break;
+    }
   }
-  if (lane == 0) st_status(status + t, kStPrefix | (excl + cnt));
+  if (lane == 0) st_status(status + t, kStPrefix | (excl + agg));
   return excl;
 }
 
-// Raster position (and detrended height) of the pixel `pix` of a tile whose first pixel sits at
-// (day0, row0, col0): 32-bit arithmetic, no division for rasters at least a tile wide.
-struct TilePos {
-  unsigned int col0, row0, W, H;
-  int day0, plane_day0;
-  const double* planes;
-};
-__device__ __forceinline__ void tile_point(const TilePos& t, unsigned int pix, const float* wz, float& fx, float& fy,
-                                           float& zz) {
-  unsigned int col = t.col0 + pix, row = t.row0;
-  int dcur = t.day0;
-  if (t.W >= (unsigned int)kTile) {  // at most one row boundary inside the tile
-    if (col >= t.W) { col -= t.W; ++row; }
-  } else {
-    const unsigned int q = col / t.W;
-    col -= q * t.W;
-    row += q;
-  }
-  while (row >= t.H) {  // a tile may run into the next day(s)
-    row -= t.H;
-    ++dcur;
-  }
-  zz = wz[pix];
-  if (t.planes) {
-    // plugin.py:171: height_rel = dot(P - center, normal)
-    const double* pl = t.planes + (size_t)(dcur - t.plane_day0) * 8;
-    zz = (float)(((double)col - pl[0]) * pl[3] + ((double)row - pl[1]) * pl[4] + ((double)zz - pl[2]) * pl[5]);
-  }
-  fx = (float)col;
-  fy = (float)row;
+// plugin.py:171: height_rel = dot(P - center, normal), in a fixed evaluation order
+__device__ __forceinline__ float plane_height(const double* __restrict__ pl, unsigned int col, unsigned int row, float z) {
+  double v = __dmul_rn((double)z - pl[2], pl[5]);
+  v = __fma_rn((double)row - pl[1], pl[4], v);
+  v = __fma_rn((double)col - pl[0], pl[3], v);
+  return (float)v;
 }
 
-// One CTA takes a super-tile of kThreads / 32 = 8 consecutive warp tiles per ticket: the warps rank
-// their tiles independently, ONE look-back per super-tile (by warp 0) yields the CTA's offset, and
-// the warps' own offsets follow from the eight counts in shared memory.  The look-back depth is
-// bounded by the number of resident CTAs (a few hundred), not by the number of resident warps.
-__global__ void __launch_bounds__(kThreads) unproject_fused_kernel(const UnprojParams p) {
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned int ldg_stream_u16(const void* p) {
+  unsigned short r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned int ldg_stream_u8(const void* p) {
+  unsigned int r;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// One tile's pixels: heights into registers (all loads of a lane in flight at once), validity
+// (plugin.py:151-152: isfinite(h) & (|h| <= limit) & validity_mask; NaN and inf fail the <= test)
+// as one bit per step.  `limit` = pixels of the tile inside the range.
+template <int kSteps>
+__device__ __forceinline__ void load_tile(const UnprojParams& p, long long pix0, int lane, float (&hv)[kSteps],
+                                          unsigned int& vmask, unsigned int& limit) {
+  const long long left = p.pix_count - pix0;
+  limit = left < (long long)(kSteps * 32) ? (unsigned int)left : (unsigned int)(kSteps * 32);
+  // (the mask bytes first: folded into one word before the heights are requested, so that only
+  // one set of loads occupies registers at a time)
+  unsigned int keep = 0xffffffffu;
+  if (p.mask) {
+    const uint8_t* ms = p.mask + pix0 + lane;
+    unsigned int mb[kSteps];
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) mb[s] = (unsigned int)(s * 32 + lane) < limit ? ldg_stream_u8(ms + s * 32) : 0u;
+    keep = 0u;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) keep |= mb[s] ? (1u << s) : 0u;
+  }
+  if (p.dtype == 0) {
+    const float* src = reinterpret_cast<const float*>(p.hm) + pix0 + lane;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+      hv[s] = (unsigned int)(s * 32 + lane) < limit ? ldg_stream_f32(src + s * 32) : __int_as_float(0x7fc00000);
+  } else if (p.dtype == 1) {
+    const short* src = reinterpret_cast<const short*>(p.hm) + pix0 + lane;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+      hv[s] = (unsigned int)(s * 32 + lane) < limit ? p.scale * (float)(short)ldg_stream_u16(src + s * 32)
+                                                      : __int_as_float(0x7fc00000);
+  } else {
+    // the reference's own 5-out-F.tif: (height, -, final_defined) per pixel; `final_defined`
+    // first, folded into the keep bits like the mask
+    const float* src = reinterpret_cast<const float*>(p.hm) + 3 * (pix0 + lane);
+    {
+      float dd[kSteps];
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s) dd[s] = (unsigned int)(s * 32 + lane) < limit ? ldg_stream_f32(src + 3 * s * 32 + 2) : 0.f;
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s) keep &= dd[s] != 0.f ? 0xffffffffu : ~(1u << s);  // not `final_defined` -> nodata
+    }
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+      hv[s] = (unsigned int)(s * 32 + lane) < limit ? ldg_stream_f32(src + 3 * s * 32) : __int_as_float(0x7fc00000);
+  }
+  vmask = 0;
+#pragma unroll
+  for (int s = 0; s < kSteps; ++s) vmask |= (fabsf(hv[s]) <= p.max_abs) ? (1u << s) : 0u;  // (outside the range: NaN)
+  vmask &= keep;
+}
+
+// The fused pass.  A warp takes a tile of kTile consecutive pixels as kSteps steps of 32 pixels, ONE
+// pixel per lane and step (coalesced 128-byte requests, all of a lane's loads in flight at once);
+// heights and validity bits stay in registers.  A CTA takes a super-tile of 8 warp tiles per ticket:
+// the warps count their valid pixels (one POPC + one REDUX), the super-tile's aggregate is published,
+// ONE look-back per super-tile (by warp 0) yields the CTA's offset -- its depth is bounded by the
+// number of resident CTAs -- and the warps' own offsets follow from the eight counts in shared
+// memory.  Then every step ranks its valid pixels with one ballot and the lanes store x, y, z at
+// offset + rank: the 32 outputs of a step are consecutive, so the scalar stores of a step form dense
+// 128-byte runs, in np.where's order.  No staging in shared memory, no index list.
+//
+// The loop is software-pipelined: the NEXT super-tile is requested, counted and its aggregate
+// published BEFORE the look-back of the current one, so the wait for the predecessors' status words
+// overlaps the next tile's DRAM latency, and no aggregate ever waits for a look-back.
+//
+// kMode 0: W and pix_begin are multiples of 32 -- a step never straddles a raster row, the row / day
+//          bookkeeping is per step (warp-uniform);
+//       1: W >= 32 -- at most one row boundary inside a step;
+//       2: any W (per-pixel division).
+template <int kMode, bool kPlanes>
+__global__ void __launch_bounds__(kThreads, MDKM_UNPROJ_CTAS) unproject_fused_kernel(const UnprojParams p) {
   constexpr int kWarps = kThreads / 32;
-  extern __shared__ __align__(16) unsigned char s_stage[];  // kFusedSmem bytes: heights [8][1024] f32 (pixel order), valid-pixel lists [8][1024] u16
-  __shared__ unsigned int s_cnt[kWarps];
+  constexpr int kSteps = kTile / 32;
+  static_assert(kSteps <= 32, "one validity bit per step in a 32-bit word");
+  __shared__ unsigned int s_cnt[2][kWarps];
   __shared__ unsigned long long s_base;
   __shared__ long long s_super;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* wz = reinterpret_cast<float*>(s_stage) + warp * kTile;
-  unsigned short* wix = reinterpret_cast<unsigned short*>(s_stage + kWarps * kTile * 4) + warp * kTile;
-  // bounding box of the points this warp writes (the frame of the cloud needs it: no extra pass)
+  const unsigned int lt = (1u << lane) - 1u;
+  // bounding box of the points this thread writes (the frame of the cloud needs it: no extra pass)
   float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
   float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
   const long long super_begin = p.tile_begin / kWarps;  // (launch boundaries are whole super-tiles)
-  while (true) {
+  const unsigned int W = (unsigned int)p.W, H = (unsigned int)p.H;
+
+  // prologue: the first super-tile of this CTA, counted and announced
+  if (threadIdx.x == 0) s_super = super_begin + (long long)atomicAdd(p.ticket, 1u);
+  __syncthreads();
+  long long sup = s_super;
+  float hv[kSteps];
+  unsigned int vmask = 0, limit = 0, cnt = 0;
+  bool have = sup * kWarps < p.tile_end;  // CTA-uniform
+  if (have) {
+    if (sup * kWarps + warp < p.tile_end) load_tile<kSteps>(p, (sup * kWarps + warp) * kTile, lane, hv, vmask, limit);
+    cnt = __reduce_add_sync(0xffffffffu, (unsigned int)__popc(vmask));
+    if (lane == 0) s_cnt[0][warp] = cnt;
+  }
+  __syncthreads();  // (also: everybody has read s_super)
+  if (have && threadIdx.x == 0 && sup > 0) {
+    unsigned int agg = 0;
+    for (int w = 0; w < kWarps; ++w) agg += s_cnt[0][w];
+    st_status(p.status + sup, kStAggregate | agg);
+  }
+  for (int par = 0; have; par ^= 1) {
+    // 1. the next super-tile: ticket, pixels, counts, aggregate -- before this one's look-back
     if (threadIdx.x == 0) s_super = super_begin + (long long)atomicAdd(p.ticket, 1u);
     __syncthreads();
-    const long long sup = s_super;
-    if (sup * kWarps >= p.tile_end) break;  // CTA-uniform
-    const long long t = sup * kWarps + warp;
-    const bool active = t < p.tile_end;     // warp-uniform
-    const long long pix0 = t * kTile;  // local index of the tile's first pixel
-    unsigned int cnt = 0;
-    unsigned int head[kTile / 128];  // rank of this lane's first pixel of round r
-    if (active) {
-    // 1. the tile's pixels: 8 x 16 B per lane in flight; the heights are parked in shared memory
-    // in PIXEL order at once (the registers are free again), only the validity bits stay
-    unsigned int vbits = 0;  // 4 bits per round
-#pragma unroll
-    for (int r = 0; r < kTile / 128; ++r) {
-      float hv[4];
-      unsigned int vb;
-      load_heights4(p, pix0 + r * 128 + lane * 4, hv, vb);
-      *reinterpret_cast<float4*>(wz + r * 128 + lane * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      vbits |= vb << (4 * r);
+    const long long sup_n = s_super;
+    const bool have_n = sup_n * kWarps < p.tile_end;  // CTA-uniform
+    float hn[kSteps];
+    unsigned int vmask_n = 0, limit_n = 0, cnt_n = 0;
+    if (have_n) {
+      if (sup_n * kWarps + warp < p.tile_end) load_tile<kSteps>(p, (sup_n * kWarps + warp) * kTile, lane, hn, vmask_n, limit_n);
+      cnt_n = __reduce_add_sync(0xffffffffu, (unsigned int)__popc(vmask_n));
+      if (lane == 0) s_cnt[par ^ 1][warp] = cnt_n;
     }
-    // 2. rank of every valid pixel inside the tile, in pixel order: the list of valid pixels
-#pragma unroll
-    for (int r = 0; r < kTile / 128; ++r) {
-      const unsigned int lt = (1u << lane) - 1u;
-      const unsigned int vb = (vbits >> (4 * r)) & 0xfu;
-      unsigned int before = 0, total = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned int m = __ballot_sync(0xffffffffu, (vb >> e) & 1u);
-        before += __popc(m & lt);
-        total += __popc(m);
-      }
-      head[r] = cnt + before;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if ((vb >> e) & 1u) wix[head[r] + __popc(vb & ((1u << e) - 1u))] = (unsigned short)(r * 128 + lane * 4 + e);
-      cnt += total;
-    }
-    }  // active
-    if (lane == 0) s_cnt[warp] = cnt;
-    __syncthreads();
-    // 4. points of all earlier super-tiles (one look-back per CTA), then of the earlier warps
+    __syncthreads();  // (also: everybody has read s_super)
+    // 2. points of all earlier super-tiles (one look-back per CTA), then of the earlier warps
     if (warp == 0) {
-      const unsigned int agg = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_cnt[lane] : 0u);
+      if (have_n) {
+        const unsigned int agg_n = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_cnt[par ^ 1][lane] : 0u);
+        if (lane == 0) st_status(p.status + sup_n, kStAggregate | agg_n);
+      }
+      const unsigned int agg = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_cnt[par][lane] : 0u);
       const unsigned long long base = tile_lookback(p.status, sup, agg, lane, p.ticket + 1);
       if (lane == 0) s_base = base;
     }
     __syncthreads();
-    if (!active) continue;
-    unsigned long long excl = s_base;
-    for (int w = 0; w < warp; ++w) excl += s_cnt[w];
-    if (lane == 0) {
-      if ((t & (kChunk / kTile - 1)) == 0) p.chunk_offsets[t / (kChunk / kTile)] = (long long)excl;
-      if (t == p.tile_end - 1 && p.total_out) *p.total_out = (long long)(excl + cnt);
-    }
-    if (p.run_src && (lane & 1) == 0) {
+    const long long t = sup * kWarps + warp;
+    if (t < p.tile_end) {  // warp-uniform
+      const long long pix0 = t * kTile;  // local index of the tile's first pixel
+      unsigned long long excl = s_base;
+      for (int w = 0; w < warp; ++w) excl += s_cnt[par][w];
+      if (lane == 0) {
+        if ((t & (kChunk / kTile - 1)) == 0) p.chunk_offsets[t / (kChunk / kTile)] = (long long)excl;
+        if (t == p.tile_end - 1 && p.total_out) *p.total_out = (long long)(excl + cnt);
+      }
+      // 3. x, y, z of the valid pixels at offset + rank.  Position of the tile's first pixel once per
+      // tile (64-bit); per step / pixel only 32-bit arithmetic
+      const long long gp0 = p.pix_begin + pix0;
+      const long long day0 = gp0 / p.HW;
+      const long long rem0 = gp0 - day0 * p.HW;
+      unsigned int rowb = (unsigned int)(rem0 / p.W);                 // row, column, day of the step's first pixel
+      unsigned int cb = (unsigned int)(rem0 - (long long)rowb * p.W);
+      int dayb = (int)(day0 - p.day0);
+      // (offsets inside the cloud relative to the block of the tile's first output: 32-bit)
+      float* const tile_dst = p.pts + (long long)(excl >> 7) * kBlockFloats;
+      unsigned int rel = (unsigned int)(excl & 127ull);                // offset of the step's first output
+      const unsigned int run_base = (unsigned int)excl - rel;
+      unsigned int* const run_dst = p.run_src ? p.run_src + (pix0 >> 3) + (lane >> 3) : nullptr;
 #pragma unroll
-      for (int r = 0; r < kTile / 128; ++r) {
-        const long long o = pix0 + r * 128 + lane * 4;  // a multiple of 8
-        if (o < p.pix_count) p.run_src[o >> 3] = (unsigned int)(excl + head[r]);
+      for (int s = 0; s < kSteps; ++s) {
+        const bool ok = (vmask >> s) & 1u;
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        const unsigned int o = rel + (unsigned int)__popc(m & lt);
+        unsigned int col = cb + (unsigned int)lane, row = rowb;
+        int day = dayb;
+        if (kMode == 1) {
+          if (col >= W) {
+            col -= W;
+            if (++row == H) { row = 0; ++day; }
+          }
+        } else if (kMode == 2) {
+          const unsigned int q = col / W;
+          col -= q * W;
+          row += q;
+          while (row >= H) { row -= H; ++day; }
+        }
+        if (ok) {
+          float z = hv[s];
+          if (kPlanes) z = plane_height(p.planes + (size_t)day * 8, col, row, z);
+          const float fx = (float)col, fy = (float)row;
+          float* dst = tile_dst + (o >> 7) * (unsigned int)kBlockFloats + (o & 127u);
+          dst[0] = fx;
+          dst[kGroup] = fy;
+          dst[2 * kGroup] = z;
+          mn[0] = fminf(mn[0], fx); mx[0] = fmaxf(mx[0], fx);
+          mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
+          mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+        }
+        // run table: points produced before every 8th pixel of the range
+        if (run_dst && (lane & 7) == 0 && (unsigned int)(s * 32 + lane) < limit) run_dst[s * 4] = run_base + o;
+        rel += (unsigned int)__popc(m);
+        // first pixel of the next step
+        cb += 32u;
+        if (kMode == 0) {
+          if (cb >= W) {  // (== W: a step never straddles a row)
+            cb = 0;
+            if (++rowb == H) { rowb = 0; ++dayb; }
+          }
+        } else if (kMode == 1) {
+          if (cb >= W) {
+            cb -= W;
+            if (++rowb == H) { rowb = 0; ++dayb; }
+          }
+        } else {
+          const unsigned int q = cb / W;
+          cb -= q * W;
+          rowb += q;
+          while (rowb >= H) { rowb -= H; ++dayb; }
+        }
       }
     }
-    // 5. contiguous runs of x, y, z.  Position of the tile's first pixel once per tile (64-bit);
-    // per point only 32-bit arithmetic, and no division at all for rasters at least a tile wide
-    const long long gp0 = p.pix_begin + pix0;
-    const long long day0 = gp0 / p.HW;
-    const long long rem0 = gp0 - day0 * p.HW;
-    const unsigned int row0 = (unsigned int)(rem0 / p.W);
-    const unsigned int col0 = (unsigned int)(rem0 - (long long)row0 * p.W);
-    const unsigned int W = (unsigned int)p.W, H = (unsigned int)p.H;
-    const TilePos tp{col0, row0, W, H, (int)day0, p.day0, p.planes};
-    // outputs [excl, excl + cnt): a few single points up to the next multiple of four, then four
-    // consecutive points per lane and round as three 16-byte stores (a block of the cloud holds
-    // 128 points, so an aligned quad never straddles two blocks), then the rest
-    const unsigned int lead = min(cnt, (4u - (unsigned int)(excl & 3ull)) & 3u);
-    const unsigned int quads = (cnt - lead) >> 2;
-    for (unsigned int j = lane; j < quads; j += 32) {
-      const unsigned int i = lead + 4u * j;
-      float4 vx, vy, vz;
-      tile_point(tp, wix[i + 0], wz, vx.x, vy.x, vz.x);
-      tile_point(tp, wix[i + 1], wz, vx.y, vy.y, vz.y);
-      tile_point(tp, wix[i + 2], wz, vx.z, vy.z, vz.z);
-      tile_point(tp, wix[i + 3], wz, vx.w, vy.w, vz.w);
-      float* dst = p.pts + pt_off((long long)excl + i);
-      *reinterpret_cast<float4*>(dst) = vx;
-      *reinterpret_cast<float4*>(dst + kGroup) = vy;
-      *reinterpret_cast<float4*>(dst + 2 * kGroup) = vz;
-      mn[0] = fminf(fminf(mn[0], vx.x), fminf(fminf(vx.y, vx.z), vx.w)); mx[0] = fmaxf(fmaxf(mx[0], vx.x), fmaxf(fmaxf(vx.y, vx.z), vx.w));
-      mn[1] = fminf(fminf(mn[1], vy.x), fminf(fminf(vy.y, vy.z), vy.w)); mx[1] = fmaxf(fmaxf(mx[1], vy.x), fmaxf(fmaxf(vy.y, vy.z), vy.w));
-      mn[2] = fminf(fminf(mn[2], vz.x), fminf(fminf(vz.y, vz.z), vz.w)); mx[2] = fmaxf(fmaxf(mx[2], vz.x), fmaxf(fmaxf(vz.y, vz.z), vz.w));
-    }
-    {  // the (at most 3 + 3) points before and behind the quads: one lane each
-      const unsigned int tail0 = lead + 4u * quads;
-      const unsigned int n_single = lead + (cnt - tail0);
-      if ((unsigned int)lane < n_single) {
-        const unsigned int i = (unsigned int)lane < lead ? (unsigned int)lane : tail0 + ((unsigned int)lane - lead);
-        float fx, fy, zz;
-        tile_point(tp, wix[i], wz, fx, fy, zz);
-        float* dst = p.pts + pt_off((long long)excl + i);
-        dst[0] = fx;
-        dst[kGroup] = fy;
-        dst[2 * kGroup] = zz;
-        mn[0] = fminf(mn[0], fx); mx[0] = fmaxf(mx[0], fx);
-        mn[1] = fminf(mn[1], fy); mx[1] = fmaxf(mx[1], fy);
-        mn[2] = fminf(mn[2], zz); mx[2] = fmaxf(mx[2], zz);
-      }
-    }
+    // 4. the next super-tile becomes the current one
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) hv[s] = hn[s];
+    vmask = vmask_n; limit = limit_n; cnt = cnt_n;
+    sup = sup_n;
+    have = have_n;
   }
   if (p.minmax) {
 #pragma unroll

@@ -457,7 +457,7 @@ def run_mine(args):
                               "step_kernels": ph["step"][0] / n_prof, "final_labels_inertia": ph["final"][0] / n_prof,
                               "fit_total": ms_total / args.steps},
         "unproject": {
-            "kernels": "unproject_count + scan_chunks + unproject_scatter on device-resident rasters",
+            "kernels": "unproject_fused_kernel (one pass: validity, rank, decoupled look-back, x/y/z runs) on device-resident rasters",
             "ms": un_ms / 4, "pixels": un_px // 4,
             "achieved": ALGO_BYTES_PER_PIXEL_UNPROJECT * (un_px / 4) / (un_ms / 4 * 1e-3) / 1e9 if un_ms > 0 else None,
             "frac": (ALGO_BYTES_PER_PIXEL_UNPROJECT * (un_px / 4) / (un_ms / 4 * 1e-3) / 1e9 / peak) if un_ms > 0 else None,
