@@ -20,6 +20,7 @@ OPT_SETTLE_GROUPS = 1
 OPT_RASTER_MIRROR = 2
 OPT_CELL_PX, OPT_CELL_ROWS = 3, 4
 OPT_TWO_LEVEL = 5
+OPT_DEPENDENT_LAUNCH = 6
 PHASE_UNPROJECT, PHASE_BUILD, PHASE_STEP, PHASE_FINAL = 0, 1, 2, 3
 NCCL_UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64

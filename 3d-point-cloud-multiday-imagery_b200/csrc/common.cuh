@@ -35,6 +35,9 @@ struct DevStatus {
   int n_empty;    // empty clusters found by the last update
   int k;
   int first;      // 1 until the first step has run (labels_old = -1 in sklearn)
+  int pending;    // 1: the sums of E-step `last_seq` wait for their centroid update (applied by the next launch)
+  int last_seq;   // launch index (StepParams::seq) of the last E-step that ran: its sums sit in acc[last_seq % 3],
+                  // its table in table[last_seq & 1]
   unsigned long long n_changed;  // labels changed in the last step (global after allreduce)
   unsigned long long n_refined;  // point-iterations re-decided in float64 (this rank)
   unsigned long long n_relocated;
@@ -46,6 +49,8 @@ struct DevStatus {
   unsigned long long epoch;       // fused steps completed since the communicator was created
   int xchg_timeout;               // 1: a kernel-side wait (peer sums, grid barrier) timed out (fatal)
   unsigned int grid_bar;          // arrival counter of the step kernel's grid barrier
+  unsigned int upd_flag;          // (epoch << 2) | verdict of the deferred update CTA 0 applied for the grid (large tables)
+  float next_thresh;              // its error threshold (published with upd_flag)
   unsigned long long work_sum;    // groups handed to the per-point pass, summed over the fused steps of a fit
   // diagnostics (MDKM_TIMING builds only): globaltimer stamps of the last fused step, ns
   unsigned long long t_start, t_first_done, t_last_done, t_update_done, t_classify_start, t_classify_done;

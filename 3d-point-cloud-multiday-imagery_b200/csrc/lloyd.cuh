@@ -53,6 +53,7 @@ struct UpdateParams {
   unsigned char* table;     // centroid table, updated in place
   DevStatus* st;
   Frame fr;
+  double inv_scale[3];      // 1 / fr.scale (powers of two: multiplying is exact)
   double mean[3];           // data mean (only used for sklearn's empty-cluster copy quirk)
   int k, kpad;
   int allow_pause;          // 1: pause for relocation when a cluster is empty
@@ -82,9 +83,11 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
   return t;
 }
 
-// Buckets the k centroids of `table` by the x-y grid of common.cuh (for k >= kBucketMinK).
+// Buckets the k centroids whose fast rows are in `fast` (shared or global memory) by the x-y grid of
+// common.cuh (for k >= kBucketMinK) into the bucket section `sec` (shared or global memory).
 // Executed by all threads of ONE CTA right after that CTA wrote the fast rows.
-__device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int k, int kpad, const Frame& fr) {
+__device__ __forceinline__ void build_centroid_buckets(const float4* fast, unsigned char* sec, int k, int kpad,
+                                                       const Frame& fr) {
   if (k < kBucketMinK) return;
   __shared__ int s_cnt[32 * 32 + 1];
   const int g = bucket_g(k), cells = g * g, tid = threadIdx.x;
@@ -92,8 +95,6 @@ __device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int
   hdr.hx = (float)fr.halfrange[0]; hdr.hy = (float)fr.halfrange[1];
   hdr.inv_x = (float)g / (2.0f * fmaxf(hdr.hx, 1e-30f));
   hdr.inv_y = (float)g / (2.0f * fmaxf(hdr.hy, 1e-30f));
-  const float4* fast = reinterpret_cast<const float4*>(table);
-  unsigned char* sec = table + bucket_offset(kpad);
   unsigned short* start = reinterpret_cast<unsigned short*>(sec + sizeof(BucketHdr));
   unsigned short* perm = start + cells + 1;
   __syncthreads();  // the fast rows of this CTA's other threads are visible
@@ -105,16 +106,38 @@ __device__ __forceinline__ void build_centroid_buckets(unsigned char* table, int
     atomicAdd(&s_cnt[b], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int b = 0; b < cells; ++b) {
-      const int c = s_cnt[b];
-      s_cnt[b] = run;
-      start[b] = (unsigned short)run;
-      run += c;
+  {
+    // exclusive scan of the cell counts, in place (cells <= 1024: four per thread of a 256-thread CTA)
+    __shared__ int s_wsum[32];
+    int v[4], tsum = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid * 4 + e;
+      v[e] = idx < cells ? s_cnt[idx] : 0;
+      tsum += v[e];
     }
-    start[cells] = (unsigned short)run;
-    *reinterpret_cast<BucketHdr*>(sec) = hdr;
+    int incl = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+    __syncthreads();
+    int run = incl - tsum;
+    for (int w = 0; w < (tid >> 5); ++w) run += s_wsum[w];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid * 4 + e;
+      if (idx < cells) {
+        s_cnt[idx] = run;
+        start[idx] = (unsigned short)run;
+        run += v[e];
+      }
+    }
+    if (tid == 0) {
+      start[cells] = (unsigned short)k;
+      *reinterpret_cast<BucketHdr*>(sec) = hdr;
+    }
   }
   __syncthreads();
   for (int j = tid; j < k; j += blockDim.x) {
@@ -202,9 +225,9 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
         raw = jmax > j;
       }
       const double sc = (double)b.y;
-      const double qx = (double)(long long)a.x / u.fr.scale[0];
-      const double qy = (double)(long long)a.y / u.fr.scale[1];
-      const double qz = (double)(long long)b.x / u.fr.scale[2];
+      const double qx = (double)(long long)a.x * u.inv_scale[0];
+      const double qy = (double)(long long)a.y * u.inv_scale[1];
+      const double qz = (double)(long long)b.x * u.inv_scale[2];
       if (!raw) {
         const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
         cx = qx * alpha;
@@ -231,7 +254,7 @@ __device__ __forceinline__ void lloyd_update_body(const UpdateParams& u) {
       exact[j] = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
     }
   }
-  build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
+  build_centroid_buckets(fast, u.table + bucket_offset(u.kpad), u.k, u.kpad, u.fr);
   // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
   for (int o = 16; o > 0; o >>= 1) {
     shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
@@ -312,8 +335,11 @@ struct StepParams {
   const float* pts;           // blocked cloud (common.cuh)
   long long n;
   void* labels;               // uint8 (k <= 256) or uint16, capacity = whole groups
-  const unsigned char* table; // centroid table (see common.cuh)
-  unsigned long long* acc;    // [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed
+  unsigned char* table;       // TWO centroid tables (see common.cuh), table_stride bytes apart: launch `seq` assigns
+  size_t table_stride;        //   with table[seq & 1]
+  unsigned long long* acc;    // THREE accumulators of acc_slot words: [kpad*4] (qx,qy,qz,count) + [kpad*4 + 0] n_changed;
+  int acc_slot;               //   launch `seq` adds into acc[seq % 3]
+  int seq;                    // index of this launch among the fused launches since the last settle kernel (0 otherwise)
   DevStatus* st;
   FrameF f;
   int k, kpad;
@@ -326,7 +352,7 @@ struct StepParams {
   const GroupSummary* gsum;   // per-group box + cached sums (static per cloud and frame)
   const void* ssum;           // SuperSummary per kSuper groups (defined with the classification pass)
   int* worklist;              // groups the classification pass could not settle
-  int* work_count;            // number of entries; cleared by the tail of the kernel
+  int* work_count;            // TWO counters of entries: launch `seq` uses work_count[seq & 1] and clears the other
   int* glabel;                // per group: the label that owns its whole box, else -1
   unsigned int* grid_bar;     // arrival counter of the in-kernel grid barrier
   UpdateParams upd;
@@ -1165,20 +1191,21 @@ __device__ __forceinline__ void acc_add(unsigned long long* s_acc, int lab, long
 // ---------------------------------------------------------------------------------------
 constexpr int kStages = 3;
 
-// All-gather + sum of the ranks' partial sums, inside the step kernel.  Every 64-bit word travels
+// All-gather + sum of the ranks' partial sums without a collective call.  Every 64-bit word travels
 // as two 8-byte packets (32 bits of the value, 32 bits of the step's epoch) written with ONE store
 // each straight into the peers' buffers over NVLink (peer-mapped memory): value and flag arrive
-// together, so there is no separate flag, no fence and no second round trip -- the receiver
-// polls the packet itself until it carries this step's epoch (the "LL" scheme of collective
-// libraries).  Slots are double-buffered by the epoch's parity: a rank can run at most one step
-// ahead of the slowest one.  Integer sums: every rank ends with bit-identical totals.  Executed by
-// all threads of one CTA; thread t owns word t, t + kThreads, ...
-__device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned long long* acc, int n,
-                                                   DevStatus* st) {
+// together, so there is no separate flag, no fence and no second round trip -- a receiver polls
+// the packet itself until it carries the step's epoch (the "LL" scheme of collective libraries).
+// Slots are double-buffered by the epoch's parity: a rank can run at most one step ahead of the
+// slowest one.  Integer sums: every rank ends with bit-identical totals.
+//
+// peer_send_sums: the SENDING half, run by the last CTA of a step kernel to finish (it owns the
+// complete local sums); nobody waits here -- the packets fly while the kernel drains and the next
+// one starts.  Thread t owns word t, t + kThreads, ...
+__device__ __forceinline__ void peer_send_sums(const PeerXchg& px, const unsigned long long* acc, int n,
+                                               unsigned int tag) {
   const int tid = threadIdx.x, R = px.n_ranks;
-  const unsigned long long epoch = st->epoch + 1ull;
-  const int par = (int)(epoch & 1ull);
-  const unsigned int tag = (unsigned int)epoch;
+  const int par = (int)(tag & 1u);
   // packets of (parity, source rank): 2 * slot of them, 8 bytes each
   const size_t mine = ((size_t)par * R + px.rank) * (size_t)px.slot * 2;
   for (int i = tid; i < n; i += kThreads) {
@@ -1190,48 +1217,474 @@ __device__ __forceinline__ void peer_exchange_sums(const PeerXchg& px, unsigned 
       st_relaxed_sys_v2u32(dst + 1, (unsigned int)(v >> 32), tag);
     }
   }
-  bool timed_out = false;
-  const long long t0 = clock64();
-  for (int i = tid; i < n; i += kThreads) {
-    // all peers' packets of this word are requested together (2 (R - 1) independent loads in flight:
-    // one L2 round trip when everything has arrived), and only what is still missing is asked again
-    uint2 lo[kMaxRanks], hi[kMaxRanks];
-    const unsigned long long* base = px.data[px.rank] + (size_t)par * R * (size_t)px.slot * 2 + 2 * (size_t)i;
-    unsigned int missing = 0;
+}
+
+// The RECEIVING half: word i of the global sums = this rank's word + the peers' packets of epoch
+// `tag`.  All peers' packets of the word are requested together (2 (R - 1) independent loads in
+// flight: one L2 round trip when everything has arrived); only what is still missing is asked again.
+__device__ __forceinline__ unsigned long long gather_sum_word(const PeerXchg& px, const unsigned long long* acc,
+                                                              int i, unsigned int tag, long long t0, bool& timed_out) {
+  unsigned long long s = __ldcg(acc + i);
+  const int R = px.n_ranks;
+  if (R <= 1) return s;
+  const int par = (int)(tag & 1u);
+  uint2 lo[kMaxRanks], hi[kMaxRanks];
+  const unsigned long long* base = px.data[px.rank] + (size_t)par * R * (size_t)px.slot * 2 + 2 * (size_t)i;
+  unsigned int missing = 0;
+#pragma unroll
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (q < R && q != px.rank) {
+      const unsigned long long* src = base + (size_t)q * (size_t)px.slot * 2;
+      lo[q] = ld_relaxed_sys_v2u32(src);
+      hi[q] = ld_relaxed_sys_v2u32(src + 1);
+    }
+#pragma unroll
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (q < R && q != px.rank && (lo[q].y != tag || hi[q].y != tag)) missing |= 1u << q;
+  while (missing && !timed_out) {
+    // bounded wait (about 4 s): a missing peer must not hang the GPU
+    if (clock64() - t0 > (8ll << 30)) timed_out = true;
 #pragma unroll
     for (int q = 0; q < kMaxRanks; ++q)
-      if (q < R && q != px.rank) {
+      if ((missing >> q) & 1u) {
         const unsigned long long* src = base + (size_t)q * (size_t)px.slot * 2;
         lo[q] = ld_relaxed_sys_v2u32(src);
         hi[q] = ld_relaxed_sys_v2u32(src + 1);
       }
 #pragma unroll
     for (int q = 0; q < kMaxRanks; ++q)
-      if (q < R && q != px.rank && (lo[q].y != tag || hi[q].y != tag)) missing |= 1u << q;
-    while (missing && !timed_out) {
-      // bounded wait (about 4 s): a missing peer must not hang the GPU
-      if (clock64() - t0 > (8ll << 30)) timed_out = true;
+      if (((missing >> q) & 1u) && lo[q].y == tag && hi[q].y == tag) missing &= ~(1u << q);
+  }
 #pragma unroll
-      for (int q = 0; q < kMaxRanks; ++q)
-        if ((missing >> q) & 1u) {
-          const unsigned long long* src = base + (size_t)q * (size_t)px.slot * 2;
-          lo[q] = ld_relaxed_sys_v2u32(src);
-          hi[q] = ld_relaxed_sys_v2u32(src + 1);
-        }
-#pragma unroll
-      for (int q = 0; q < kMaxRanks; ++q)
-        if (((missing >> q) & 1u) && lo[q].y == tag && hi[q].y == tag) missing &= ~(1u << q);
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (q < R && q != px.rank) s += (unsigned long long)lo[q].x | ((unsigned long long)hi[q].x << 32);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Deferred centroid update.  A fused step kernel ends as soon as its sums are in acc[seq % 3]
+// (and, with several ranks, on their way to the peers): there is no last-CTA tail.  The update
+// that turns those sums into the next centroid table (_k_means_common.pyx:274-311,
+// _kmeans.py:721-738) runs in the PROLOGUE of the next launch, redundantly in every CTA: each
+// one gathers the K x 4 sums (one L2 round trip, the same one the table load used to cost),
+// computes the new rows straight into its shared-memory table and takes the same decisions
+// (converged / max_iter / empty cluster) from the same integers.  CTA 0 (`writer`) additionally
+// writes the new table to table[seq & 1] (the FP64 rows are read from there in pass 2, behind the
+// grid barrier) and the status block.  The latency chain of an iteration loses the ticket, the
+// fence and two dependent L2 round trips of the old tail, and the peers' packets travel during
+// the launch boundary.
+//
+// Returns 0: go on with the E-step (fast rows and buckets are in shared memory, threshold in
+// ds.thresh; the writer publishes ds.* after the grid barrier), 1: converged or max_iter reached
+// (status written, final table in `new_table`), 2: an empty cluster needs the host (sums parked in
+// acc_saved, status paused, update NOT applied).  Executed by all kThreads threads of a CTA.
+// ---------------------------------------------------------------------------------------
+struct DeferredShared {
+  double red[5][kThreads / 32];
+  unsigned long long nchg;
+  unsigned long long maxcnt;  // (count << 13) | (2 * kMaxK - 1 - j): argmax, first wins
+  double shift2;
+  int nempty;
+  int verdict;
+  int iter;
+  float thresh;
+};
+
+// What the writer CTA publishes once every CTA of the launch has read the status block (behind the
+// grid barrier of a step kernel, or at the end of the settle kernel).
+__device__ __forceinline__ void publish_update(DevStatus* st, const DeferredShared& ds) {
+  st->thresh = ds.thresh;
+  st->shift2 = ds.shift2;
+  st->n_changed = ds.nchg;
+  st->n_empty = ds.nempty;
+  st->iter = ds.iter;
+  st->first = 0;
+}
+
+__device__ __forceinline__ int deferred_update(const UpdateParams& u, const PeerXchg& px,
+                                               const unsigned long long* acc_src, const unsigned char* old_table,
+                                               unsigned char* new_table, float4* s_fast, unsigned char* s_bkt,
+                                               unsigned long long* s_sums, DeferredShared& ds, bool writer, int seq) {
+  DevStatus* st = u.st;
+  const int tid = threadIdx.x;
+  const unsigned int tag = (unsigned int)st->epoch;  // the epoch the pending E-step's packets carry
+  const int was_first = st->first, iter_old = st->iter, max_iter = st->max_iter;
+  const double tol = st->tol;
+  if (tid == 0) {
+    ds.nempty = 0;
+    ds.maxcnt = 0ull;
+  }
+  {
+    bool timed_out = false;
+    const long long t0 = clock64();
+    for (int i = tid; i < u.kpad * 4 + 1; i += kThreads) {
+      const unsigned long long v = gather_sum_word(px, acc_src, i, tag, t0, timed_out);
+      if (i < u.kpad * 4) s_sums[i] = v;
+      else ds.nchg = v;
     }
-    unsigned long long s = __ldcg(acc + i);
+    if (timed_out) st->xchg_timeout = 1;
+  }
+  __syncthreads();
+  // empty clusters and the heaviest cluster (np.argmax: first maximum)
+  int my_empty = 0;
+  unsigned long long my_max = 0ull;
+  for (int j = tid; j < u.k; j += kThreads) {
+    const unsigned long long cnt = s_sums[j * 4 + 3];
+    if (cnt == 0ull) ++my_empty;
+    const unsigned long long key = (cnt << 13) | (unsigned long long)(kMaxK * 2 - 1 - j);
+    my_max = key > my_max ? key : my_max;
+  }
+  my_empty = __reduce_add_sync(0xffffffffu, my_empty);
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_down_sync(0xffffffffu, my_max, o);
+    my_max = t > my_max ? t : my_max;
+  }
+  if ((tid & 31) == 0) {
+    if (my_empty) atomicAdd(&ds.nempty, my_empty);
+    atomicMax(&ds.maxcnt, my_max);
+  }
+  __syncthreads();
+  const int n_empty = ds.nempty;
+  const unsigned long long n_changed = ds.nchg;
+  if (n_empty > 0 && u.allow_pause) {
+    // the host sequences the relocation kernels on the parked (global) sums and re-runs the update
+    if (writer) {
+      for (int i = tid; i < u.kpad * 4 + 8; i += kThreads)
+        u.acc_saved[i] = i < u.kpad * 4 ? s_sums[i] : (i == u.kpad * 4 ? n_changed : 0ull);
+      __syncthreads();
+      if (tid == 0) {
+        st->n_empty = n_empty;
+        __threadfence();
+        st->paused = 1;
+      }
+    }
+    return 2;
+  }
+  const int jmax = kMaxK * 2 - 1 - (int)(ds.maxcnt & 0x1fffull);
+  const double4* old_exact = reinterpret_cast<const double4*>(old_table + exact_offset(u.kpad));
+  double4* new_exact = reinterpret_cast<double4*>(new_table + exact_offset(u.kpad));
+  float4* new_fast = reinterpret_cast<float4*>(new_table);
+  double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
+  for (int j = tid; j < u.kpad; j += kThreads) {
+    float4 fr4 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    double4 ex4 = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
+    if (j < u.k) {
+      const double4 old = old_exact[j];
+      int row = j;
+      bool raw = false;
+      if (s_sums[j * 4 + 3] == 0ull) {
+        // sklearn/_k_means_common.pyx:289-293: copy of the heaviest cluster's row -- which is
+        // still the un-averaged sum when that row comes later in the loop.
+        row = jmax;
+        raw = jmax > j;
+      }
+      const unsigned long long ax = s_sums[row * 4 + 0], ay = s_sums[row * 4 + 1], az = s_sums[row * 4 + 2];
+      const double sc = (double)s_sums[row * 4 + 3];
+      const double qx = (double)(long long)ax * u.inv_scale[0];
+      const double qy = (double)(long long)ay * u.inv_scale[1];
+      const double qz = (double)(long long)az * u.inv_scale[2];
+      double cx, cy, cz;
+      if (!raw) {
+        const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
+        cx = qx * alpha;
+        cy = qy * alpha;
+        cz = qz * alpha;
+      } else {
+        // raw sum in sklearn's mean-centred frame, expressed in ours
+        cx = qx + sc * (u.fr.origin[0] - u.mean[0]) + (u.mean[0] - u.fr.origin[0]);
+        cy = qy + sc * (u.fr.origin[1] - u.mean[1]) + (u.mean[1] - u.fr.origin[1]);
+        cz = qz + sc * (u.fr.origin[2] - u.mean[2]) + (u.mean[2] - u.fr.origin[2]);
+      }
+      const double dx = cx - old.x, dy = cy - old.y, dz = cz - old.z;
+      const double sh = sqrt(dx * dx + dy * dy + dz * dz);  // _center_shift, pyx:298-311
+      shift2 += sh * sh;                                     // (center_shift**2).sum()
+      const double cn = cx * cx + cy * cy + cz * cz;
+      ex4 = make_double4(cx, cy, cz, cn);
+      fr4 = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
+      m_cn = fmax(m_cn, cn);
+      m_cx = fmax(m_cx, fabs(cx));
+      m_cy = fmax(m_cy, fabs(cy));
+      m_cz = fmax(m_cz, fabs(cz));
+    }
+    s_fast[j] = fr4;
+    if (writer) {
+      new_exact[j] = ex4;
+      new_fast[j] = fr4;
+    }
+  }
+  if (s_bkt) {
+    build_centroid_buckets(s_fast, s_bkt, u.k, u.kpad, u.fr);
+    if (writer) {
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(s_bkt);
+      uint4* dst = reinterpret_cast<uint4*>(new_table + bucket_offset(u.kpad));
+      for (int i = tid; i < (int)(bucket_bytes(u.k, u.kpad) / 16); i += kThreads) dst[i] = src[i];
+    }
+  }
+  // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
+  for (int o = 16; o > 0; o >>= 1) {
+    shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
+    m_cn = fmax(m_cn, __shfl_down_sync(0xffffffffu, m_cn, o));
+    m_cx = fmax(m_cx, __shfl_down_sync(0xffffffffu, m_cx, o));
+    m_cy = fmax(m_cy, __shfl_down_sync(0xffffffffu, m_cy, o));
+    m_cz = fmax(m_cz, __shfl_down_sync(0xffffffffu, m_cz, o));
+  }
+  if ((tid & 31) == 0) {
+    const int w = tid >> 5;
+    ds.red[0][w] = shift2; ds.red[1][w] = m_cn; ds.red[2][w] = m_cx; ds.red[3][w] = m_cy; ds.red[4][w] = m_cz;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    shift2 = 0.0; m_cn = 0.0; m_cx = 0.0; m_cy = 0.0; m_cz = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      shift2 += ds.red[0][w];
+      m_cn = fmax(m_cn, ds.red[1][w]);
+      m_cx = fmax(m_cx, ds.red[2][w]);
+      m_cy = fmax(m_cy, ds.red[3][w]);
+      m_cz = fmax(m_cz, ds.red[4][w]);
+    }
+    // FP32 error bound of the fast distances (DESIGN.md "Exactness"): u = 2^-24
+    const double ue = 5.9604644775390625e-08;
+    const double E = ue * (4.0 * m_cn + 10.0 * (u.fr.halfrange[0] * m_cx + u.fr.halfrange[1] * m_cy +
+                                                 u.fr.halfrange[2] * m_cz));
+    ds.thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
+    ds.shift2 = shift2;
+    const int it = iter_old + 1;
+    ds.iter = it;
+    const bool strict = !was_first && n_changed == 0ull;  // _kmeans.py:721-726
+    const bool done = strict || shift2 <= tol || it >= max_iter;  // _kmeans.py:729-738
+    ds.verdict = done ? 1 : 0;
+    if (done && writer) {
+      // `done` first: a CTA that starts late leaves at once whatever else it reads
+      st->done = 1;
+      if (strict) st->strict = 1;
+      __threadfence();
+      st->thresh = ds.thresh;
+      st->shift2 = shift2;
+      st->n_changed = n_changed;
+      st->n_empty = n_empty;
+      st->iter = it;
+      st->first = 0;
+      st->last_seq = seq;  // (the final table sits in table[seq & 1])
+      // `pending` stays as it is: a CTA of this launch that starts late and sees neither `done` nor
+      // a cleared `pending` must still come to the same verdict; the settle kernel clears it
+    }
+  }
+  __syncthreads();
+  return ds.verdict;
+}
+
+// The same update for tables of at most 128 rows (the step kernels with private accumulator
+// slices: every CTA runs it), ONE row per thread.  The row's sums and its old centroid are
+// requested by deferred_prefetch at the very top of the kernel, together with the status words,
+// so the whole prologue costs one L2 round trip; two CTA barriers (the first doubles as the
+// "any empty cluster" vote).  Same arithmetic, same reduction order as deferred_update.
+struct RowRegs {
+  ulonglong2 a, b;          // (sum qx, sum qy), (sum qz, count) of row threadIdx.x
+  double4 old;              // its centroid before the update
+  unsigned long long nchg;  // changed-label count (thread kThreads - 1 only)
+};
+
+__device__ __forceinline__ void deferred_prefetch(RowRegs& r, const unsigned long long* acc_src,
+                                                  const unsigned char* old_table, int k, int kpad) {
+  const int tid = threadIdx.x;
+  r.a = make_ulonglong2(0ull, 0ull);
+  r.b = r.a;
+  r.old = make_double4(0.0, 0.0, 0.0, 0.0);
+  r.nchg = 0ull;
+  if (tid < kpad) {
+    r.a = __ldcg(reinterpret_cast<const ulonglong2*>(acc_src + tid * 4));
+    r.b = __ldcg(reinterpret_cast<const ulonglong2*>(acc_src + tid * 4 + 2));
+  }
+  if (tid < k) {
+    const double2* src = reinterpret_cast<const double2*>(old_table + exact_offset(kpad)) + 2 * tid;
+    const double2 o0 = __ldcg(src), o1 = __ldcg(src + 1);
+    r.old = make_double4(o0.x, o0.y, o1.x, o1.y);
+  }
+  if (tid == kThreads - 1) r.nchg = __ldcg(acc_src + kpad * 4);
+}
+
+// The peers' shares of all n words (epoch `tag`), spread over the CTA: a thread takes (peer, word)
+// pairs, requests both packets of up to kPairs pairs at once (so the whole gather is one round trip
+// through L2 when everything has arrived; only what is missing is asked again) and parks the 64-bit
+// values in shared memory, stash[peer_index * n + word].  Ends with a CTA barrier.
+__device__ __forceinline__ void gather_peer_words(const PeerXchg& px, int n, unsigned int tag,
+                                                  unsigned long long* stash, DevStatus* st) {
+  constexpr int kPairs = 4;
+  const int tid = threadIdx.x, R = px.n_ranks, par = (int)(tag & 1u);
+  const unsigned long long* mybuf = px.data[px.rank] + (size_t)par * R * (size_t)px.slot * 2;
+  const int total = (R - 1) * n;
+  const long long t0 = clock64();
+  bool timed_out = false;
+  for (int base = 0; base < total; base += kThreads * kPairs) {
+    const unsigned long long* src[kPairs];
+    uint2 lo[kPairs], hi[kPairs];
+    int idx[kPairs];
 #pragma unroll
-    for (int q = 0; q < kMaxRanks; ++q)
-      if (q < R && q != px.rank) s += (unsigned long long)lo[q].x | ((unsigned long long)hi[q].x << 32);
-    acc[i] = s;
+    for (int u = 0; u < kPairs; ++u) {
+      idx[u] = base + u * kThreads + tid;
+      if (idx[u] < total) {
+        const int qi = idx[u] / n, w = idx[u] - qi * n;
+        const int q = qi + (qi >= px.rank ? 1 : 0);
+        src[u] = mybuf + ((size_t)q * (size_t)px.slot + (size_t)w) * 2;
+        lo[u] = ld_relaxed_sys_v2u32(src[u]);
+        hi[u] = ld_relaxed_sys_v2u32(src[u] + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPairs; ++u) {
+      if (idx[u] < total) {
+        while ((lo[u].y != tag || hi[u].y != tag) && !timed_out) {
+          if (clock64() - t0 > (8ll << 30)) timed_out = true;  // bounded wait (about 4 s): a missing peer must not hang the GPU
+          lo[u] = ld_relaxed_sys_v2u32(src[u]);
+          hi[u] = ld_relaxed_sys_v2u32(src[u] + 1);
+        }
+        stash[idx[u]] = (unsigned long long)lo[u].x | ((unsigned long long)hi[u].x << 32);
+      }
+    }
   }
   if (timed_out) st->xchg_timeout = 1;
-  if (tid == 0) st->epoch = epoch;
-  __threadfence();
   __syncthreads();
+}
+
+// the status words a step kernel needs, requested together at its very top
+struct StatusSnap {
+  int done, paused, first, iter, max_iter;
+  float thresh;
+  double tol;
+  unsigned long long epoch;
+};
+__device__ __forceinline__ StatusSnap status_snapshot(const DevStatus* st) {
+  StatusSnap s;
+  s.done = st->done; s.paused = st->paused; s.first = st->first; s.iter = st->iter; s.max_iter = st->max_iter;
+  s.thresh = st->thresh; s.tol = st->tol; s.epoch = st->epoch;
+  return s;
+}
+
+__device__ __forceinline__ int deferred_update_rows(const UpdateParams& u, const PeerXchg& px, RowRegs& r,
+                                                    const StatusSnap& snap, unsigned char* new_table, float4* s_fast,
+                                                    unsigned char* s_bkt, unsigned long long* s_stash,
+                                                    DeferredShared& ds, bool writer, int seq, float& thresh_out) {
+  DevStatus* st = u.st;
+  const int tid = threadIdx.x;
+  const int was_first = snap.first, iter_old = snap.iter, max_iter = snap.max_iter;
+  const double tol = snap.tol;
+  if (px.n_ranks > 1) {
+    // (s_stash: the idle accumulator slices, (n_ranks - 1) * (kpad * 4 + 1) words)
+    const int n = u.kpad * 4 + 1;
+    gather_peer_words(px, n, (unsigned int)snap.epoch, s_stash, st);  // the epoch the pending E-step's packets carry
+    for (int qi = 0; qi < px.n_ranks - 1; ++qi) {
+      const unsigned long long* row = s_stash + (size_t)qi * n;
+      if (tid < u.kpad) {
+        r.a.x += row[tid * 4 + 0];
+        r.a.y += row[tid * 4 + 1];
+        r.b.x += row[tid * 4 + 2];
+        r.b.y += row[tid * 4 + 3];
+      }
+      if (tid == kThreads - 1) r.nchg += row[u.kpad * 4];
+    }
+  }
+  if (tid == kThreads - 1) ds.nchg = r.nchg;
+  const int n_empty = __syncthreads_count(tid < u.k && r.b.y == 0ull);
+  if (n_empty > 0) {
+    // the host sequences the relocation kernels on the parked (global) sums and re-runs the update
+    if (writer) {
+      if (tid < u.kpad) {
+        *reinterpret_cast<ulonglong2*>(u.acc_saved + tid * 4) = r.a;
+        *reinterpret_cast<ulonglong2*>(u.acc_saved + tid * 4 + 2) = r.b;
+      }
+      if (tid >= kThreads - 8)  // the changed-label count and the unused words behind it
+        u.acc_saved[u.kpad * 4 + (tid - (kThreads - 8))] = tid == kThreads - 8 ? ds.nchg : 0ull;
+      __syncthreads();
+      if (tid == 0) {
+        st->n_empty = n_empty;
+        __threadfence();
+        st->paused = 1;
+      }
+    }
+    return 2;
+  }
+  double shift2 = 0.0, m_cn = 0.0, m_cx = 0.0, m_cy = 0.0, m_cz = 0.0;
+  if (tid < u.kpad) {
+    float4 fr4 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    double4 ex4 = make_double4(0.0, 0.0, 0.0, 1.0 / 0.0);
+    if (tid < u.k) {
+      const double sc = (double)r.b.y;
+      const double qx = (double)(long long)r.a.x * u.inv_scale[0];
+      const double qy = (double)(long long)r.a.y * u.inv_scale[1];
+      const double qz = (double)(long long)r.b.x * u.inv_scale[2];
+      const double alpha = 1.0 / sc;  // pyx:284-287: centers *= 1/weight
+      const double cx = qx * alpha, cy = qy * alpha, cz = qz * alpha;
+      const double dx = cx - r.old.x, dy = cy - r.old.y, dz = cz - r.old.z;
+      const double sh = sqrt(dx * dx + dy * dy + dz * dz);  // _center_shift, pyx:298-311
+      shift2 = sh * sh;                                      // (center_shift**2).sum()
+      const double cn = cx * cx + cy * cy + cz * cz;
+      ex4 = make_double4(cx, cy, cz, cn);
+      fr4 = make_float4((float)(-2.0 * cx), (float)(-2.0 * cy), (float)(-2.0 * cz), (float)cn);
+      m_cn = cn; m_cx = fabs(cx); m_cy = fabs(cy); m_cz = fabs(cz);
+    }
+    s_fast[tid] = fr4;
+    if (writer) {
+      reinterpret_cast<double4*>(new_table + exact_offset(u.kpad))[tid] = ex4;
+      reinterpret_cast<float4*>(new_table)[tid] = fr4;
+    }
+  }
+  if (s_bkt) {
+    build_centroid_buckets(s_fast, s_bkt, u.k, u.kpad, u.fr);
+    if (writer) {
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(s_bkt);
+      uint4* dst = reinterpret_cast<uint4*>(new_table + bucket_offset(u.kpad));
+      for (int i = tid; i < (int)(bucket_bytes(u.k, u.kpad) / 16); i += kThreads) dst[i] = src[i];
+    }
+  }
+  // fixed-order reductions: shuffle tree inside the warp, warps combined in index order
+  for (int o = 16; o > 0; o >>= 1) {
+    shift2 += __shfl_down_sync(0xffffffffu, shift2, o);
+    m_cn = fmax(m_cn, __shfl_down_sync(0xffffffffu, m_cn, o));
+    m_cx = fmax(m_cx, __shfl_down_sync(0xffffffffu, m_cx, o));
+    m_cy = fmax(m_cy, __shfl_down_sync(0xffffffffu, m_cy, o));
+    m_cz = fmax(m_cz, __shfl_down_sync(0xffffffffu, m_cz, o));
+  }
+  if ((tid & 31) == 0) {
+    const int w = tid >> 5;
+    ds.red[0][w] = shift2; ds.red[1][w] = m_cn; ds.red[2][w] = m_cx; ds.red[3][w] = m_cy; ds.red[4][w] = m_cz;
+  }
+  __syncthreads();
+  // every thread combines the warps' partials itself (no broadcast barrier)
+  shift2 = 0.0; m_cn = 0.0; m_cx = 0.0; m_cy = 0.0; m_cz = 0.0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    shift2 += ds.red[0][w];
+    m_cn = fmax(m_cn, ds.red[1][w]);
+    m_cx = fmax(m_cx, ds.red[2][w]);
+    m_cy = fmax(m_cy, ds.red[3][w]);
+    m_cz = fmax(m_cz, ds.red[4][w]);
+  }
+  // FP32 error bound of the fast distances (DESIGN.md "Exactness"): u = 2^-24
+  const double ue = 5.9604644775390625e-08;
+  const double E = ue * (4.0 * m_cn + 10.0 * (u.fr.halfrange[0] * m_cx + u.fr.halfrange[1] * m_cy +
+                                               u.fr.halfrange[2] * m_cz));
+  thresh_out = __double2float_ru(2.0 * E * 1.001 + 1e-37);
+  const unsigned long long n_changed = ds.nchg;
+  const int it = iter_old + 1;
+  const bool strict = !was_first && n_changed == 0ull;           // _kmeans.py:721-726
+  const bool done = strict || shift2 <= tol || it >= max_iter;  // _kmeans.py:729-738
+  if (writer && tid == 0) {
+    ds.thresh = thresh_out;
+    ds.shift2 = shift2;
+    ds.iter = it;
+    ds.nempty = 0;
+    if (done) {
+      // `done` first: a CTA that starts late leaves at once whatever else it reads
+      st->done = 1;
+      if (strict) st->strict = 1;
+      __threadfence();
+      publish_update(st, ds);
+      st->last_seq = seq;  // (the final table sits in table[seq & 1]; `pending` is cleared by the settle kernel)
+    }
+  }
+  return done ? 1 : 0;
 }
 
 template <typename LabT>
@@ -1254,7 +1707,11 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   __shared__ unsigned int s_refined;
   __shared__ unsigned short s_cand[kWarps * kCandCap];
   __shared__ bool s_is_last;
+  __shared__ DeferredShared s_def;
 
+  // the next kernel of the stream may be set up while this one runs (it waits for this grid's end
+  // before it reads anything, see grid_dependency_wait below)
+  grid_launch_dependents();
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
@@ -1263,18 +1720,24 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   // bucket index of the centroids (k >= kBucketMinK), behind the accumulator slices
   const uint32_t bkt_bytes = (uint32_t)bucket_bytes(p.k, p.kpad);
   unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_acc_all + (size_t)(kPrivate ? kWarps : 1) * p.kpad * 4);
-  const double4* c64 = reinterpret_cast<const double4*>(p.table + exact_offset(p.kpad));
+  // this launch's table, accumulator and worklist counter (see StepParams)
+  const int seq = p.seq;
+  unsigned char* table_cur = p.table + (size_t)(seq & 1) * p.table_stride;
+  unsigned long long* acc_w = p.acc + (size_t)(seq % 3) * p.acc_slot;
+  int* work_count = p.work_count + (seq & 1);
+  const double4* c64 = reinterpret_cast<const double4*>(table_cur + exact_offset(p.kpad));
   const FrameF f = p.f;
   // (One launch = one Lloyd iteration.  Running a batch of iterations inside one launch, with a
   // grid barrier instead of the kernel boundary, was measured: 0.9 us per iteration at best, and
   // the loop-carried state pushed the kernel over its register budget -- not kept.)
-  if (!p.ignore_status && (p.st->done | p.st->paused)) return;  // the same for every CTA
-#ifdef MDKM_TIMING
-  if (blockIdx.x == 0 && tid == 0) {
-    p.st->t_start = globaltimer_ns();
-    p.st->t_update_done = 0ull;
-  }
-#endif
+  // the update of the previous E-step is still to be applied (see deferred_update): true for every
+  // fused launch but the first one behind a settle kernel.  Tables of at most 128 rows: every CTA
+  // applies it, one row per thread -- the row's sums and old centroid are requested right here,
+  // together with the status words below
+  const bool pending = p.fuse_update && seq > 0;  // the same for every CTA
+  const unsigned long long* acc_prev = p.acc + (size_t)((seq + 2) % 3) * p.acc_slot;
+  const unsigned char* table_prev = p.table + (size_t)((seq & 1) ^ 1) * p.table_stride;
+  RowRegs rr;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     for (int i = 0; i < kWarps * kStages; ++i) mbar_init(&s_gbar[i], 1);
@@ -1282,27 +1745,28 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     s_changed = 0;
     s_refined = 0;
   }
-  for (int i = tid; i < n_slices * p.kpad * 4; i += kThreads) s_acc_all[i] = 0ull;
-  // rows [kpad, kp32) are not covered by the bulk copies: make them non-candidates
+  // rows [kpad, kp32) are not covered by the table: make them non-candidates
   for (int i = p.kpad + tid; i < kp32; i += kThreads) {
     s_fast[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
   }
-  __syncthreads();
-  if (tid == 0) {
-    // centroid rows (and their bucket index): global -> shared through the TMA unit (1-D bulk copies)
-    mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
-    tma_load_1d(s_fast, p.table, (uint32_t)p.kpad * 16u, &s_bar);
-    if (bkt_bytes) tma_load_1d(s_bkt, p.table + bucket_offset(p.kpad), bkt_bytes, &s_bar);
+  // (launched with programmatic stream serialisation: the previous kernel of the stream may still be
+  // draining -- nothing it wrote is read before this point)
+  grid_dependency_wait();
+  if (kPrivate && pending) deferred_prefetch(rr, acc_prev, table_prev, p.k, p.kpad);
+  const StatusSnap snap = status_snapshot(p.st);
+  if (!p.ignore_status && (snap.done | snap.paused)) return;  // the same for every CTA
+#ifdef MDKM_TIMING
+  if (blockIdx.x == 0 && tid == 0) {
+    p.st->t_start = globaltimer_ns();
+    p.st->t_update_done = 0ull;
   }
-  const float thresh = p.st->thresh;
-  const bool first_iter = p.st->first != 0;
+#endif
 
   // group bookkeeping is 32-bit and warp-uniform (the host guarantees n < 2^38 points)
   const int n_groups = (int)((p.n + kGroup - 1) / kGroup);
   const int n_full = (int)(p.n / kGroup);  // groups below this index have 128 real points
   LabT* labels = reinterpret_cast<LabT*>(p.labels);
   unsigned int n_chg = 0, n_ref = 0;
-  // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
   // (one-level walk: the first group's summary travels while the centroid table does)
   float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
   int pprev = -1;
@@ -1310,18 +1774,96 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
     const int g_first = (int)blockIdx.x * kThreads + tid;
     const float4* src = reinterpret_cast<const float4*>(p.gsum + g_first);
     pa = __ldg(src); pb = __ldg(src + 1); pc = __ldg(src + 2);
-    pprev = first_iter ? -1 : p.glabel[g_first];
+    pprev = (!pending && snap.first != 0) ? -1 : p.glabel[g_first];
   }
-  mbar_wait(&s_bar, 0);
+  float thresh = 0.f;
+  bool first_iter = false;
+  bool table_by_tma = !pending;
+  if (pending) {
+    int verdict;
+    if (kPrivate) {
+      verdict = deferred_update_rows(p.upd, p.px, rr, snap, table_cur, s_fast, bkt_bytes ? s_bkt : nullptr, s_acc_all,
+                                     s_def, blockIdx.x == 0, seq, thresh);
+    } else if (blockIdx.x == 0) {
+      // larger tables: CTA 0 alone applies the update and announces the verdict (the iteration is
+      // long, the redundant work would cost more than the wait)
+      verdict = deferred_update(p.upd, p.px, acc_prev, table_prev, table_cur, s_fast, bkt_bytes ? s_bkt : nullptr,
+                                s_acc_all, s_def, true, seq);
+      thresh = s_def.thresh;
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        p.st->next_thresh = thresh;
+        __threadfence();
+        st_release_gpu_u32(&p.st->upd_flag, ((unsigned int)snap.epoch << 2) | (unsigned int)verdict);
+      }
+    } else {
+      if (tid == 0) {
+        const unsigned int want = (unsigned int)snap.epoch << 2;
+        unsigned int fl;
+        const long long t0 = clock64();
+        do {
+          fl = ld_acquire_gpu_u32(&p.st->upd_flag);
+          if (clock64() - t0 > (8ll << 30)) {  // bounded wait (about 4 s); never triggers: CTA 0 is resident
+            p.st->xchg_timeout = 1;
+            fl = want | 1u;
+          }
+        } while ((fl & ~3u) != want);
+        s_def.verdict = (int)(fl & 3u);
+        s_def.thresh = *reinterpret_cast<volatile float*>(&p.st->next_thresh);
+      }
+      __syncthreads();
+      verdict = s_def.verdict;
+      thresh = s_def.thresh;
+      if (verdict == 0) {
+        // the table CTA 0 has just written: plain loads through L2 (not the TMA unit: the writes were
+        // made through the generic proxy inside this very kernel)
+        const uint4* src = reinterpret_cast<const uint4*>(table_cur);
+        uint4* dst = reinterpret_cast<uint4*>(s_fast);
+        for (int i = tid; i < p.kpad; i += kThreads) dst[i] = __ldcg(src + i);
+        if (bkt_bytes) {
+          const uint4* bs = reinterpret_cast<const uint4*>(table_cur + bucket_offset(p.kpad));
+          uint4* bd = reinterpret_cast<uint4*>(s_bkt);
+          for (int i = tid; i < (int)(bkt_bytes / 16); i += kThreads) bd[i] = __ldcg(bs + i);
+        }
+      }
+    }
+    if (verdict != 0) return;  // converged / max_iter / paused: the same for every CTA
+  } else {
+    __syncthreads();
+    if (tid == 0) {
+      // centroid rows (and their bucket index): global -> shared through the TMA unit (1-D bulk copies)
+      mbar_expect_tx(&s_bar, (uint32_t)p.kpad * 16u + bkt_bytes);
+      tma_load_1d(s_fast, table_cur, (uint32_t)p.kpad * 16u, &s_bar);
+      if (bkt_bytes) tma_load_1d(s_bkt, table_cur + bucket_offset(p.kpad), bkt_bytes, &s_bar);
+    }
+    thresh = snap.thresh;
+    first_iter = snap.first != 0;
+  }
+  // (the accumulator slices held the gathered sums during the update)
+  for (int i = tid; i < n_slices * p.kpad * 4; i += kThreads) s_acc_all[i] = 0ull;
+  if (blockIdx.x == 0 && p.fuse_update) {
+    // the accumulator the NEXT launch adds into (last read by the previous launch) and the previous
+    // launch's worklist counter
+    unsigned long long* acc_z = p.acc + (size_t)((seq + 1) % 3) * p.acc_slot;
+    for (int i = tid; i < p.kpad * 4 + 8; i += kThreads) acc_z[i] = 0ull;
+    if (tid == 0) p.work_count[(seq & 1) ^ 1] = 0;
+  }
+  __syncthreads();
+  if (table_by_tma) mbar_wait(&s_bar, 0);
+#ifdef MDKM_TIMING
+  if (blockIdx.x == 0 && tid == 0) p.st->t_classify_start = globaltimer_ns();  // table ready
+#endif
+  // ---- pass 1: settle whole groups from their summaries (no point is read) ----------------
   // the ring is idle during pass 1: its first bytes stage the worklist entries
   static_assert(kWarps * kStages * kStageB >= kClassifyList * 4, "worklist staging does not fit the ring");
   if (p.two_level)
     classify_groups_two_level<LabT, kPrivate>(p.gsum, reinterpret_cast<const SuperSummary*>(p.ssum), n_groups, labels,
-                                              p.glabel, p.worklist, p.work_count, s_fast, p.k, 4.0f * thresh, first_iter,
+                                              p.glabel, p.worklist, work_count, s_fast, p.k, 4.0f * thresh, first_iter,
                                               s_acc, reinterpret_cast<int*>(s_ring), bkt_bytes ? s_bkt : nullptr, n_chg,
                                               p.settle != 0);
   else
-    classify_groups_flat<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, p.work_count, s_fast, p.k,
+    classify_groups_flat<LabT, kPrivate>(p.gsum, n_groups, labels, p.glabel, p.worklist, work_count, s_fast, p.k,
                                          4.0f * thresh, first_iter, s_acc, reinterpret_cast<int*>(s_ring),
                                          bkt_bytes ? s_bkt : nullptr, n_chg, p.settle != 0, pa, pb, pc, pprev);
 #ifdef MDKM_TIMING
@@ -1333,7 +1875,15 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
 #endif
   // ---- pass 2: the groups a cluster boundary crosses, point by point -----------------------
   // (the "groups" below are positions in the worklist)
-  const int n_items = *reinterpret_cast<volatile int*>(p.work_count);
+  const int n_items = *reinterpret_cast<volatile int*>(work_count);
+  if (p.fuse_update && blockIdx.x == 0 && tid == 0) {
+    // every CTA has read the status block by now: the applied update and this E-step become visible
+    if (pending) publish_update(p.st, s_def);
+    p.st->pending = 1;
+    p.st->last_seq = seq;
+    p.st->epoch = p.st->epoch + 1ull;  // the epoch this E-step's packets carry
+    p.st->work_sum += (unsigned long long)n_items;
+  }
   // round-robin over the warps of the grid: neighbouring list entries are neighbouring groups
   // with similar cost, so interleaving them evens out the warps' loads
   const int stride = (int)gridDim.x * kWarps;
@@ -1525,40 +2075,81 @@ __global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParam
   for (int i = tid; i < p.kpad * 4; i += kThreads) {
     unsigned long long v = 0ull;
     for (int s = 0; s < n_slices; ++s) v += s_acc_all[s * p.kpad * 4 + i];
-    if (v) atomicAdd(&p.acc[i], v);
+    if (v) atomicAdd(&acc_w[i], v);
   }
   if (tid == 0) {
-    if (s_changed) atomicAdd(&p.acc[p.kpad * 4 + 0], (unsigned long long)s_changed);
+    if (s_changed) atomicAdd(&acc_w[p.kpad * 4 + 0], (unsigned long long)s_changed);
     if (s_refined) atomicAdd(&p.st->n_refined, (unsigned long long)s_refined);
+#ifdef MDKM_TIMING
+    atomicAdd(&p.st->t_update_done, globaltimer_ns() - p.st->t_start);  // sum of the CTAs' finish times
+    atomicMax(&p.st->t_last_done, globaltimer_ns());
+#endif
   }
-  if (!p.fuse_update) return;
-  // ---- fused tail: the last CTA to get here owns the complete local sums ----------------
+  // One rank: nothing else -- the next launch (or the settle kernel) turns the sums into centroids.
+  if (!p.fuse_update || p.px.n_ranks <= 1) return;
+  // ---- several ranks: the last CTA to get here owns the complete local sums and sends them ----
   __threadfence();
   __syncthreads();
   if (tid == 0) {
     const unsigned int t = atomicAdd(&p.st->ticket, 1u);
     s_is_last = (t == gridDim.x - 1);
-#ifdef MDKM_TIMING
-    atomicAdd(&p.st->t_update_done, globaltimer_ns() - p.st->t_start);  // sum of the CTAs' finish times
-    if (s_is_last) p.st->t_last_done = globaltimer_ns();
-#endif
   }
   __syncthreads();
   if (s_is_last) {  // CTA-uniform
     __threadfence();
-    if (tid == 0) {
-      p.st->ticket = 0u;
-      if (p.work_count) {
-        p.st->work_sum += (unsigned long long)*reinterpret_cast<volatile int*>(p.work_count);
-        *p.work_count = 0;
-      }
-    }
-    if (p.px.n_ranks > 1) peer_exchange_sums(p.px, p.acc, p.kpad * 4 + 8, p.st);
-    lloyd_update_body(p.upd);
-#ifdef MDKM_TIMING
-    __syncthreads();
-    if (tid == 0) p.st->t_classify_start = globaltimer_ns();  // (field reused: end of the update)
-#endif
+    if (tid == 0) p.st->ticket = 0u;
+    const unsigned int tag = (unsigned int)__ldcg(&p.st->epoch);  // (incremented by CTA 0 behind the grid barrier)
+    peer_send_sums(p.px, acc_w, p.kpad * 4 + 8, tag);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Settle kernel (one CTA), enqueued by the host behind a run of fused step launches and before
+// anything else reads the table: applies the update that is still pending (the last E-step's
+// sums), moves the current table to table[0] and clears the rotating buffers, so that every
+// other kernel -- final pass, relocation, stand-alone update, the next run of fused launches
+// starting at seq 0 -- finds the classic layout: table[0], acc[0], pending = 0.
+// ---------------------------------------------------------------------------------------
+struct SettleParams {
+  UpdateParams upd;     // acc = acc[0], table = table[0]
+  PeerXchg px;
+  size_t table_stride;
+  int acc_slot;
+  int* work_count;      // two counters
+};
+
+__global__ void __launch_bounds__(kThreads, 1) lloyd_settle_kernel(const SettleParams sp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ DeferredShared s_def;
+  const UpdateParams& u = sp.upd;
+  DevStatus* st = u.st;
+  const int tid = threadIdx.x;
+  float4* s_fast = reinterpret_cast<float4*>(smem_raw);
+  unsigned long long* s_sums = reinterpret_cast<unsigned long long*>(s_fast + u.kpad);
+  unsigned char* s_bkt = reinterpret_cast<unsigned char*>(s_sums + u.kpad * 4);
+  const uint32_t bkt_bytes = (uint32_t)bucket_bytes(u.k, u.kpad);
+  const int last = st->last_seq;
+  const bool apply = st->pending != 0 && !st->paused && !st->done;
+  unsigned char* t_last = u.table + (size_t)(last & 1) * sp.table_stride;
+  int verdict = -1;
+  if (apply) {
+    verdict = deferred_update(u, sp.px, u.acc + (size_t)(last % 3) * sp.acc_slot, t_last, u.table, s_fast,
+                              bkt_bytes ? s_bkt : nullptr, s_sums, s_def, true, 0);
+    if (verdict == 0 && tid == 0) publish_update(st, s_def);  // (more iterations to come)
+  }
+  __syncthreads();
+  if ((last & 1) && (!apply || verdict == 2)) {
+    // the table the last E-step used (final, or the one a paused update starts from) -> table[0]
+    const uint4* src = reinterpret_cast<const uint4*>(t_last);
+    uint4* dst = reinterpret_cast<uint4*>(u.table);
+    for (int i = tid; i < (int)(table_bytes(u.k, u.kpad) / 16); i += kThreads) dst[i] = src[i];
+  }
+  for (int i = tid; i < 3 * sp.acc_slot; i += kThreads) u.acc[i] = 0ull;
+  if (tid == 0) {
+    sp.work_count[0] = 0;
+    sp.work_count[1] = 0;
+    st->pending = 0;
+    st->last_seq = 0;
   }
 }
 
@@ -1603,7 +2194,7 @@ __global__ void __launch_bounds__(kThreads, 1) init_table_kernel(const InitTable
                                                  u.fr.halfrange[2] * m_cz));
     u.st->thresh = __double2float_ru(2.0 * E * 1.001 + 1e-37);
   }
-  build_centroid_buckets(u.table, u.k, u.kpad, u.fr);
+  build_centroid_buckets(fast, u.table + bucket_offset(u.kpad), u.k, u.kpad, u.fr);
 }
 
 // Reads the table back as K x 3 float64 centroids in original coordinates.

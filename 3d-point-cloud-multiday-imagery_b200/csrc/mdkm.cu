@@ -98,6 +98,7 @@ struct mdkm_handle {
   int opt_raster_mirror = 1;  // MDKM_OPT_RASTER_MIRROR
   int opt_cell_px = 0, opt_cell_rows = 0;  // MDKM_OPT_CELL_PX / MDKM_OPT_CELL_ROWS (0 = automatic)
   int opt_two_level = -1;                  // MDKM_OPT_TWO_LEVEL (-1 = automatic)
+  int opt_pdl = 1;                         // MDKM_OPT_DEPENDENT_LAUNCH
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // global min x,y,z / max x,y,z of the cloud
   DevStatus* d_status = nullptr;
   DevStatus* h_status = nullptr;  // pinned, 2 slots
@@ -158,6 +159,8 @@ struct mdkm_handle {
   PeerXchg px{};
   bool p2p_ok = false;
   unsigned long long epoch_base = 0;  // fused steps completed on this communicator
+  int step_seq = 0;                   // fused step launches since the last settle kernel (StepParams::seq)
+  size_t settle_smem = 0;
 
   // profiling: CUDA-event spans around the kernels of a phase (mdkm_profile_*)
   bool prof = false;
@@ -582,8 +585,8 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.final_smem = kp32 * 16 + bucket_bytes(k, kb.kpad);
   const long long cap = round_up(std::max<long long>(h->n, 1), kGroup);
   OK(ensure(h, h->labels, (size_t)cap * (kb.wide ? 2 : 1)));
-  OK(ensure(h, h->table, table_bytes(k, kb.kpad)));
-  OK(ensure(h, h->acc, 2 * ((size_t)kb.kpad * 4 + 8)));  // live sums + the copy parked on a pause
+  OK(ensure(h, h->table, 2 * table_bytes(k, kb.kpad)));  // fused launches alternate between two tables
+  OK(ensure(h, h->acc, 4 * ((size_t)kb.kpad * 4 + 8)));  // three rotating accumulators + the copy parked on a pause
   OK(ensure(h, h->dscratch, (size_t)std::max(64, k * 4 + 16)));
   OK(ensure(h, h->uscratch, 16));
   const long long tiles = (h->n + kThreads * 4 - 1) / (kThreads * 4);  // 8 warp-groups per CTA pass
@@ -656,10 +659,11 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
 UpdateParams make_update_params(mdkm_handle* h, const KmBuffers& kb, int allow_pause, int ignore_status) {
   UpdateParams up{};
   up.acc = h->acc.p;
-  up.acc_saved = h->acc.p + ((size_t)kb.kpad * 4 + 8);
+  up.acc_saved = h->acc.p + 3 * ((size_t)kb.kpad * 4 + 8);
   up.table = h->table.p;
   up.st = h->d_status;
   up.fr = h->fr;
+  for (int d = 0; d < 3; ++d) up.inv_scale[d] = 1.0 / h->fr.scale[d];
   for (int d = 0; d < 3; ++d) up.mean[d] = h->mean_ok ? h->mean[d] : h->fr.origin[d];
   up.k = kb.k; up.kpad = kb.kpad;
   up.allow_pause = allow_pause;
@@ -676,7 +680,10 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.pts = h->tpts.p; sp.n = h->n;  // the tile-ordered mirror; labels / summaries / worklist follow its order
   sp.labels = h->labels.p;
   sp.table = h->table.p;
+  sp.table_stride = table_bytes(kb.k, kb.kpad);
   sp.acc = h->acc.p;
+  sp.acc_slot = kb.kpad * 4 + 8;
+  sp.seq = fuse_update ? h->step_seq++ : 0;
   sp.st = h->d_status;
   sp.f = h->ff;
   sp.k = kb.k; sp.kpad = kb.kpad;
@@ -691,7 +698,7 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   }
   // pass 1 (inside the kernel): whole groups settled from their summaries; the rest lands in
   // the worklist that pass 2 streams point by point
-  int* work_count = h->worklist.p + kb.n_groups;
+  int* work_count = h->worklist.p + kb.n_groups;  // two counters (StepParams)
   sp.gsum = reinterpret_cast<const GroupSummary*>(h->gsum.p);
   sp.ssum = h->ssum.p;
   sp.worklist = h->worklist.p;
@@ -699,9 +706,32 @@ int launch_step(mdkm_handle* h, const KmBuffers& kb, int ignore_status, int fuse
   sp.glabel = h->glabel.p;
   sp.grid_bar = &h->d_status->grid_bar;
   // cooperative launch: the grid barrier between the two passes needs every CTA resident
+  // The first launch behind a settle kernel is cooperative (the runtime guarantees that the whole grid
+  // is resident, which the in-kernel grid barrier needs).  The following launches of the run use
+  // programmatic stream serialisation instead -- the runtime does not combine the two (measured: the
+  // cooperative attribute silently wins) --: the next kernel is set up while the current one drains
+  // (CTAs take the SM slots as the previous kernel's retire, shared memory is initialised) and waits
+  // for the previous grid's end before it reads anything (griddepcontrol.wait).  Its grid is the
+  // same full wave the cooperative launch was accepted with; the barrier's bounded wait flags the
+  // error if a foreign kernel ever kept part of it from becoming resident.  1.7 us per iteration.
   void* args[] = {&sp};
-  CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kb.step_fn), dim3(kb.step_grid), dim3(kThreads), args,
-                                 kb.step_smem, h->stream));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kb.step_grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kb.step_smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr;
+  if (fuse_update && h->opt_pdl && sp.seq > 0) {
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+  } else {
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+  }
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kb.step_fn), args);
+  CU(le);
   ++h->launches;
   if (!fuse_update) CU(cudaMemsetAsync(work_count, 0, 4, h->stream));
   return MDKM_OK;
@@ -712,6 +742,28 @@ int launch_update(mdkm_handle* h, const KmBuffers& kb, int allow_pause, int igno
   lloyd_update_kernel<<<1, kThreads, 0, h->stream>>>(up);
   ++h->launches;
   CU(cudaGetLastError());
+  return MDKM_OK;
+}
+
+// Behind a run of fused step launches: applies the pending update, restores the classic layout
+// (table[0], acc[0]) and restarts the launch numbering (lloyd.cuh: lloyd_settle_kernel).
+int launch_settle(mdkm_handle* h, const KmBuffers& kb) {
+  SettleParams sp{};
+  sp.upd = make_update_params(h, kb, /*allow_pause=*/1, 0);
+  sp.px = h->px;
+  if (h->n_ranks == 1 || !can_fuse(h)) sp.px.n_ranks = 1;
+  sp.table_stride = table_bytes(kb.k, kb.kpad);
+  sp.acc_slot = kb.kpad * 4 + 8;
+  sp.work_count = h->worklist.p + kb.n_groups;
+  const size_t smem = (size_t)kb.kpad * 48 + bucket_bytes(kb.k, kb.kpad);
+  if (smem > 48 * 1024 && h->settle_smem < smem) {
+    CU(cudaFuncSetAttribute(lloyd_settle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->settle_smem = smem;
+  }
+  lloyd_settle_kernel<<<1, kThreads, smem, h->stream>>>(sp);
+  ++h->launches;
+  CU(cudaGetLastError());
+  h->step_seq = 0;
   return MDKM_OK;
 }
 
@@ -1049,6 +1101,9 @@ int mdkm_set_option(mdkm_handle* h, int option, long long value) {
       return MDKM_OK;
     case MDKM_OPT_TWO_LEVEL:
       h->opt_two_level = value < 0 ? -1 : (value != 0);
+      return MDKM_OK;
+    case MDKM_OPT_DEPENDENT_LAUNCH:
+      h->opt_pdl = value != 0;
       return MDKM_OK;
     case MDKM_OPT_CELL_PX:
       if (value != 0 && value != 8 && value != 16) return fail(h, MDKM_ERR_INVALID, "cell width must be 0 (automatic), 8 or 16 pixels");
@@ -1443,104 +1498,123 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   st0.epoch = h->epoch_base;
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
-  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 4, h->stream));
+  const size_t acc_slot = (size_t)kb.kpad * 4 + 8;
+  CU(cudaMemsetAsync(h->acc.p, 0, 3 * acc_slot * 8, h->stream));
+  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 8, h->stream));
+  h->step_seq = 0;
   OK(upload_table(h, kb, init));
+
+  // the host-sequenced rare path (empty cluster): everything behind the pause has left early;
+  // relocate on the device from the parked global sums, finish the paused iteration
+  long long relocs = 0;
+  int guard = 0;
+  auto relocate_and_resume = [&](const DevStatus& s, int& enq) -> int {
+    if (!h->mean_ok) OK(compute_moments(h, nullptr));
+    CU(cudaMemcpyAsync(h->acc.p, h->acc.p + 3 * acc_slot, acc_slot * 8, cudaMemcpyDeviceToDevice, h->stream));
+    OK(relocate_empty(h, kb, s.n_empty));
+    relocs += s.n_empty;
+    OK(launch_update(h, kb, /*allow_pause=*/0, 0));
+    enq = s.iter + 1;
+    if (++guard > max_iter + 8) return fail(h, MDKM_ERR_STATE, "relocation loop did not terminate");
+    return MDKM_OK;
+  };
 
   // Lloyd loop: batches of iterations are enqueued back to back; the host only looks at the
   // device status between batches, one batch behind the GPU (no per-iteration sync).
   int enq = 0;  // iterations enqueued that can still complete
-  int inflight = 0, head = 0, tail = 0;
-  long long relocs = 0;
-  int guard = 0;
-  while (true) {
-    while (inflight < 2 && enq < max_iter) {
-      const int nb = std::min(kBatch, max_iter - enq);
-      // profiling: one event pair around the batch's step kernels (back-to-back launches, so
-      // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
-      const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
-      for (int b = 0; b < nb; ++b) {
-        if (can_fuse(h)) {
-          OK(launch_step(h, kb, 0, /*fuse_update=*/1));
-        } else {
-          OK(launch_step(h, kb, 0));
-          OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));
-          OK(launch_update(h, kb, /*allow_pause=*/1, 0));
+  for (;;) {  // (one pass, unless the very last update finds an empty cluster)
+    int inflight = 0, head = 0, tail = 0;
+    while (true) {
+      while (inflight < 2 && enq < max_iter) {
+        const int nb = std::min(kBatch, max_iter - enq);
+        // profiling: one event pair around the batch's step kernels (back-to-back launches, so
+        // the figure is immune to host-side enqueue gaps); only fused batches are bracketed
+        const int span = can_fuse(h) ? prof_begin(h, MDKM_PHASE_STEP, nb) : -1;
+        for (int b = 0; b < nb; ++b) {
+          if (can_fuse(h)) {
+            OK(launch_step(h, kb, 0, /*fuse_update=*/1));
+          } else {
+            OK(launch_step(h, kb, 0));
+            OK(allreduce(h, h->acc.p, acc_slot, kNcclUint64, kNcclSum));
+            OK(launch_update(h, kb, /*allow_pause=*/1, 0));
+          }
         }
+        prof_end(h, span);
+        OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
+        CU(cudaEventRecord(h->batch_ev[tail], h->stream));
+        tail ^= 1;
+        ++inflight;
+        enq += nb;
       }
-      prof_end(h, span);
-      OK(small_d2h(h, &h->h_status[tail], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
-      CU(cudaEventRecord(h->batch_ev[tail], h->stream));
-      tail ^= 1;
-      ++inflight;
-      enq += nb;
-    }
-    if (inflight == 0) break;
-    if (inflight == 2 && enq >= max_iter) {
-      // nothing more to enqueue: the newer batch's status supersedes the older one (a pause or
-      // an early exit makes every later kernel return at once), so wait only for that
+      if (inflight == 0) break;
+      if (inflight == 2 && enq >= max_iter) {
+        // nothing more to enqueue: the newer batch's status supersedes the older one (a pause or
+        // an early exit makes every later kernel return at once), so wait only for that
+        head ^= 1;
+        --inflight;
+      }
+      CU(cudaEventSynchronize(h->batch_ev[head]));
+      const DevStatus s = h->h_status[head];
       head ^= 1;
       --inflight;
+      if (s.paused && !s.done) {
+        CU(cudaStreamSynchronize(h->stream));
+        inflight = 0;
+        head = tail = 0;
+        if (can_fuse(h)) OK(launch_settle(h, kb));  // the table the paused update starts from -> table[0]
+        OK(relocate_and_resume(s, enq));
+        continue;
+      }
+      if (s.done) break;
     }
-    CU(cudaEventSynchronize(h->batch_ev[head]));
-    const DevStatus s = h->h_status[head];
-    head ^= 1;
-    --inflight;
-    if (s.paused && !s.done) {
-      // rare path (empty cluster): everything behind the pause exits early; drain, relocate
-      // on the device, finish the paused iteration, resume enqueueing after it
+    // (no synchronisation here: everything below is ordered behind the loop on the stream)
+    // fused launches leave the last E-step's update to their successor: apply it now
+    if (can_fuse(h)) OK(launch_settle(h, kb));
+
+    // final E-step (unless strict) + inertia + int32 labels
+    int* labels_dev = nullptr;
+    if (labels_out) {
+      if (labels_mem == MDKM_MEM_DEVICE) {
+        labels_dev = labels_out;
+      } else {
+        OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
+        labels_dev = h->labels32.p;
+      }
+    }
+    // labels in the reference's point order: always recomputed from the final centroids (the
+    // stored ones follow the mirror's order).  After a strict exit the table equals the one the
+    // last E-step used -- the sums are integers -- so this reproduces that step's labels exactly.
+    {
+      const int span = prof_begin(h, MDKM_PHASE_FINAL, h->n);
+      OK(run_final(h, kb, labels_dev));
+      prof_end(h, span);
+    }
+    OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
+    read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
+    if (centroids_out) OK(small_d2h(h, centroids_out, h->dscratch.p, (size_t)k * 3 * sizeof(double)));
+    OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
+    if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
+      CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    OK(sync_small(h));
+    if (h->h_status[0].paused && !h->h_status[0].done && !h->h_status[0].xchg_timeout) {
+      // the settle kernel found an empty cluster in the very last update: relocate, go on
+      const DevStatus s = h->h_status[0];
       CU(cudaStreamSynchronize(h->stream));
-      inflight = 0;
-      head = tail = 0;
-      if (!h->mean_ok) OK(compute_moments(h, nullptr));
-      CU(cudaMemcpyAsync(h->acc.p, h->acc.p + ((size_t)kb.kpad * 4 + 8), ((size_t)kb.kpad * 4 + 8) * 8,
-                         cudaMemcpyDeviceToDevice, h->stream));
-      OK(relocate_empty(h, kb, s.n_empty));
-      relocs += s.n_empty;
-      OK(launch_update(h, kb, /*allow_pause=*/0, 0));
-      enq = s.iter + 1;
-      if (++guard > max_iter + 8) return fail(h, MDKM_ERR_STATE, "relocation loop did not terminate");
+      OK(relocate_and_resume(s, enq));
       continue;
     }
-    if (s.done) break;
+    break;
   }
-  // (no synchronisation here: everything below is ordered behind the loop on the stream)
-
-  // final E-step (unless strict) + inertia + int32 labels
-  int* labels_dev = nullptr;
-  if (labels_out) {
-    if (labels_mem == MDKM_MEM_DEVICE) {
-      labels_dev = labels_out;
-    } else {
-      OK(ensure(h, h->labels32, (size_t)std::max<long long>(h->n, 1)));
-      labels_dev = h->labels32.p;
-    }
-  }
-  // labels in the reference's point order: always recomputed from the final centroids (the
-  // stored ones follow the mirror's order).  After a strict exit the table equals the one the
-  // last E-step used -- the sums are integers -- so this reproduces that step's labels exactly.
-  {
-    const int span = prof_begin(h, MDKM_PHASE_FINAL, h->n);
-    OK(run_final(h, kb, labels_dev));
-    prof_end(h, span);
-  }
-  OK(ensure(h, h->dscratch, (size_t)k * 3 + 16));
-  read_table_kernel<<<(k + 255) / 256, 256, 0, h->stream>>>(h->table.p, k, kb.kpad, h->fr, h->dscratch.p);
-  ++h->launches;
-  CU(cudaGetLastError());
-  if (h->n_ranks > 1) OK(allreduce(h, &h->d_status->inertia, 1, kNcclFloat64, kNcclSum));
-  if (centroids_out) OK(small_d2h(h, centroids_out, h->dscratch.p, (size_t)k * 3 * sizeof(double)));
-  OK(small_d2h(h, &h->h_status[0], h->d_status, sizeof(DevStatus), /*dst_is_pinned=*/true));
-  if (labels_out && labels_mem != MDKM_MEM_DEVICE && h->n > 0)
-    CU(cudaMemcpyAsync(labels_out, labels_dev, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
-  OK(sync_small(h));
   const DevStatus& fin = h->h_status[0];
   h->epoch_base = fin.epoch;
 #ifdef MDKM_TIMING
-  fprintf(stderr, "[mdkm timing] last iteration: latest end of pass 1 +%.1f us | after grid barrier +%.1f us | CTAs done on average +%.1f us, last +%.1f us | update done +%.1f us\n",
-          ((double)fin.t_first_done - (double)fin.t_start) * 1e-3, (fin.t_classify_done - fin.t_start) * 1e-3,
-          (double)fin.t_update_done * 1e-3 / std::max(1, kb.step_grid), (fin.t_last_done - fin.t_start) * 1e-3,
-          ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3);
+  fprintf(stderr, "[mdkm timing] last iteration: table ready +%.1f us | latest end of pass 1 +%.1f us | after grid barrier +%.1f us | CTAs done on average +%.1f us, last +%.1f us\n",
+          ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3, ((double)fin.t_first_done - (double)fin.t_start) * 1e-3,
+          (fin.t_classify_done - fin.t_start) * 1e-3, (double)fin.t_update_done * 1e-3 / std::max(1, kb.step_grid),
+          (fin.t_last_done - fin.t_start) * 1e-3);
 #endif
   if (fin.xchg_timeout) return fail(h, MDKM_ERR_NCCL, "a kernel-side wait timed out (peer exchange of the partial sums: a rank is missing; or the grid barrier)");
   if (n_iter_out) *n_iter_out = fin.iter;
@@ -1583,7 +1657,7 @@ int mdkm_lloyd_step(mdkm_handle* h, int k, const double* centroids, int32_t* lab
   h->h_status[0] = st0;
   CU(cudaMemcpyAsync(h->d_status, &h->h_status[0], sizeof(DevStatus), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->acc.p, 0, ((size_t)kb.kpad * 4 + 8) * 8, h->stream));
-  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 4, h->stream));
+  CU(cudaMemsetAsync(h->worklist.p + kb.n_groups, 0, 8, h->stream));
   OK(upload_table(h, kb, centroids));
   OK(launch_step(h, kb, 1));
   OK(allreduce(h, h->acc.p, (size_t)kb.kpad * 4 + 8, kNcclUint64, kNcclSum));

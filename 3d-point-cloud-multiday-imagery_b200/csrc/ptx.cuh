@@ -136,6 +136,22 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   return v;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialisation attribute
+// may start while its predecessor in the stream still runs; it must not touch the predecessor's
+// results before grid_dependency_wait() (a no-op for ordinary launches).
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// gpu-scope release / acquire on a 32-bit flag (one CTA announces, the others of the grid wait)
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // 8-byte (value, flag) packets: one store / one load each, so a reader never sees one without the other
 __device__ __forceinline__ void st_relaxed_sys_v2u32(void* p, unsigned int a, unsigned int b) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");

@@ -103,9 +103,13 @@ void* mdkm_get_stream(const mdkm_handle* h);
  * MDKM_OPT_CELL_PX (0 = automatic, 8 or 16) / MDKM_OPT_CELL_ROWS (0 = automatic, 1..64): width and
  * height, in pixels, of the x-y cells the mirror of a raster cloud is ordered by (tuning).
  * MDKM_OPT_TWO_LEVEL (-1 = automatic by cloud size, 0, 1): whether the classification pass of the
- * Lloyd kernel tests super-groups of 1024 points before it looks at 128-point groups. */
+ * Lloyd kernel tests super-groups of 1024 points before it looks at 128-point groups.
+ * MDKM_OPT_DEPENDENT_LAUNCH (default 1): after the first (cooperative) Lloyd kernel of a fit, the
+ * following ones are launched with programmatic stream serialisation -- the next iteration's kernel
+ * is set up while the current one drains -- instead of the cooperative attribute (the runtime does
+ * not combine the two); 0 = every launch cooperative.  Results are identical. */
 enum { MDKM_OPT_SETTLE_GROUPS = 1, MDKM_OPT_RASTER_MIRROR = 2, MDKM_OPT_CELL_PX = 3, MDKM_OPT_CELL_ROWS = 4,
-       MDKM_OPT_TWO_LEVEL = 5 };
+       MDKM_OPT_TWO_LEVEL = 5, MDKM_OPT_DEPENDENT_LAUNCH = 6 };
 int mdkm_set_option(mdkm_handle* h, int option, long long value);
 
 /* ---- K1: unprojection ----------------------------------------------------------------
