@@ -1690,8 +1690,13 @@ __device__ __forceinline__ int deferred_update_rows(const UpdateParams& u, const
 template <typename LabT>
 __host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGroup * (int)sizeof(LabT); }
 
+// (Handing the tail of the worklist out dynamically -- an atomic claim per entry, 16 counters, two
+// steps ahead of the ring -- was measured: the claims' latency under load stalls the warps more than
+// the static round-robin's imbalance costs; config 2 +3.7 us, config 5 +67 us per iteration.  Not kept.)
+// Tables of more than 256 rows (16-bit labels) leave room for two CTAs per SM only (shared memory), so
+// those kernels may use up to 128 registers.
 template <typename LabT, bool kPrivate, int kChunks>
-__global__ void __launch_bounds__(kThreads, 3) lloyd_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, sizeof(LabT) == 2 ? 2 : 3) lloyd_step_kernel(const StepParams p) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kStageB = stage_bytes<LabT>();
   constexpr int kLabB = kGroup * (int)sizeof(LabT);

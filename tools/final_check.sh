@@ -18,7 +18,7 @@ python bench.py $args > $out/plain_$tag.log 2>&1 &&
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 500 --csv \
   --log-file $out/launches_$tag.csv python bench.py $args > $out/ncu1_$tag.log 2>&1
 # steady-state iterations of a fit, caches left as the previous kernels left them (what a fit sees)
-timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:lloyd_step -s 40 -c 2 -f \
+timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:lloyd_step -s 47 -c 2 -f \
   -o $out/prof_step_$tag python bench.py $args > $out/ncu2_$tag.log 2>&1
 # the once-per-cloud kernels and the final pass
 timeout 300 ncu --set full --clock-control none --import-source on \
