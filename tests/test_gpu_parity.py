@@ -512,6 +512,44 @@ def test_two_level_classification_equals_flat(engine, shape, k):
     check_labels(P, ref["centers"], ref["labels"], res[1]["labels"])
 
 
+@pytest.mark.parametrize("shape,k", [((3, 200, 256), 7), ((2, 300, 520), 40), ((1, 64, 2048), 300)])
+def test_dependent_launch_equals_cooperative_launch(engine, shape, k):
+    """After the first (cooperative) launch of a fit the Lloyd kernels use programmatic stream
+    serialisation (MDKM_OPT_DEPENDENT_LAUNCH, default on); with every launch cooperative the fit
+    must be the same, bit for bit."""
+    cabi = importlib.import_module("3d-point-cloud-multiday-imagery_b200._cabi")
+    hm = synth.make_stack(*shape, seed=k + 1, n_buildings=10).numpy()
+    engine.unproject(hm)
+    init = synth.init_from_points(engine.get_cloud(False), k, 2)
+    res = {}
+    try:
+        for mode in (0, 1):
+            engine.set_option(cabi.OPT_DEPENDENT_LAUNCH, mode)
+            res[mode] = engine.fit(init, max_iter=25, tol=0.0)
+    finally:
+        engine.set_option(cabi.OPT_DEPENDENT_LAUNCH, 1)
+    assert res[0]["centers"].tobytes() == res[1]["centers"].tobytes() and res[0]["n_iter"] == res[1]["n_iter"]
+    assert np.array_equal(res[0]["labels"], res[1]["labels"]) and res[0]["inertia"] == res[1]["inertia"]
+
+
+@pytest.mark.parametrize("k", [5, 48, 300])
+def test_deferred_update_iteration_counts(engine, k):
+    """The centroid update of an iteration is applied by the NEXT launch (or by the settle kernel
+    behind the last one).  Whatever max_iter is -- one iteration, the end of a batch of launches, one
+    past it, convergence in the middle of a batch -- centroids, labels and n_iter must equal the
+    oracle's."""
+    hm = synth.make_stack(2, 160, 192, seed=11 + k, n_buildings=8).numpy()
+    engine.unproject(hm)
+    P = UO.unproject_stack(hm)
+    init = synth.init_from_points(P.astype(np.float32), k, 4)
+    for max_iter, tol in ((1, 0.0), (2, 0.0), (10, 0.0), (11, 0.0), (21, 0.0), (300, 1e-4), (300, 0.0)):
+        res = engine.fit(init, max_iter=max_iter, tol=tol)
+        ref = KO.kmeans_fit(P, init, max_iter=max_iter, tol=tol)
+        assert res["n_iter"] == ref["n_iter"], (max_iter, tol, res["n_iter"], ref["n_iter"])
+        check_labels(P, ref["centers"], ref["labels"], res["labels"])
+        check_centroids(ref["centers"], res["centers"], P)
+
+
 def test_fit_errors(engine):
     engine.set_points(np.zeros((3, 3), dtype=np.float32))
     with pytest.raises(Exception, match="n_samples=3 should be >= n_clusters=4"):
