@@ -355,6 +355,28 @@ def test_fit_relocation_golden(engine, golden):
     check_centroids(g["centers"], r["centers"], X)
 
 
+@pytest.mark.parametrize("max_iter", [1, 2, 3, 11])
+def test_fit_relocation_at_any_iteration_count(engine, golden, max_iter):
+    """An empty cluster is found by the update, and the update of an iteration is applied by the next
+    launch -- or by the settle kernel when it was the last one (max_iter = 1 here: the host then
+    relocates after the final pass was already enqueued and goes round again).  Against live
+    scikit-learn on the relocation fixture's data."""
+    from oracle import sklearn_ref
+
+    if not sklearn_ref.available():
+        pytest.skip("scikit-learn not importable")
+    g = golden("kmeans_relocate.npz")
+    X = g["X"].astype(np.float64)
+    engine.set_points(g["X"])
+    r = engine.fit(g["init"], max_iter=max_iter, tol=0.0)
+    ref = sklearn_ref.fit(X, g["init"], max_iter=max_iter, tol=0.0)
+    assert r["n_relocations"] >= 1
+    assert r["n_iter"] == ref["n_iter"]
+    check_labels(X, ref["centers"], ref["labels"], r["labels"])
+    check_centroids(ref["centers"], r["centers"], X)
+    np.testing.assert_allclose(r["inertia"], ref["inertia"], rtol=1e-6)  # (as test_fit_relocation_golden)
+
+
 def test_fit_sklearn_known_answers(engine):
     # sklearn/cluster/tests/test_k_means.py:85-111, padded to d = 3 (unit weights)
     X = np.array([[0, 0, 0], [0.5, 0, 0], [0.5, 1, 0], [1, 1, 0]], dtype=np.float32)
