@@ -54,6 +54,7 @@ struct DevStatus {
   unsigned long long work_sum;    // groups handed to the per-point pass, summed over the fused steps of a fit
   // diagnostics (MDKM_TIMING builds only): globaltimer stamps of the last fused step, ns
   unsigned long long t_start, t_first_done, t_last_done, t_update_done, t_classify_start, t_classify_done;
+  unsigned long long t_a, t_b;  // stamps inside the deferred update
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

@@ -1,6 +1,11 @@
 // Lloyd k-means kernels for d = 3 on sm_100a.
 //
-//   lloyd_step_kernel   ONE kernel per Lloyd iteration (cooperative launch):
+//   lloyd_step_kernel   ONE kernel per Lloyd iteration:
+//                         prologue  the centroid update the PREVIOUS iteration left behind
+//                                 (_k_means_common.pyx:274-311, _kmeans.py:721-738: average, centre
+//                                 shift, convergence test, next centroid table), applied from its
+//                                 sums -- gathered from the peer ranks' NVLink packets when there are
+//                                 several -- by every CTA (deferred_update_rows / deferred_update);
 //                         pass 1  classification: whole 128-point groups settled from their
 //                                 cached summaries (box + fixed-point sums), no point read;
 //                         --      grid barrier;
@@ -9,10 +14,10 @@
 //                                 (sklearn/cluster/_k_means_lloyd.pyx:168-218; the reference
 //                                 reaches it through KMeans.fit at
 //                                 members/jasraj/land_use_classification/core.py:227-228);
-//                         tail    the last CTA completes the sums (peer exchange over NVLink
-//                                 when there are several ranks) and runs the centroid update,
-//                                 centre shift, convergence test and next centroid table
-//                                 (_k_means_common.pyx:274-311, _kmeans.py:721-738).
+//                         end     the sums go to acc[seq % 3]; with several ranks the last CTA
+//                                 sends them to the peers; nobody waits.
+//   lloyd_settle_kernel the update still pending behind the last launch of a run; table / buffers
+//                       back to the layout every other kernel expects
 //   lloyd_update_kernel the update alone (NCCL exchange path, and after a relocation)
 //   lloyd_final_kernel  labels in the reference's point order from the final centroids +
 //                       inertia + int32 labels (_kmeans.py:742-756, _k_means_common.pyx:94-124)
@@ -344,8 +349,9 @@ struct StepParams {
   FrameF f;
   int k, kpad;
   int ignore_status;          // 1: test hook (run even when done/paused)
-  int fuse_update;            // 1: the last CTA to finish exchanges the sums with the peer ranks
-                              //    (NVLink, no host, no NCCL) and runs the centroid update
+  int fuse_update;            // 1: fused run -- this launch applies the update the previous one left behind (seq > 0),
+                              //    adds into the rotating accumulators and, with several ranks, sends its sums to the
+                              //    peers (NVLink, no host, no NCCL); 0: the host exchanges and updates between launches
   int two_level;              // 1: classification pass walks super-groups first (large clouds)
   int settle;                 // 0: measurement mode, no group is settled from its summary --
                               //    every point goes through the per-point pass (MDKM_OPT_SETTLE_GROUPS)
@@ -1586,6 +1592,9 @@ __device__ __forceinline__ int deferred_update_rows(const UpdateParams& u, const
   }
   if (tid == kThreads - 1) ds.nchg = r.nchg;
   const int n_empty = __syncthreads_count(tid < u.k && r.b.y == 0ull);
+#ifdef MDKM_TIMING
+  if (writer && tid == 0) st->t_a = globaltimer_ns();
+#endif
   if (n_empty > 0) {
     // the host sequences the relocation kernels on the parked (global) sums and re-runs the update
     if (writer) {
@@ -1651,6 +1660,9 @@ __device__ __forceinline__ int deferred_update_rows(const UpdateParams& u, const
     ds.red[0][w] = shift2; ds.red[1][w] = m_cn; ds.red[2][w] = m_cx; ds.red[3][w] = m_cy; ds.red[4][w] = m_cz;
   }
   __syncthreads();
+#ifdef MDKM_TIMING
+  if (writer && tid == 0) st->t_b = globaltimer_ns();
+#endif
   // every thread combines the warps' partials itself (no broadcast barrier)
   shift2 = 0.0; m_cn = 0.0; m_cx = 0.0; m_cy = 0.0; m_cz = 0.0;
 #pragma unroll

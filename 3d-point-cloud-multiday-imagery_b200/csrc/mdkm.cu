@@ -1611,6 +1611,8 @@ int mdkm_fit(mdkm_handle* h, int k, const double* init, int max_iter, double tol
   const DevStatus& fin = h->h_status[0];
   h->epoch_base = fin.epoch;
 #ifdef MDKM_TIMING
+  fprintf(stderr, "[mdkm timing] deferred update: sums and vote +%.2f us | rows and reductions +%.2f us\n",
+          ((double)fin.t_a - (double)fin.t_start) * 1e-3, ((double)fin.t_b - (double)fin.t_start) * 1e-3);
   fprintf(stderr, "[mdkm timing] last iteration: table ready +%.1f us | latest end of pass 1 +%.1f us | after grid barrier +%.1f us | CTAs done on average +%.1f us, last +%.1f us\n",
           ((double)fin.t_classify_start - (double)fin.t_start) * 1e-3, ((double)fin.t_first_done - (double)fin.t_start) * 1e-3,
           (fin.t_classify_done - fin.t_start) * 1e-3, (double)fin.t_update_done * 1e-3 / std::max(1, kb.step_grid),
