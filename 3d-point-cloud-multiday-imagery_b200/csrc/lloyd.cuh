@@ -800,6 +800,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, int* timeout
   __syncthreads();
 }
 
+#ifndef MDKM_FINAL_CTAS0
+#define MDKM_FINAL_CTAS0 3
+#endif
 struct FinalParams {
   const float* pts;           // resident cloud, reference point order
   long long n;
@@ -2310,7 +2313,7 @@ __device__ __forceinline__ void final_emit(const FinalParams& p, const double4* 
 // -> int32 labels, and the inertia in FP64 (direct form, fixed-order reduction).
 // ---------------------------------------------------------------------------------------
 template <int kChunks>
-__global__ void __launch_bounds__(kThreads, 3) lloyd_final_kernel(const FinalParams p) {
+__global__ void __launch_bounds__(kThreads, kChunks == 0 ? MDKM_FINAL_CTAS0 : 3) lloyd_final_kernel(const FinalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kp32 = kChunks > 0 ? kChunks * 32 : ((p.kpad + 31) & ~31);
   float4* s_fast = reinterpret_cast<float4*>(smem_raw);

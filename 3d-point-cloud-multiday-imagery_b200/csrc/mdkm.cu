@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/mdkm.h"
@@ -161,6 +162,7 @@ struct mdkm_handle {
   unsigned long long epoch_base = 0;  // fused steps completed on this communicator
   int step_seq = 0;                   // fused step launches since the last settle kernel (StepParams::seq)
   size_t settle_smem = 0;
+  std::map<const void*, int> occ_cache;  // resident CTAs per SM of the grid-stride kernels
 
   // profiling: CUDA-event spans around the kernels of a phase (mdkm_profile_*)
   bool prof = false;
@@ -266,6 +268,24 @@ int grid_for(const mdkm_handle* h, long long work_items, int per_sm) {
   return (int)std::max<long long>(1, g);
 }
 
+// CTAs of `fn` (kThreads threads, `smem` bytes of dynamic shared memory) that are resident on one SM
+// at a time, as the runtime reports it (cached per kernel).  Grid-stride kernels are launched as ONE
+// full wave: a grid of 8 CTAs per SM for a kernel of which 6 fit runs a second, one-third-full wave
+// at a fraction of the bandwidth (raster_gather_kernel: 213 -> 19x us on config 2).
+template <typename Kernel>
+int resident_per_sm(mdkm_handle* h, Kernel fn, size_t smem = 0) {
+  const void* key = reinterpret_cast<const void*>(fn);
+  auto it = h->occ_cache.find(key);
+  if (it != h->occ_cache.end()) return it->second;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 4;
+  }
+  h->occ_cache[key] = occ;
+  return occ;
+}
+
 // Blocks until the asynchronous result copies issued so far have landed in host memory.
 int wait_pending(mdkm_handle* h) {
   if (h->d2h_pending) {
@@ -324,7 +344,7 @@ int compute_frame(mdkm_handle* h, bool minmax_ready = false) {
   unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   if (!minmax_ready) CU(cudaMemcpyAsync(h->uscratch.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   if (h->n > 0 && !minmax_ready) {
-    minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, 8), kThreads, 0, h->stream>>>(h->pts.p, h->n,
+    minmax_kernel<<<grid_for(h, (h->n + 1023) / 1024, resident_per_sm(h, minmax_kernel)), kThreads, 0, h->stream>>>(h->pts.p, h->n,
                                                                                      h->uscratch.p + 4);
     ++h->launches;
     CU(cudaGetLastError());
@@ -555,14 +575,14 @@ int build_mirror_raster(mdkm_handle* h, int cell_px) {
     CU(cudaGetLastError());
     return MDKM_OK;
   }
-  const int cgrid = grid_for(h, (n_cells + 7) / 8, 16);  // one warp per cell
+  const int cgrid = grid_for(h, (n_cells + 7) / 8, std::min(resident_per_sm(h, raster_cell_count_kernel), resident_per_sm(h, raster_runs_kernel)));  // one warp per cell
   raster_cell_count_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_counts.p);
   long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
   mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
   mirror_scan_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, tile_sums);
   raster_runs_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_offsets.p, h->n, reinterpret_cast<uint2*>(h->druns.p),
                                                         h->gfirst.p);
-  raster_gather_kernel<<<grid_for(h, (n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
+  raster_gather_kernel<<<grid_for(h, (n_groups + 7) / 8, resident_per_sm(h, raster_gather_kernel)), kThreads, 0, h->stream>>>(
       h->pts.p, h->n, reinterpret_cast<const uint2*>(h->druns.p), n_entries, h->gfirst.p, h->ff, h->tpts.p,
       reinterpret_cast<float4*>(h->gsum.p));
   h->launches += 5;
@@ -624,7 +644,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
       OK(build_mirror_raster(h, cell_px));
     } else {
       OK(build_mirror(h, k <= 16 ? 16 : 8));
-      group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, 8), kThreads, 0, h->stream>>>(
+      group_summary_kernel<<<grid_for(h, (kb.n_groups + 7) / 8, resident_per_sm(h, group_summary_kernel)), kThreads, 0, h->stream>>>(
           h->tpts.p, h->n, h->ff, reinterpret_cast<GroupSummary*>(h->gsum.p));
       ++h->launches;
       CU(cudaGetLastError());
@@ -639,7 +659,7 @@ int prepare_kmeans(mdkm_handle* h, int k, KmBuffers& kb) {
   kb.two_level = h->opt_two_level >= 0 ? h->opt_two_level != 0 : kb.n_groups > 6ll * kb.step_grid * kThreads;
   if (kb.two_level && !h->ssum_ok) {  // super-group summaries: only when they will be used
     const int span = prof_begin(h, MDKM_PHASE_BUILD, 0);
-    super_summary_kernel<<<grid_for(h, (kb.n_groups + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+    super_summary_kernel<<<grid_for(h, (kb.n_groups + kThreads - 1) / kThreads, resident_per_sm(h, super_summary_kernel)), kThreads, 0, h->stream>>>(
         reinterpret_cast<const GroupSummary*>(h->gsum.p), (int)kb.n_groups, reinterpret_cast<SuperSummary*>(h->ssum.p));
     ++h->launches;
     CU(cudaGetLastError());
@@ -1438,7 +1458,7 @@ static int get_cloud_impl(mdkm_handle* h, float* out, int napari_order, int mem,
     OK(ensure(h, h->cloud_aos, (size_t)h->n * 3));
     dst = h->cloud_aos.p;
   }
-  blocked_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, 8), kThreads, 0, h->stream>>>(
+  blocked_to_aos_kernel<<<grid_for(h, (h->n * 3 + kThreads - 1) / kThreads, resident_per_sm(h, blocked_to_aos_kernel)), kThreads, 0, h->stream>>>(
       h->pts.p, h->n, napari_order, dst);
   ++h->launches;
   CU(cudaGetLastError());

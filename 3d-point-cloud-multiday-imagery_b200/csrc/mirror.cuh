@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(kThreads) mirror_scatter_kernel(const float* p
 // be mirror_count + mirror_scatter + group_summary_kernel.  The order inside a cell is fixed
 // (day, row, x), so the mirror is deterministic.
 // =======================================================================================
+#ifndef MDKM_GATHER_CTAS
+#define MDKM_GATHER_CTAS 6
+#endif
 struct RasterGeom {
   const unsigned int* run_src;  // [n_rows * nb8 + 1]
   long long row0;   // global row (day * H + y) of the first row of the range
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kThreads) raster_runs_kernel(const RasterGeom 
 // the run list (32 entries per window, binary search by shuffles), fetch, write the block, emit
 // the summary.  `summaries` is an array of 48-byte GroupSummary records (lloyd.cuh), written as
 // three float4 here to keep this header independent of it.
-__global__ void __launch_bounds__(kThreads) raster_gather_kernel(const float* __restrict__ pts, long long n,
+__global__ void __launch_bounds__(kThreads, MDKM_GATHER_CTAS) raster_gather_kernel(const float* __restrict__ pts, long long n,
                                                                  const uint2* __restrict__ druns, long long n_entries,
                                                                  const unsigned int* __restrict__ gfirst, FrameF f,
                                                                  float* __restrict__ tpts, float4* __restrict__ summaries) {
