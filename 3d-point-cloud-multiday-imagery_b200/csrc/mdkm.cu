@@ -1288,8 +1288,12 @@ int mdkm_unproject(mdkm_handle* h, const void* hm, int hm_dtype, float hm_scale,
       cut.push_back(pix_count);
     } else {
       long long next_day = detrend ? HW : pix_count;
+      // (the first slabs are small so that the result copies start early: the end-to-end call is bound
+      // by the device-to-host link, which idles until the first slab has been unprojected)
+      long long slab = kSlabPix / 8;
       for (long long p = 0; p < pix_count;) {
-        long long e = std::min<long long>(pix_count, p + kSlabPix);
+        long long e = std::min<long long>(pix_count, p + slab);
+        slab = std::min<long long>(kSlabPix, slab * 2);
         if (detrend && e > next_day) e = next_day;
         if (e == next_day) next_day += HW;
         cut.push_back(e);
