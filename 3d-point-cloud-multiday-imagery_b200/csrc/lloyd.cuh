@@ -1708,6 +1708,8 @@ __host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGro
 // (Handing the tail of the worklist out dynamically -- an atomic claim per entry, 16 counters, two
 // steps ahead of the ring -- was measured: the claims' latency under load stalls the warps more than
 // the static round-robin's imbalance costs; config 2 +3.7 us, config 5 +67 us per iteration.  Not kept.)
+// (Letting the last label of a mixed group take what the others left of the group's totals -- one round
+// of masked sums less -- was measured too: +0.6 us on config 2, +2 us on the config-3 shape.  Not kept.)
 // Tables of more than 256 rows (16-bit labels) leave room for two CTAs per SM only (shared memory), so
 // those kernels may use up to 128 registers.
 template <typename LabT, bool kPrivate, int kChunks>
