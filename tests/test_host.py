@@ -44,6 +44,38 @@ def test_ctypes_prototypes_cover_header(built):
     assert lib.mdkm_version().decode().endswith("sm_100a")
 
 
+def test_ctypes_constants_match_header():
+    """Option / memory / dtype / phase constants of the Python binding against the enums of the header."""
+    cabi = importlib.import_module(PKG + "._cabi")
+    txt = open(os.path.join(ROOT, "include", "mdkm.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    enums = {}
+    for body in re.findall(r"enum\s*\w*\s*\{(.*?)\}", txt, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, val = (t.strip() for t in item.split("=", 1))
+                nxt = int(val, 0)
+            else:
+                name = item
+            enums[name] = nxt
+            nxt += 1
+    checked = 0
+    for name, val in vars(cabi).items():
+        for prefix in ("OPT_", "MEM_", "HM_", "PHASE_", "POINTS_"):
+            if name.startswith(prefix) and isinstance(val, int) and "MDKM_" + name in enums:
+                assert enums["MDKM_" + name] == val, (name, val, enums["MDKM_" + name])
+                checked += 1
+    assert checked >= 12, checked
+    assert enums["MDKM_OPT_DEPENDENT_LAUNCH"] == cabi.OPT_DEPENDENT_LAUNCH
+    for name, code in cabi.STATUS_BY_NAME.items():
+        if name in enums:
+            assert enums[name] == code, name
+
+
 def test_library_is_sm100a_only(built):
     import shutil
     import subprocess
