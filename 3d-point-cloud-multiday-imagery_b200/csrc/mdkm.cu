@@ -575,8 +575,9 @@ int build_mirror_raster(mdkm_handle* h, int cell_px) {
     CU(cudaGetLastError());
     return MDKM_OK;
   }
-  const int cgrid = grid_for(h, (n_cells + 7) / 8, std::min(resident_per_sm(h, raster_cell_count_kernel), resident_per_sm(h, raster_runs_kernel)));  // one warp per cell
-  raster_cell_count_kernel<<<cgrid, kThreads, 0, h->stream>>>(g, h->cell_counts.p);
+  const int cgrid = grid_for(h, (n_cells + 7) / 8, resident_per_sm(h, raster_runs_kernel));  // one warp per cell
+  raster_cell_count_kernel<<<grid_for(h, (n_cells + kThreads - 1) / kThreads, resident_per_sm(h, raster_cell_count_kernel)), kThreads, 0,
+                             h->stream>>>(g, h->cell_counts.p);  // one thread per cell
   long long* tile_sums = reinterpret_cast<long long*>(h->partials.p);
   mirror_tile_sums_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, tile_sums);
   mirror_scan_kernel<<<n_tiles, 1024, 0, h->stream>>>(h->cell_counts.p, n_cells, h->cell_offsets.p, tile_sums);

@@ -280,22 +280,23 @@ __device__ __forceinline__ unsigned int raster_run(const RasterGeom& g, int cxi,
   return __ldg(g.run_src + j1) - src;
 }
 
-// points per cell.  One WARP per cell, one lane per (day, row) run: the loads of a cell's runs
-// are in flight together instead of one after the other.
+// points per cell.  One THREAD per cell, consecutive threads on consecutive cells of a row of cells:
+// the run-table entries a warp asks for in one step are neighbours (coalesced 8-byte strides), a
+// quarter of the sectors the one-warp-per-cell form touched (lanes over the (day, row) runs: one
+// sector per lane).
 __global__ void __launch_bounds__(kThreads) raster_cell_count_kernel(const RasterGeom g, unsigned int* counts) {
-  const int n_cells = g.gx * g.gy, per_cell = g.nd * g.rpc, lane = threadIdx.x & 31;
-  const int stride = gridDim.x * (kThreads / 32);
-  for (int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < n_cells; c += stride) {
+  const int n_cells = g.gx * g.gy, per_cell = g.nd * g.rpc;
+  for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_cells; c += gridDim.x * kThreads) {
     const int cyi = c / g.gx, cxi = c - cyi * g.gx;
     unsigned int tot = 0;
-    const float inv_rpc = 1.0f / (float)g.rpc;  // e / rpc without an integer division
-    for (int e = lane; e < per_cell; e += 32) {
+    int dd = 0, ry = 0;
+#pragma unroll 4
+    for (int e = 0; e < per_cell; ++e) {
       unsigned int src;
-      const int dd = per_cell <= 4096 ? (int)(((float)e + 0.5f) * inv_rpc) : e / g.rpc;  // (checked exact for e < 4096)
-      tot += raster_run(g, cxi, cyi, dd, e - dd * g.rpc, src);
+      tot += raster_run(g, cxi, cyi, dd, ry, src);
+      if (++ry == g.rpc) { ry = 0; ++dd; }
     }
-    tot = __reduce_add_sync(0xffffffffu, tot);
-    if (lane == 0) counts[raster_cell_index(g, cxi, cyi)] = tot;
+    counts[raster_cell_index(g, cxi, cyi)] = tot;
   }
 }
 
