@@ -1708,6 +1708,11 @@ __host__ __device__ constexpr int stage_bytes() { return kBlockFloats * 4 + kGro
 // (Handing the tail of the worklist out dynamically -- an atomic claim per entry, 16 counters, two
 // steps ahead of the ring -- was measured: the claims' latency under load stalls the warps more than
 // the static round-robin's imbalance costs; config 2 +3.7 us, config 5 +67 us per iteration.  Not kept.)
+// (Two more hand-out schemes were measured after that: the warps of a CTA drawing their CTA's share from a
+// shared-memory counter -- no change --, and a quarter of the list kept as a pool the CTAs draw from in chunks
+// of eight entries, one global atomic per chunk -- the CTAs then finish within 5 instead of 8 us of each
+// other on the config-3 shape, but all of them later: the pass is bound by the SMs' issue rate, an early
+// CTA's slots were being used by its neighbours on the SM all along.)
 // (Letting the last label of a mixed group take what the others left of the group's totals -- one round
 // of masked sums less -- was measured too: +0.6 us on config 2, +2 us on the config-3 shape.  Not kept.)
 // Tables of more than 256 rows (16-bit labels) leave room for two CTAs per SM only (shared memory), so
